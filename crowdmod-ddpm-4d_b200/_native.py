@@ -1,0 +1,130 @@
+"""ctypes binding of libcrowdmod_b200.so (the C ABI declared in include/crowdmod_b200.h).
+
+There is no fallback: if the shared library is missing the import of any compute path raises,
+and every entry point that needs a GPU raises when called without one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrowdmod_b200.so")
+
+CM_MAX_LEVELS = 8
+
+
+class UNetConfig(C.Structure):
+    """struct cm_unet_config (include/crowdmod_b200.h)."""
+
+    _fields_ = [
+        ("in_channels", C.c_int32),
+        ("out_channels", C.c_int32),
+        ("num_res_blocks", C.c_int32),
+        ("base_channels", C.c_int32),
+        ("num_levels", C.c_int32),
+        ("mult", C.c_int32 * CM_MAX_LEVELS),
+        ("attn", C.c_int32 * CM_MAX_LEVELS),
+        ("time_multiple", C.c_int32),
+        ("rows", C.c_int32),
+        ("cols", C.c_int32),
+        ("past_len", C.c_int32),
+        ("future_len", C.c_int32),
+        ("table_steps", C.c_int32),
+        ("weight_terms", C.c_int32),
+    ]
+
+
+class ChainArgs(C.Structure):
+    """struct cm_chain_args (include/crowdmod_b200.h)."""
+
+    _fields_ = [
+        ("past", C.c_void_p),
+        ("x", C.c_void_p),
+        ("n", C.c_int32),
+        ("nsteps", C.c_int32),
+        ("tsteps", C.c_void_p),
+        ("coef", C.c_void_p),
+        ("mode", C.c_int32),
+        ("noise", C.c_void_p),
+        ("seed", C.c_uint64),
+        ("sample_offset", C.c_int64),
+        ("history", C.c_void_p),
+        ("use_graph", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list EVERY function include/crowdmod_b200.h declares
+# (tests/test_abi.py checks the two against each other).
+SIGNATURES = {
+    "cm_version": (C.c_int, []),
+    "cm_last_error": (C.c_char_p, []),
+    "cm_device_error": (C.c_int, []),
+    "cm_unet_create": (C.c_int, [C.POINTER(UNetConfig), C.POINTER(C.c_void_p)]),
+    "cm_unet_destroy": (C.c_int, [C.c_void_p]),
+    "cm_unet_param_count": (C.c_int, [C.c_void_p]),
+    "cm_unet_param_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "cm_unet_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "cm_unet_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cm_unet_reserve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
+    "cm_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_void_p]),
+    "cm_unet_launches_per_forward": (C.c_int, [C.c_void_p]),
+    "cm_unet_flops_per_sample": (C.c_double, [C.c_void_p]),
+    "cm_ddpm_sample": (C.c_int, [C.c_void_p, C.POINTER(ChainArgs), C.c_void_p]),
+    "cm_last_chain_launches": (C.c_int64, [C.c_void_p]),
+    "cm_op_conv3d": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cm_op_gn_silu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "cm_op_attn_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p]),
+    "cm_op_first_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "cm_op_final_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU or PyTorch fallback for the hot path)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().cm_last_error()
+        raise NativeError(f"crowdmod_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,112 @@
+// Library-level C ABI: error reporting, device error flag, op-level entry points used by the
+// unit tests (each wraps one kernel of the hot path; they allocate temporaries and synchronise,
+// the model-level calls in unet.cu do not).
+#include <mutex>
+#include <string>
+
+#include "../../include/crowdmod_b200.h"
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace cm {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* get_error() { return g_err.c_str(); }
+
+static int* g_flag = nullptr;
+int* device_error_flag() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (cudaMalloc(&g_flag, sizeof(int)) == cudaSuccess) cudaMemset(g_flag, 0, sizeof(int));
+    else g_flag = nullptr;
+  });
+  return g_flag;
+}
+
+}  // namespace cm
+
+using namespace cm;
+
+extern "C" {
+
+int cm_version(void) { return 100; }
+const char* cm_last_error(void) { return get_error(); }
+
+int cm_device_error(void) {
+  int* f = device_error_flag();
+  if (!f) return -1;
+  int v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+  cudaMemset(f, 0, sizeof(int));
+  return v;
+}
+
+int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int cin,
+                 const void* extra16, int cin_extra, const float* w, const float* wx,
+                 const float* bias, int cout, int terms, const float* resid, float* out32,
+                 void* out16, int impl, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = kernels_init()) return e;
+  const size_t ktot = conv_packed_k(mode, cin, cin_extra);
+  __half* wp = nullptr;
+  CM_CUDA(cudaMalloc(&wp, (size_t)terms * cout * ktot * sizeof(__half)));
+  int rc = 0;
+  if (mode == 2) rc = pack_upsample_weights(w, wp, cout, cin, terms, st);
+  else rc = pack_conv_weights(w, wx, wp, cout, cin, cin_extra, mode == 3 ? 1 : 27, terms, st);
+  ConvLaunch L;
+  if (!rc) rc = conv_prepare(&L, mode, static_cast<const __half*>(act16), B, D, H, W, cin,
+                             static_cast<const __half*>(extra16), cin_extra, wp, cout, terms);
+  if (!rc) {
+    L.p.bias = bias;
+    L.p.resid = resid;
+    L.p.out32 = out32;
+    L.p.out16 = static_cast<__half*>(out16);
+    if (impl == 0) rc = conv_enqueue(L, st);
+    else rc = conv_ref_enqueue(L.p, static_cast<const __half*>(act16),
+                               static_cast<const __half*>(extra16), wp, B, D, H, W, st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(wp);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
+}
+
+int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, const float* gamma,
+                  const float* beta, int B, int pixels, float eps, int silu, void* out_norm16,
+                  void* out_raw16, void* stream) {
+  GnParams g{};
+  g.src0 = src0; g.c0 = c0; g.src1 = src1; g.c1 = c1;
+  g.gamma = gamma; g.beta = beta; g.B = B; g.pixels = pixels; g.eps = eps; g.silu = silu;
+  g.out_norm = static_cast<__half*>(out_norm16);
+  g.out_raw = static_cast<__half*>(out_raw16);
+  return gn_silu_enqueue(g, static_cast<cudaStream_t>(stream));
+}
+
+int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream) {
+  if (int e = kernels_init()) return e;
+  return attn_core_enqueue(qkv, static_cast<__half*>(ctx16), B, S, C, heads,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int cm_op_first_conv(const float* x, const float* past, const float* w, const float* bias,
+                     float* out, int B, int H, int W, int P, int F, int cin, int cout,
+                     void* stream) {
+  if (int e = kernels_init()) return e;
+  return first_conv_enqueue(x, past, w, bias, out, B, H, W, P, F, cin, cout,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int cm_op_final_conv(const void* act16, const float* w, const float* bias, float* eps_out, int B,
+                     int H, int W, int L, int P, int cin, int cout, void* stream) {
+  if (int e = kernels_init()) return e;
+  FinalParams f{};
+  f.act = static_cast<const __half*>(act16);
+  f.w = w; f.bias = bias; f.B = B; f.H = H; f.W = W; f.L = L; f.P = P; f.cin = cin; f.cout = cout;
+  f.eps_out = eps_out;
+  return final_conv_enqueue(f, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+// Host side of the tcgen05 implicit-GEMM conv: tensor-map construction and launch.
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+
+namespace cm {
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+int g_driver_version = 0;
+
+int load_driver_syms() {
+  if (g_encode_tiled && g_encode_im2col) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  CM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  CM_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not found");
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  fn = nullptr;
+  CM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  CM_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not found");
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  CM_CUDA(cudaDriverGetVersion(&g_driver_version));
+  return 0;
+}
+
+// Activation tensor [B, D, H, W, C] fp16 -> 5-D im2col map, dims ordered (C, W, H, D, N).
+int make_act_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int bk,
+                 int lower_w, int lower_h, int lower_d, int stride) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)D * H * W * C * 2};
+  // For every conv shape used here (k3 p1 s1|s2, 2x2x2 phase taps, 1x1x1) the upper corner
+  // (upper_pad - (k-1)) equals the lower corner (-lower_pad).
+  int lower[3] = {lower_w, lower_h, lower_d};
+  int upper[3] = {lower_w, lower_h, lower_d};
+  cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides,
+                               lower, upper, (cuuint32_t)bk, (cuuint32_t)CONV_BM, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed: %d (B=%d D=%d H=%d W=%d C=%d bk=%d)",
+           (int)r, B, D, H, W, C, bk);
+  // Driver quirk mirrored from CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): for tensors
+  // smaller than 128 KiB, drivers <= 13.1 set a descriptor bit that must be cleared.
+  if (g_driver_version <= 13010) {
+    size_t bytes = (size_t)B * D * H * W * C * 2;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  }
+  return 0;
+}
+
+int make_weight_map(CUtensorMap* map, const __half* base, size_t rows, size_t ktot, int bk, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: %d (rows=%zu k=%zu)", (int)r, rows,
+           ktot);
+  return 0;
+}
+
+template <int BN, int BK>
+int launch_t(const ConvLaunch& L, cudaStream_t st) {
+  conv_umma_kernel<BN, BK><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN, int BK>
+int set_attr_t() {
+  CM_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024));
+  return 0;
+}
+
+}  // namespace
+
+int conv_init() {
+  static bool done = false;
+  if (done) return 0;
+  if (int rc = load_driver_syms()) return rc;
+  if (int rc = set_attr_t<128, 64>()) return rc;
+  if (int rc = set_attr_t<64, 64>()) return rc;
+  if (int rc = set_attr_t<32, 64>()) return rc;
+  if (int rc = set_attr_t<128, 32>()) return rc;
+  if (int rc = set_attr_t<64, 32>()) return rc;
+  if (int rc = set_attr_t<32, 32>()) return rc;
+  done = true;
+  return 0;
+}
+
+size_t conv_packed_k(int mode, int cin, int cin_extra) {
+  switch (mode) {
+    case 0:
+    case 1: return (size_t)27 * cin + cin_extra;
+    case 2: return (size_t)64 * cin;
+    default: return (size_t)cin + cin_extra;
+  }
+}
+
+int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
+                 const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms) {
+  if (int rc = load_driver_syms()) return rc;
+  CM_CHECK(mode >= 0 && mode <= 3, "bad conv mode %d", mode);
+  CM_CHECK(cin % 32 == 0 && cin_extra % 32 == 0, "channels must be multiples of 32 (cin=%d extra=%d)",
+           cin, cin_extra);
+  CM_CHECK(cout % 32 == 0, "cout must be a multiple of 32 (%d)", cout);
+  CM_CHECK(terms == 1 || terms == 2, "terms must be 1 or 2");
+  CM_CHECK(!(mode == 2 && cin_extra), "upsample conv takes no extra source");
+  memset(L, 0, sizeof(*L));
+  ConvParams& p = L->p;
+  const int bk = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
+  const int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
+  L->bk = bk;
+  L->bn = bn;
+
+  int stride = 1, k = 3, od = D, oh = H, ow = W;
+  if (mode == 1) {
+    stride = 2;
+    od = (D - 1) / 2 + 1;
+    oh = (H - 1) / 2 + 1;
+    ow = (W - 1) / 2 + 1;
+  } else if (mode == 2) {
+    k = 2;
+  } else if (mode == 3) {
+    k = 1;
+  }
+  p.nphase = (mode == 2) ? 8 : 1;
+  for (int ph = 0; ph < p.nphase; ++ph) {
+    int lw, lh, ld;
+    if (mode == 2) {
+      lw = (ph & 1) ? 0 : -1;
+      lh = (ph & 2) ? 0 : -1;
+      ld = (ph & 4) ? 0 : -1;
+    } else if (mode == 3) {
+      lw = lh = ld = 0;
+    } else {
+      lw = lh = ld = -1;
+    }
+    p.lower[ph][0] = (signed char)lw;
+    p.lower[ph][1] = (signed char)lh;
+    p.lower[ph][2] = (signed char)ld;
+    if (int rc = make_act_map(&p.amap[ph], act, B, D, H, W, cin, bk, lw, lh, ld, stride)) return rc;
+  }
+  if (cin_extra) {
+    CM_CHECK(extra != nullptr, "extra source pointer missing");
+    if (int rc = make_act_map(&p.xmap, extra, B, od, oh, ow, cin_extra, bk, 0, 0, 0, 1)) return rc;
+  }
+  const size_t ktot = conv_packed_k(mode, cin, cin_extra);
+  if (int rc = make_weight_map(&p.bmap, wpacked, (size_t)terms * cout, ktot, bk, bn)) return rc;
+
+  p.M = B * od * oh * ow;
+  p.od = od;
+  p.oh = oh;
+  p.ow = ow;
+  p.pps = od * oh * ow;
+  p.conv_stride = stride;
+  p.kd = p.kh = p.kw = k;
+  p.cin_main = cin;
+  p.cin_extra = cin_extra;
+  p.kphase = (mode == 2) ? 8 * cin : 0;
+  p.terms = terms;
+  p.cout = cout;
+  p.out_ld = cout;
+  p.scatter = (mode == 2) ? 1 : 0;
+  p.err_flag = device_error_flag();
+
+  const int stage_bytes = CONV_BM * bk * 2 + terms * bn * bk * 2;
+  int stages = 4;
+  while (stages > 2 && (size_t)stages * stage_bytes + 2048 > 200 * 1024) --stages;
+  p.stages = stages;
+  L->smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  L->grid = dim3((p.M + CONV_BM - 1) / CONV_BM, cout / bn, p.nphase);
+  L->flops = 2.0 * p.M * cout * (double)(k * k * k * cin + cin_extra) * p.nphase;
+  return 0;
+}
+
+int conv_enqueue(const ConvLaunch& L, cudaStream_t st) {
+  if (L.bk == 64) {
+    if (L.bn == 128) return launch_t<128, 64>(L, st);
+    if (L.bn == 64) return launch_t<64, 64>(L, st);
+    return launch_t<32, 64>(L, st);
+  } else {
+    if (L.bn == 128) return launch_t<128, 32>(L, st);
+    if (L.bn == 64) return launch_t<64, 32>(L, st);
+    return launch_t<32, 32>(L, st);
+  }
+}
+
+}  // namespace cm

@@ -1,0 +1,99 @@
+// Bandwidth / small-op kernels of the UNet hot path (everything that is not the tcgen05 conv).
+// Each launcher cites the reference op it replaces.
+#pragma once
+#include "common.cuh"
+
+namespace cm {
+
+// ---- weight packing (fp32 torch layouts -> fp16 K-major rows, optional hi+lo split) ----
+// w: [cout][cin][taps] (nn.Conv3d weight flattened; taps = 27 or 1), wx: [cout][cinx] or null.
+// dst: [terms*cout][taps*cin + cinx], column = tap*cin + ci, then 27*cin + cx.
+int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, int cin, int cinx,
+                      int taps, int terms, cudaStream_t st);
+// nearest-x2 + k3 conv folded into 8 phase convs with 2x2x2 combined taps
+// (layers.py:92-94).  dst: [terms*cout][64*cin], column = phase*8*cin + tap8*cin + ci.
+int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms,
+                          cudaStream_t st);
+
+// ---- GroupNorm(8) [+SiLU] [+Dropout3d scale] -> fp16 operand (layers.py:30,41,57,70; :9,14) ----
+struct GnParams {
+  const float* src0;   // fp32 channels-last [B][pixels][c0]
+  const float* src1;   // optional second source (skip concat, unet.py:160), channels c0..c0+c1
+  int c0, c1;
+  const float* gamma;
+  const float* beta;
+  int B, pixels;
+  float eps;
+  int silu;
+  const float* drop_scale;  // [B][C] per-(sample,channel) multiplier or nullptr
+  __half* out_norm;         // [B][pixels][C]
+  __half* out_raw;          // optional raw fp16 copy of the (concatenated) input
+  float* stats;             // optional [B][8][2] (mean, rstd) for backward
+};
+int gn_silu_enqueue(const GnParams& p, cudaStream_t st);
+
+// ---- first conv: 3(+)->base channels straight from the API layout (unet.py:32,138,144) ----
+// x: [B][cin][H][W][F] fp32, past: [B][cin][H][W][P] fp32 (virtual concat along time),
+// w: [cout][cin][3][3][3], out: fp32 channels-last [B][H][W][P+F][cout].
+int first_conv_enqueue(const float* x, const float* past, const float* w, const float* bias,
+                       float* out, int B, int H, int W, int P, int F, int cin, int cout,
+                       cudaStream_t st);
+
+// ---- final conv base->3 fused with the DDPM/DDIM update (unet.py:118-122,165-167; ddpm.py:25-38,262-265) ----
+struct FinalParams {
+  const __half* act;     // fp16 channels-last [B][H][W][L][cin], already GN+SiLU'ed
+  const float* w;        // [cout][cin][27] fp32
+  const float* bias;
+  int B, H, W, L, P;     // L = P + F; only frames l >= P are produced
+  int cin, cout;
+  float* eps_out;        // optional [B][cout][H][W][F]
+  // --- reverse-step update (all optional; x == nullptr -> eps only) ---
+  float* x;              // [B][cout][H][W][F] in/out
+  const float* coef;     // [nsteps][8] per-step coefficients
+  const int* step_dev;   // device step index
+  int mode;              // 0 = DDPM, 1 = DDIM
+  const float* noise;    // [nsteps][B*cout*H*W*F] or nullptr -> Philox
+  unsigned long long seed;
+  long long sample_offset;  // global index of sample 0 of this shard (Philox counter)
+  float* history;        // optional [nsteps+1][B*cout*H*W*F]; slot step+1 written
+};
+int final_conv_enqueue(const FinalParams& p, cudaStream_t st);
+
+// ---- time embedding MLP + every block's dense_1 (embeddings.py:22-34; layers.py:35,62) ----
+struct TembParams {
+  const float* table;    // [T][base] frozen sinusoid table
+  const float* w1; const float* b1;   // [E][base]
+  const float* w2; const float* b2;   // [E][E]
+  const float* const* wd;  // device array [nblocks] of [cout_k][E]
+  const float* const* bd;  // device array [nblocks] of [cout_k]
+  const int* couts;        // device array [nblocks]
+  const int* offs;         // device array [nblocks] column offsets in out
+  int nblocks;
+  int base, E;
+  const long long* t;      // [rows] int64 timesteps, or nullptr -> t = row index
+  int rows;
+  float* out;              // [rows][ld]
+  int ld;
+};
+int temb_enqueue(const TembParams& p, cudaStream_t st);
+
+// ---- attention core softmax(QK^T/sqrt(dh))V per (sample, head) (layers.py:16) ----
+// qkv: fp32 [B*S][3*C] (q | k | v), ctx: fp16 [B*S][C]
+int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int heads,
+                      cudaStream_t st);
+
+// ---- chain bookkeeping: step += 1; t_dev = tsteps[step] ----
+int advance_step_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaStream_t st);
+
+// ---- test-only: scalar restatement of exactly what conv_umma computes (same packed operands) ----
+struct ConvParams;
+int conv_ref_enqueue(const ConvParams& p, const __half* act, const __half* extra,
+                     const __half* wpacked, int B, int D, int H, int W, cudaStream_t st);
+
+// one-time cudaFuncSetAttribute calls (kept out of stream capture)
+int kernels_init();
+int conv_init();
+
+int cast_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t st);
+
+}  // namespace cm

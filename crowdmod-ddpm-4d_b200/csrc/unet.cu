@@ -1,0 +1,774 @@
+// UNet execution plan + reverse-chain driver behind the C ABI (include/crowdmod_b200.h).
+//
+// The plan is a flat op list derived from the same constructor arguments the reference UNet
+// takes (models/backbones/unet.py:11-122) and executed in the order of UNet.forward
+// (unet.py:124-167) / ResnetBlock.forward (layers.py:55-78) / AttentionBlock.forward
+// (layers.py:12-18).  torch.cat calls disappear (GroupNorm reads two sources), match_input is
+// a K-slab of conv_2, residual/time-embedding adds live in conv epilogues, nearest-x2
+// upsampling is folded into 8 phase convolutions, and DDPM.step (ddpm.py:25-38) is the
+// epilogue of the last conv.
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/crowdmod_b200.h"
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace cm {
+
+struct ParamEntry {
+  std::string name;
+  std::vector<int64_t> shape;
+  const float* ptr = nullptr;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct Tens {
+  int level = 0;
+  int C = 0;
+  bool need32 = false, need16 = false;
+  float* p32 = nullptr;
+  __half* p16 = nullptr;
+};
+
+enum OpType { OP_FIRST, OP_GN, OP_CONV, OP_ATTN, OP_FINAL };
+
+struct Op {
+  OpType type;
+  std::string tag;
+  // GN
+  int src0 = -1, src1 = -1, gamma = -1, beta = -1, silu = 0, out_norm = -1, out_raw = -1;
+  // CONV
+  int mode = 0, in = -1, extra = -1, w = -1, wx = -1, bias = -1, bias2 = -1, temb_off = -1,
+      resid = -1, out = -1, cin = 0, cin_extra = 0, cout = 0, in_level = 0;
+  size_t wpack_off = 0;   // element offset into the packed-weight buffer
+  ConvLaunch launch;
+  // ATTN
+  int qkv = -1, ctx = -1, heads = 4;
+};
+
+struct Level {
+  int D, H, W;   // grid rows, grid cols, frames
+  int pps() const { return D * H * W; }
+};
+
+}  // namespace cm
+
+using namespace cm;
+
+struct cm_unet {
+  cm_unet_config cfg;
+  std::vector<ParamEntry> params;
+  std::map<std::string, int> pindex;
+  std::vector<Tens> tens;
+  std::vector<Op> ops;
+  std::vector<Level> levels;
+  // time embedding
+  std::vector<int> temb_dense_w, temb_dense_b, temb_couts, temb_offs;
+  int temb_ld = 0;
+  int p_table = -1, p_w1 = -1, p_b1 = -1, p_w2 = -1, p_b2 = -1;
+  int p_first_w = -1, p_first_b = -1, p_final_w = -1, p_final_b = -1;
+  // device state
+  __half* wpack = nullptr;
+  size_t wpack_elems = 0;
+  float* temb_table = nullptr;          // [table_steps][temb_ld]
+  const float** d_wd = nullptr;
+  const float** d_bd = nullptr;
+  int* d_couts = nullptr;
+  int* d_offs = nullptr;
+  bool packed = false;
+  // workspace (per reserved batch)
+  int reserved_batch = 0;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  float* temb_batch = nullptr;          // [batch][temb_ld]
+  int* d_step = nullptr;                // [0] step index, [1] current timestep
+  int* d_tsteps = nullptr;
+  float* d_coef = nullptr;
+  int chain_cap = 0;
+  // graph cache for the chain
+  cudaGraphExec_t graph_exec = nullptr;
+  cm_chain_args graph_key{};
+  int64_t last_chain_launches = 0;
+  double flops_per_sample = 0.0;
+
+  int add_param(const std::string& name, std::vector<int64_t> shape) {
+    ParamEntry e;
+    e.name = name;
+    e.shape = std::move(shape);
+    params.push_back(e);
+    pindex[name] = (int)params.size() - 1;
+    return (int)params.size() - 1;
+  }
+  int add_tensor(int level, int C) {
+    Tens t;
+    t.level = level;
+    t.C = C;
+    tens.push_back(t);
+    return (int)tens.size() - 1;
+  }
+};
+
+namespace {
+
+// ---- plan construction ---------------------------------------------------------------------
+
+int add_gn(cm_unet* u, const std::string& prefix, int src0, int src1, int silu, bool want_raw,
+           int* out_norm, int* out_raw) {
+  const int C = u->tens[src0].C + (src1 >= 0 ? u->tens[src1].C : 0);
+  Op op;
+  op.type = OP_GN;
+  op.tag = prefix;
+  op.src0 = src0;
+  op.src1 = src1;
+  op.gamma = u->add_param(prefix + ".weight", {C});
+  op.beta = u->add_param(prefix + ".bias", {C});
+  op.silu = silu;
+  u->tens[src0].need32 = true;
+  if (src1 >= 0) u->tens[src1].need32 = true;
+  op.out_norm = u->add_tensor(u->tens[src0].level, C);
+  u->tens[op.out_norm].need16 = true;
+  if (want_raw) {
+    op.out_raw = u->add_tensor(u->tens[src0].level, C);
+    u->tens[op.out_raw].need16 = true;
+  }
+  *out_norm = op.out_norm;
+  if (out_raw) *out_raw = op.out_raw;
+  u->ops.push_back(op);
+  return 0;
+}
+
+// generic conv op; weight/bias params are registered by the caller (ordering of state_dict)
+int add_conv(cm_unet* u, const std::string& tag, int mode, int in, int extra, int w, int wx,
+             int bias, int bias2, int temb_off, int resid, int cout, int out_level) {
+  Op op;
+  op.type = OP_CONV;
+  op.tag = tag;
+  op.mode = mode;
+  op.in = in;
+  op.extra = extra;
+  op.w = w;
+  op.wx = wx;
+  op.bias = bias;
+  op.bias2 = bias2;
+  op.temb_off = temb_off;
+  op.resid = resid;
+  op.cin = u->tens[in].C;
+  op.cin_extra = extra >= 0 ? u->tens[extra].C : 0;
+  op.cout = cout;
+  op.in_level = u->tens[in].level;
+  u->tens[in].need16 = true;
+  if (extra >= 0) u->tens[extra].need16 = true;
+  if (resid >= 0) u->tens[resid].need32 = true;
+  op.out = u->add_tensor(out_level, cout);
+  op.wpack_off = u->wpack_elems;
+  u->wpack_elems += (size_t)u->cfg.weight_terms * cout * conv_packed_k(mode, op.cin, op.cin_extra);
+  u->ops.push_back(op);
+  return op.out;
+}
+
+int add_resblock(cm_unet* u, const std::string& prefix, int src0, int src1, int cout, bool attn) {
+  const int level = u->tens[src0].level;
+  const int cin = u->tens[src0].C + (src1 >= 0 ? u->tens[src1].C : 0);
+  const bool has_match = cin != cout;
+  const int E = u->cfg.base_channels * u->cfg.time_multiple;
+  // state_dict order follows ResnetBlock.__init__ (layers.py:30-52)
+  int a1, xr = -1;
+  add_gn(u, prefix + ".normalize_1", src0, src1, 1, has_match, &a1, &xr);
+  const int w1 = u->add_param(prefix + ".conv_1.weight", {cout, cin, 3, 3, 3});
+  const int b1 = u->add_param(prefix + ".conv_1.bias", {cout});
+  const int dw = u->add_param(prefix + ".dense_1.weight", {cout, E});
+  const int db = u->add_param(prefix + ".dense_1.bias", {cout});
+  const int temb_off = u->temb_ld;
+  u->temb_dense_w.push_back(dw);
+  u->temb_dense_b.push_back(db);
+  u->temb_couts.push_back(cout);
+  u->temb_offs.push_back(temb_off);
+  u->temb_ld += cout;
+  const int h1 = add_conv(u, prefix + ".conv_1", 0, a1, -1, w1, -1, b1, -1, temb_off, -1, cout, level);
+  int a2;
+  add_gn(u, prefix + ".normalize_2", h1, -1, 1, false, &a2, nullptr);
+  const int w2 = u->add_param(prefix + ".conv_2.weight", {cout, cout, 3, 3, 3});
+  const int b2 = u->add_param(prefix + ".conv_2.bias", {cout});
+  int wm = -1, bm = -1;
+  if (has_match) {
+    wm = u->add_param(prefix + ".match_input.weight", {cout, cin, 1, 1, 1});
+    bm = u->add_param(prefix + ".match_input.bias", {cout});
+  }
+  if (!has_match && src1 >= 0) {
+    set_error("identity residual with two sources is impossible");
+    return -1;
+  }
+  int o = add_conv(u, prefix + ".conv_2", 0, a2, has_match ? xr : -1, w2, wm, b2, bm, -1,
+                   has_match ? -1 : src0, cout, level);
+  if (attn) {
+    // AttentionBlock (layers.py:5-18)
+    int a3;
+    add_gn(u, prefix + ".attention.group_norm", o, -1, 0, false, &a3, nullptr);
+    const int wi = u->add_param(prefix + ".attention.mhsa.in_proj_weight", {3 * cout, cout});
+    const int bi = u->add_param(prefix + ".attention.mhsa.in_proj_bias", {3 * cout});
+    const int wo = u->add_param(prefix + ".attention.mhsa.out_proj.weight", {cout, cout});
+    const int bo = u->add_param(prefix + ".attention.mhsa.out_proj.bias", {cout});
+    const int qkv = add_conv(u, prefix + ".attention.in_proj", 3, a3, -1, wi, -1, bi, -1, -1, -1,
+                             3 * cout, level);
+    u->tens[qkv].need32 = true;
+    Op at;
+    at.type = OP_ATTN;
+    at.tag = prefix + ".attention.core";
+    at.qkv = qkv;
+    at.heads = 4;   // layers.py:10
+    at.ctx = u->add_tensor(level, cout);
+    u->tens[at.ctx].need16 = true;
+    u->ops.push_back(at);
+    o = add_conv(u, prefix + ".attention.out_proj", 3, at.ctx, -1, wo, -1, bo, -1, -1, o, cout, level);
+  }
+  return o;
+}
+
+int build_plan(cm_unet* u) {
+  const cm_unet_config& c = u->cfg;
+  CM_CHECK(c.num_levels >= 1 && c.num_levels <= CM_MAX_LEVELS, "num_levels out of range");
+  CM_CHECK(c.base_channels % 32 == 0 && c.base_channels > 0, "base_channels must be a multiple of 32");
+  CM_CHECK(c.in_channels >= 1 && c.in_channels <= 4 && c.out_channels >= 1 && c.out_channels <= 4,
+           "in/out channels must be in 1..4");
+  CM_CHECK(c.weight_terms == 1 || c.weight_terms == 2, "weight_terms must be 1 or 2");
+  CM_CHECK(c.num_res_blocks >= 1, "num_res_blocks must be >= 1");
+  const int div = 1 << (c.num_levels - 1);
+  const int L = c.past_len + c.future_len;
+  CM_CHECK(c.rows % div == 0 && c.cols % div == 0 && L % div == 0,
+           "rows/cols/(past+future) must be divisible by 2^(levels-1)=%d (skip concat, unet.py:160)", div);
+  u->levels.resize(c.num_levels);
+  for (int l = 0; l < c.num_levels; ++l) u->levels[l] = {c.rows >> l, c.cols >> l, L >> l};
+
+  const int base = c.base_channels, E = base * c.time_multiple;
+  // state_dict order: time_embeddings, first, encoder, bottleneck, decoder, final (unet.py:27-122)
+  u->p_table = u->add_param("time_embeddings.time_blocks.0.weight", {c.table_steps, base});
+  u->p_w1 = u->add_param("time_embeddings.time_blocks.1.weight", {E, base});
+  u->p_b1 = u->add_param("time_embeddings.time_blocks.1.bias", {E});
+  u->p_w2 = u->add_param("time_embeddings.time_blocks.3.weight", {E, E});
+  u->p_b2 = u->add_param("time_embeddings.time_blocks.3.bias", {E});
+  u->p_first_w = u->add_param("first.weight", {base, c.in_channels, 3, 3, 3});
+  u->p_first_b = u->add_param("first.bias", {base});
+
+  Op first;
+  first.type = OP_FIRST;
+  first.tag = "first";
+  first.out = u->add_tensor(0, base);
+  u->tens[first.out].need32 = true;
+  u->ops.push_back(first);
+
+  int cur = first.out;
+  std::vector<int> skips{cur};
+  int in_ch = base, idx = 0;
+  for (int level = 0; level < c.num_levels; ++level) {
+    const int out_ch = base * c.mult[level];
+    for (int r = 0; r < c.num_res_blocks; ++r) {
+      cur = add_resblock(u, "encoder_blocks." + std::to_string(idx++), cur, -1, out_ch, c.attn[level] != 0);
+      if (cur < 0) return 3;
+      in_ch = out_ch;
+      skips.push_back(cur);
+    }
+    if (level != c.num_levels - 1) {
+      const std::string p = "encoder_blocks." + std::to_string(idx++) + ".downsample";
+      const int w = u->add_param(p + ".weight", {in_ch, in_ch, 3, 3, 3});
+      const int b = u->add_param(p + ".bias", {in_ch});
+      cur = add_conv(u, p, 1, cur, -1, w, -1, b, -1, -1, -1, in_ch, level + 1);
+      skips.push_back(cur);
+    }
+  }
+  cur = add_resblock(u, "bottleneck_blocks.0", cur, -1, in_ch, true);
+  cur = add_resblock(u, "bottleneck_blocks.1", cur, -1, in_ch, false);
+  idx = 0;
+  for (int level = c.num_levels - 1; level >= 0; --level) {
+    const int out_ch = base * c.mult[level];
+    for (int r = 0; r < c.num_res_blocks + 1; ++r) {
+      const int skip = skips.back();
+      skips.pop_back();
+      cur = add_resblock(u, "decoder_blocks." + std::to_string(idx++), cur, skip, out_ch,
+                         c.attn[level] != 0);
+      if (cur < 0) return 3;
+      in_ch = out_ch;
+    }
+    if (level != 0) {
+      const std::string p = "decoder_blocks." + std::to_string(idx++) + ".upsample.1";
+      const int w = u->add_param(p + ".weight", {in_ch, in_ch, 3, 3, 3});
+      const int b = u->add_param(p + ".bias", {in_ch});
+      cur = add_conv(u, p, 2, cur, -1, w, -1, b, -1, -1, -1, in_ch, level - 1);
+    }
+  }
+  int afin;
+  add_gn(u, "final.0", cur, -1, 1, false, &afin, nullptr);
+  u->p_final_w = u->add_param("final.2.weight", {c.out_channels, in_ch, 3, 3, 3});
+  u->p_final_b = u->add_param("final.2.bias", {c.out_channels});
+  Op fin;
+  fin.type = OP_FINAL;
+  fin.tag = "final.2";
+  fin.in = afin;
+  fin.cin = in_ch;
+  u->ops.push_back(fin);
+
+  // algorithmic FLOPs per sample of the reference graph (dense formulation: 27-tap upsample
+  // convs, separate 1x1 match_input, attention), SURVEY.md §8(d)
+  double fl = 0.0;
+  {
+    const Level& l0 = u->levels[0];
+    fl += 2.0 * l0.pps() * base * 27.0 * c.in_channels;
+    fl += 2.0 * l0.pps() * c.out_channels * 27.0 * in_ch;
+  }
+  for (const Op& op : u->ops) {
+    if (op.type == OP_CONV) {
+      const Level& lo = u->levels[u->tens[op.out].level];
+      const double taps = (op.mode == 3) ? 1.0 : 27.0;
+      fl += 2.0 * lo.pps() * op.cout * (taps * op.cin + op.cin_extra);
+    } else if (op.type == OP_ATTN) {
+      const Level& lv = u->levels[u->tens[op.qkv].level];
+      const double S = lv.pps(), Ce = u->tens[op.ctx].C;
+      fl += 4.0 * S * S * Ce;
+    }
+  }
+  u->flops_per_sample = fl;
+  return 0;
+}
+
+int check_params_bound(cm_unet* u) {
+  for (auto& p : u->params)
+    CM_CHECK(p.ptr != nullptr, "parameter '%s' not bound (cm_unet_set_param)", p.name.c_str());
+  return 0;
+}
+
+// ---- workspace ---------------------------------------------------------------------------
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int reserve(cm_unet* u, int batch) {
+  if (batch <= u->reserved_batch) return 0;
+  if (u->graph_exec) {
+    cudaGraphExecDestroy(u->graph_exec);
+    u->graph_exec = nullptr;
+  }
+  if (u->arena) CM_CUDA(cudaFree(u->arena));
+  u->arena = nullptr;
+  size_t off = 0;
+  std::vector<size_t> o32(u->tens.size(), 0), o16(u->tens.size(), 0);
+  for (size_t i = 0; i < u->tens.size(); ++i) {
+    Tens& t = u->tens[i];
+    const size_t n = (size_t)batch * u->levels[t.level].pps() * t.C;
+    if (t.need32) { o32[i] = off; off = align_up(off + n * 4, 1024); }
+    if (t.need16) { o16[i] = off; off = align_up(off + n * 2, 1024); }
+  }
+  const size_t temb_off = off;
+  off = align_up(off + (size_t)batch * u->temb_ld * 4, 1024);
+  CM_CUDA(cudaMalloc(&u->arena, off));
+  CM_CUDA(cudaMemset(u->arena, 0, off));
+  u->arena_bytes = off;
+  for (size_t i = 0; i < u->tens.size(); ++i) {
+    Tens& t = u->tens[i];
+    t.p32 = t.need32 ? reinterpret_cast<float*>(u->arena + o32[i]) : nullptr;
+    t.p16 = t.need16 ? reinterpret_cast<__half*>(u->arena + o16[i]) : nullptr;
+  }
+  u->temb_batch = reinterpret_cast<float*>(u->arena + temb_off);
+  if (!u->d_step) CM_CUDA(cudaMalloc(&u->d_step, 2 * sizeof(int)));
+  u->reserved_batch = batch;
+  return 0;
+}
+
+// conv launches depend on the live batch (grid, tensor-map extents): (re)built per call batch
+int prepare_convs(cm_unet* u, int batch) {
+  for (Op& op : u->ops) {
+    if (op.type != OP_CONV) continue;
+    const Level& li = u->levels[op.in_level];
+    const Tens& tin = u->tens[op.in];
+    const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
+    if (int rc = conv_prepare(&op.launch, op.mode, tin.p16, batch, li.D, li.H, li.W, op.cin, extra,
+                              op.cin_extra, u->wpack + op.wpack_off, op.cout, u->cfg.weight_terms))
+      return rc;
+    ConvParams& p = op.launch.p;
+    p.bias = op.bias >= 0 ? u->params[op.bias].ptr : nullptr;
+    p.bias2 = op.bias2 >= 0 ? u->params[op.bias2].ptr : nullptr;
+    p.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
+    p.out32 = u->tens[op.out].p32;
+    p.out16 = u->tens[op.out].p16;
+    CM_CHECK(p.out32 || p.out16, "conv '%s' has no consumer", op.tag.c_str());
+  }
+  return 0;
+}
+
+int live_batch_of(const cm_unet* u) {
+  for (const Op& op : u->ops)
+    if (op.type == OP_CONV) return op.launch.p.pps ? op.launch.p.M / op.launch.p.pps : 0;
+  return 0;
+}
+
+// ---- execution -----------------------------------------------------------------------------
+
+struct RunCtx {
+  int batch;
+  const float* future;
+  const float* past;
+  // time embedding source
+  const float* temb;     // table or per-batch buffer
+  const int* t_dev;      // device timestep (table mode) or nullptr
+  int temb_bstride;
+  FinalParams fin;       // eps_out / update parameters (act, w, geometry filled here)
+};
+
+int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches) {
+  const cm_unet_config& c = u->cfg;
+  for (Op& op : u->ops) {
+    switch (op.type) {
+      case OP_FIRST: {
+        const Level& l0 = u->levels[0];
+        if (int e = first_conv_enqueue(rc.future, rc.past, u->params[u->p_first_w].ptr,
+                                       u->params[u->p_first_b].ptr, u->tens[op.out].p32, rc.batch,
+                                       l0.D, l0.H, c.past_len, c.future_len, c.in_channels,
+                                       c.base_channels, st))
+          return e;
+      } break;
+      case OP_GN: {
+        GnParams g{};
+        g.src0 = u->tens[op.src0].p32;
+        g.c0 = u->tens[op.src0].C;
+        g.src1 = op.src1 >= 0 ? u->tens[op.src1].p32 : nullptr;
+        g.c1 = op.src1 >= 0 ? u->tens[op.src1].C : 0;
+        g.gamma = u->params[op.gamma].ptr;
+        g.beta = u->params[op.beta].ptr;
+        g.B = rc.batch;
+        g.pixels = u->levels[u->tens[op.src0].level].pps();
+        g.eps = 1e-5f;   // nn.GroupNorm default (layers.py:9,30,41)
+        g.silu = op.silu;
+        g.out_norm = u->tens[op.out_norm].p16;
+        g.out_raw = op.out_raw >= 0 ? u->tens[op.out_raw].p16 : nullptr;
+        if (int e = gn_silu_enqueue(g, st)) return e;
+      } break;
+      case OP_CONV: {
+        ConvLaunch L = op.launch;
+        if (op.temb_off >= 0) {
+          L.p.temb = rc.temb + op.temb_off;
+          L.p.t_dev = rc.t_dev;
+          L.p.temb_ld = u->temb_ld;
+          L.p.temb_bstride = rc.temb_bstride;
+        }
+        if (int e = conv_enqueue(L, st)) return e;
+      } break;
+      case OP_ATTN: {
+        const Tens& q = u->tens[op.qkv];
+        const int S = u->levels[q.level].pps();
+        if (int e = attn_core_enqueue(q.p32, u->tens[op.ctx].p16, rc.batch, S, u->tens[op.ctx].C,
+                                      op.heads, st))
+          return e;
+      } break;
+      case OP_FINAL: {
+        const Level& l0 = u->levels[0];
+        FinalParams f = rc.fin;
+        f.act = u->tens[op.in].p16;
+        f.w = u->params[u->p_final_w].ptr;
+        f.bias = u->params[u->p_final_b].ptr;
+        f.B = rc.batch;
+        f.H = l0.D;
+        f.W = l0.H;
+        f.L = l0.W;
+        f.P = c.past_len;
+        f.cin = op.cin;
+        f.cout = c.out_channels;
+        if (int e = final_conv_enqueue(f, st)) return e;
+      } break;
+    }
+    if (launches) ++*launches;
+  }
+  return 0;
+}
+
+int ensure_ready(cm_unet* u, int batch) {
+  CM_CHECK(batch >= 1, "batch must be >= 1");
+  if (int e = kernels_init()) return e;
+  CM_CHECK(u->packed, "cm_unet_pack has not been called since parameters were bound");
+  if (int e = reserve(u, batch)) return e;
+  if (live_batch_of(u) != batch) {
+    if (u->graph_exec) {
+      cudaGraphExecDestroy(u->graph_exec);
+      u->graph_exec = nullptr;
+    }
+    if (int e = prepare_convs(u, batch)) return e;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int cm_unet_create(const cm_unet_config* cfg, cm_unet** out) {
+  CM_CHECK(cfg && out, "null argument");
+  auto u = std::make_unique<cm_unet>();
+  u->cfg = *cfg;
+  if (u->cfg.table_steps <= 0) u->cfg.table_steps = 1000;
+  if (u->cfg.weight_terms <= 0) u->cfg.weight_terms = 2;
+  if (int e = build_plan(u.get())) return e;
+  *out = u.release();
+  return 0;
+}
+
+int cm_unet_destroy(cm_unet* u) {
+  if (!u) return 0;
+  if (u->graph_exec) cudaGraphExecDestroy(u->graph_exec);
+  cudaFree(u->arena);
+  cudaFree(u->wpack);
+  cudaFree(u->temb_table);
+  cudaFree(u->d_wd);
+  cudaFree(u->d_bd);
+  cudaFree(u->d_couts);
+  cudaFree(u->d_offs);
+  cudaFree(u->d_step);
+  cudaFree(u->d_tsteps);
+  cudaFree(u->d_coef);
+  delete u;
+  return 0;
+}
+
+int cm_unet_param_count(const cm_unet* u) { return u ? (int)u->params.size() : -1; }
+
+int cm_unet_param_info(const cm_unet* u, int idx, char* name, int name_cap, int64_t* shape5,
+                       int* ndim) {
+  CM_CHECK(u && idx >= 0 && idx < (int)u->params.size(), "bad param index %d", idx);
+  const ParamEntry& p = u->params[idx];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", p.name.c_str());
+  if (ndim) *ndim = (int)p.shape.size();
+  if (shape5)
+    for (size_t i = 0; i < p.shape.size() && i < 5; ++i) shape5[i] = p.shape[i];
+  return 0;
+}
+
+int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_t numel) {
+  CM_CHECK(u && name, "null argument");
+  auto it = u->pindex.find(name);
+  CM_CHECK(it != u->pindex.end(), "unknown parameter '%s'", name);
+  ParamEntry& p = u->params[it->second];
+  CM_CHECK(p.numel() == numel, "parameter '%s': expected %lld elements, got %lld", name,
+           (long long)p.numel(), (long long)numel);
+  CM_CHECK((reinterpret_cast<uintptr_t>(dev_ptr) & 15) == 0, "parameter '%s' must be 16-byte aligned", name);
+  if (p.ptr != dev_ptr) {
+    p.ptr = dev_ptr;
+    u->packed = false;
+    if (u->graph_exec) {   // baked pointers are stale
+      cudaGraphExecDestroy(u->graph_exec);
+      u->graph_exec = nullptr;
+    }
+    for (Op& op : u->ops)
+      if (op.type == OP_CONV) op.launch.p.M = 0;   // force prepare_convs (bias pointers)
+  }
+  return 0;
+}
+
+int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
+  CM_CHECK(u, "null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = check_params_bound(u)) return e;
+  const int terms = u->cfg.weight_terms;
+  if (!u->wpack) CM_CUDA(cudaMalloc(&u->wpack, u->wpack_elems * sizeof(__half)));
+  for (Op& op : u->ops) {
+    if (op.type != OP_CONV) continue;
+    __half* dst = u->wpack + op.wpack_off;
+    const float* w = u->params[op.w].ptr;
+    if (op.mode == 2) {
+      if (int e = pack_upsample_weights(w, dst, op.cout, op.cin, terms, st)) return e;
+    } else {
+      const float* wx = op.wx >= 0 ? u->params[op.wx].ptr : nullptr;
+      if (int e = pack_conv_weights(w, wx, dst, op.cout, op.cin, op.cin_extra, op.mode == 3 ? 1 : 27,
+                                    terms, st))
+        return e;
+    }
+  }
+  const int nb = (int)u->temb_couts.size();
+  if (!u->d_wd) {
+    CM_CUDA(cudaMalloc(&u->d_wd, nb * sizeof(float*)));
+    CM_CUDA(cudaMalloc(&u->d_bd, nb * sizeof(float*)));
+    CM_CUDA(cudaMalloc(&u->d_couts, nb * sizeof(int)));
+    CM_CUDA(cudaMalloc(&u->d_offs, nb * sizeof(int)));
+    CM_CUDA(cudaMalloc(&u->temb_table, (size_t)u->cfg.table_steps * u->temb_ld * sizeof(float)));
+  }
+  {
+    std::vector<const float*> wd(nb), bd(nb);
+    for (int k = 0; k < nb; ++k) {
+      wd[k] = u->params[u->temb_dense_w[k]].ptr;
+      bd[k] = u->params[u->temb_dense_b[k]].ptr;
+    }
+    // pageable host sources: these copies are synchronous w.r.t. the host buffers
+    CM_CUDA(cudaMemcpyAsync(u->d_wd, wd.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(u->d_bd, bd.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(u->d_couts, u->temb_couts.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(u->d_offs, u->temb_offs.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+  }
+  if (build_time_table) {
+    TembParams t{};
+    t.table = u->params[u->p_table].ptr;
+    t.w1 = u->params[u->p_w1].ptr;
+    t.b1 = u->params[u->p_b1].ptr;
+    t.w2 = u->params[u->p_w2].ptr;
+    t.b2 = u->params[u->p_b2].ptr;
+    t.wd = u->d_wd;
+    t.bd = u->d_bd;
+    t.couts = u->d_couts;
+    t.offs = u->d_offs;
+    t.nblocks = nb;
+    t.base = u->cfg.base_channels;
+    t.E = u->cfg.base_channels * u->cfg.time_multiple;
+    t.t = nullptr;
+    t.rows = u->cfg.table_steps;
+    t.out = u->temb_table;
+    t.ld = u->temb_ld;
+    if (int e = temb_enqueue(t, st)) return e;
+  }
+  u->packed = true;
+  return 0;
+}
+
+int cm_unet_reserve(cm_unet* u, int batch, int64_t* bytes) {
+  CM_CHECK(u, "null handle");
+  if (int e = reserve(u, batch)) return e;
+  if (bytes) *bytes = (int64_t)u->arena_bytes;
+  return 0;
+}
+
+int cm_unet_launches_per_forward(const cm_unet* u) { return u ? (int)u->ops.size() + 1 : -1; }
+double cm_unet_flops_per_sample(const cm_unet* u) { return u ? u->flops_per_sample : 0.0; }
+int64_t cm_last_chain_launches(const cm_unet* u) { return u ? u->last_chain_launches : -1; }
+
+int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
+                    float* eps_out, int batch, void* stream) {
+  CM_CHECK(u && future && t && past && eps_out, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = ensure_ready(u, batch)) return e;
+  // per-sample time embedding projections (t may differ per sample: ddpm.py:113)
+  TembParams tp{};
+  tp.table = u->params[u->p_table].ptr;
+  tp.w1 = u->params[u->p_w1].ptr;
+  tp.b1 = u->params[u->p_b1].ptr;
+  tp.w2 = u->params[u->p_w2].ptr;
+  tp.b2 = u->params[u->p_b2].ptr;
+  tp.wd = u->d_wd;
+  tp.bd = u->d_bd;
+  tp.couts = u->d_couts;
+  tp.offs = u->d_offs;
+  tp.nblocks = (int)u->temb_couts.size();
+  tp.base = u->cfg.base_channels;
+  tp.E = u->cfg.base_channels * u->cfg.time_multiple;
+  tp.t = reinterpret_cast<const long long*>(t);
+  tp.rows = batch;
+  tp.out = u->temb_batch;
+  tp.ld = u->temb_ld;
+  if (int e = temb_enqueue(tp, st)) return e;
+  RunCtx rc{};
+  rc.batch = batch;
+  rc.future = future;
+  rc.past = past;
+  rc.temb = u->temb_batch;
+  rc.t_dev = nullptr;
+  rc.temb_bstride = u->temb_ld;
+  rc.fin = FinalParams{};
+  rc.fin.eps_out = eps_out;
+  return run_ops(u, rc, st, nullptr);
+}
+
+int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
+  CM_CHECK(u && a && a->past && a->x && a->tsteps && a->coef, "null argument");
+  CM_CHECK(a->nsteps >= 1 && a->n >= 1, "nsteps and n must be >= 1");
+  CM_CHECK(a->mode == 0 || a->mode == 1, "mode must be 0 (DDPM) or 1 (DDIM)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = ensure_ready(u, a->n)) return e;
+  for (int i = 0; i < a->nsteps; ++i)
+    CM_CHECK(a->tsteps[i] >= 0 && a->tsteps[i] < u->cfg.table_steps, "tsteps[%d]=%d out of range", i,
+             a->tsteps[i]);
+  if (a->nsteps > u->chain_cap) {
+    cudaFree(u->d_tsteps);
+    cudaFree(u->d_coef);
+    CM_CUDA(cudaMalloc(&u->d_tsteps, a->nsteps * sizeof(int)));
+    CM_CUDA(cudaMalloc(&u->d_coef, (size_t)a->nsteps * 8 * sizeof(float)));
+    u->chain_cap = a->nsteps;
+    if (u->graph_exec) {
+      cudaGraphExecDestroy(u->graph_exec);
+      u->graph_exec = nullptr;
+    }
+  }
+  // schedule tables + step counter (host -> device, synchronous w.r.t. the host arrays)
+  CM_CUDA(cudaMemcpyAsync(u->d_tsteps, a->tsteps, a->nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+  CM_CUDA(cudaMemcpyAsync(u->d_coef, a->coef, (size_t)a->nsteps * 8 * sizeof(float),
+                          cudaMemcpyHostToDevice, st));
+  const int init[2] = {0, a->tsteps[0]};
+  CM_CUDA(cudaMemcpyAsync(u->d_step, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  CM_CUDA(cudaStreamSynchronize(st));
+
+  RunCtx rc{};
+  rc.batch = a->n;
+  rc.future = a->x;
+  rc.past = a->past;
+  rc.temb = u->temb_table;
+  rc.t_dev = u->d_step + 1;
+  rc.temb_bstride = 0;
+  rc.fin = FinalParams{};
+  rc.fin.x = a->x;
+  rc.fin.coef = u->d_coef;
+  rc.fin.step_dev = u->d_step;
+  rc.fin.mode = a->mode;
+  rc.fin.noise = a->noise;
+  rc.fin.seed = a->seed;
+  rc.fin.sample_offset = a->sample_offset;
+  rc.fin.history = a->history;
+
+  u->last_chain_launches = 0;
+  if (!a->use_graph) {
+    for (int i = 0; i < a->nsteps; ++i) {
+      if (int e = run_ops(u, rc, st, &u->last_chain_launches)) return e;
+      if (int e = advance_step_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, a->nsteps, st)) return e;
+      ++u->last_chain_launches;
+    }
+    return 0;
+  }
+  // One denoiser step (+ update + step advance) captured once; the graph reads the step index
+  // from device memory, so the same executable graph is replayed for every step.
+  const cm_chain_args& k = u->graph_key;
+  const bool reuse = u->graph_exec && k.past == a->past && k.x == a->x && k.n == a->n &&
+                     k.mode == a->mode && k.noise == a->noise && k.seed == a->seed &&
+                     k.sample_offset == a->sample_offset && k.history == a->history &&
+                     k.nsteps == a->nsteps;
+  int64_t per_step = 0;
+  if (!reuse) {
+    if (u->graph_exec) {
+      cudaGraphExecDestroy(u->graph_exec);
+      u->graph_exec = nullptr;
+    }
+    cudaStream_t cs;
+    CM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int e = run_ops(u, rc, cs, &per_step);
+    if (!e) e = advance_step_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, a->nsteps, cs);
+    ++per_step;
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cs, &g);
+    cudaStreamDestroy(cs);
+    if (e) {
+      if (g) cudaGraphDestroy(g);
+      return e;
+    }
+    CM_CUDA(ce);
+    CM_CUDA(cudaGraphInstantiate(&u->graph_exec, g, 0));
+    cudaGraphDestroy(g);
+    u->graph_key = *a;
+  } else {
+    per_step = (int64_t)u->ops.size() + 1;
+  }
+  for (int i = 0; i < a->nsteps; ++i) CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
+  u->last_chain_launches = per_step * a->nsteps;
+  return 0;
+}
+
+}  // extern "C"

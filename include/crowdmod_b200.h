@@ -1,0 +1,123 @@
+/*
+ * crowdmod_b200.h — C ABI of the B200-native (sm_100a) hot path of marcemq/crowdmod-ddpm-4D.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); these entry points are what a
+ * binding of its hot path consumes.  Each one names the reference interface it replaces
+ * (paths relative to the reference repo root).  Plain pointers and sizes only: no torch types.
+ * All device pointers are caller-owned; every call is stream-ordered on `stream` (a
+ * cudaStream_t passed as void*) and never synchronises unless stated.
+ *
+ * Return value: 0 = ok, non-zero = error; cm_last_error() returns the message.
+ *
+ * Tensor conventions (reference utils/dataset.py:48-53, models/backbones/unet.py:133-138):
+ *   API tensors   : fp32, contiguous, [B, C, H(rows), W(cols), L(time)], time fastest.
+ *   internal      : channels-last [B, H, W, L, C]; fp32 residual stream, fp16 MMA operands.
+ */
+#ifndef CROWDMOD_B200_H
+#define CROWDMOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_MAX_LEVELS 8
+#if defined(__GNUC__)
+#define CM_API __attribute__((visibility("default")))
+#else
+#define CM_API
+#endif
+
+/* Mirrors the constructor of models/backbones/unet.py:11-25 plus the tensor geometry the
+ * reference takes from cfg.MACROPROPS / cfg.DATASET (models/diffusion/ddpm.py:211). */
+typedef struct cm_unet_config {
+  int32_t in_channels;      /* UNet(input_channels)  = mprops_count               */
+  int32_t out_channels;     /* UNet(output_channels)                              */
+  int32_t num_res_blocks;   /* cfg ... UNET.NUM_RES_BLOCKS                        */
+  int32_t base_channels;    /* BASE_CH (multiple of 32)                           */
+  int32_t num_levels;       /* len(BASE_CH_MULT)                                  */
+  int32_t mult[CM_MAX_LEVELS];   /* BASE_CH_MULT                                  */
+  int32_t attn[CM_MAX_LEVELS];   /* APPLY_ATTENTION[level] (extra entries ignored)*/
+  int32_t time_multiple;    /* TIME_EMB_MULT                                      */
+  int32_t rows, cols;       /* MACROPROPS.ROWS / COLS                             */
+  int32_t past_len, future_len;  /* DATASET.PAST_LEN / FUTURE_LEN                 */
+  int32_t table_steps;      /* rows of the sinusoid table (1000, embeddings.py:7) */
+  int32_t weight_terms;     /* 1: fp16 weights, 2: fp16 hi+lo split weights       */
+} cm_unet_config;
+
+typedef struct cm_unet cm_unet;   /* opaque */
+
+/* ---- library ---- */
+CM_API int cm_version(void);
+CM_API const char* cm_last_error(void);
+/* Reads and clears the device-side protocol-error flag (0 = none).  Synchronises. */
+CM_API int cm_device_error(void);
+
+/* ---- backbone: replaces UNet.__init__/state_dict/forward (unet.py:11-167) ---- */
+CM_API int cm_unet_create(const cm_unet_config* cfg, cm_unet** out);
+CM_API int cm_unet_destroy(cm_unet* u);
+/* state_dict mirror: number of entries, and entry i's name / shape (ndim <= 5). */
+CM_API int cm_unet_param_count(const cm_unet* u);
+CM_API int cm_unet_param_info(const cm_unet* u, int idx, char* name, int name_cap, int64_t* shape5,
+                       int* ndim);
+/* Bind the fp32 device tensor of state_dict entry `name` (not copied: must stay alive). */
+CM_API int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_t numel);
+/* Re-derive the kernel-layout caches (fp16 packed weights, time-embedding projection table)
+ * from the bound fp32 parameters.  Call after load_state_dict / optimizer.step. */
+CM_API int cm_unet_pack(cm_unet* u, int build_time_table, void* stream);
+/* Size internal workspaces + TMA descriptors for batches up to `batch` (allocates; not
+ * capturable).  Returns bytes via *bytes if non-NULL. */
+CM_API int cm_unet_reserve(cm_unet* u, int batch, int64_t* bytes);
+/* eps = UNet.forward(future[B,C,H,W,F], t[B] int64, past[B,C,H,W,P]) (unet.py:124-167), eval mode. */
+CM_API int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
+                    float* eps_out, int batch, void* stream);
+/* Number of kernel launches one forward enqueues / algorithmic conv+attention FLOPs per sample. */
+CM_API int cm_unet_launches_per_forward(const cm_unet* u);
+CM_API double cm_unet_flops_per_sample(const cm_unet* u);
+
+/* ---- reverse chain: replaces DDPM_model._generate_ddpm/_generate_ddim (ddpm.py:206-282)
+ *      with DDPM.step (ddpm.py:25-38) fused into the last conv's epilogue ---- */
+typedef struct cm_chain_args {
+  const float* past;        /* [n,C,H,W,P] device                                   */
+  float* x;                 /* [n,C,H,W,F] device; in: x_T, out: x_0                */
+  int32_t n;                /* samples in this shard                                */
+  int32_t nsteps;           /* denoiser evaluations                                 */
+  const int32_t* tsteps;    /* HOST [nsteps] timestep fed to the denoiser at step i */
+  const float* coef;        /* HOST [nsteps][8] per-step update coefficients:
+                               mode 0 (DDPM): {1/sqrt(alpha_t), beta_t/sqrt(1-abar_t), sqrt(beta_t)|0, g, ...}
+                               mode 1 (DDIM): {sqrt(1-abar_t), sqrt(abar_t), sqrt(abar_prev), dir, sigma, g, ...}
+                               g = lambda*sigma for Sparsity guidance, else 0       */
+  int32_t mode;             /* 0 DDPM, 1 DDIM                                       */
+  const float* noise;       /* device [nsteps][n*C*H*W*F] injected z, or NULL -> Philox(seed) */
+  uint64_t seed;
+  int64_t sample_offset;    /* global index of sample 0 (shard-invariant Philox)    */
+  float* history;           /* optional device [nsteps+1][n*C*H*W*F] (slot 0 = x_T by caller) */
+  int32_t use_graph;        /* 1: capture one step as a CUDA graph and replay it    */
+} cm_chain_args;
+CM_API int cm_ddpm_sample(cm_unet* u, const cm_chain_args* args, void* stream);
+/* kernels enqueued by the last cm_ddpm_sample call (for bench accounting) */
+CM_API int64_t cm_last_chain_launches(const cm_unet* u);
+
+/* ---- op-level entry points (unit tests / layer parity; allocate temporaries, synchronise) ---- */
+/* mode: 0 k3 s1 p1, 1 k3 s2 p1, 2 nearest-x2 + k3 p1, 3 1x1x1.  act16: fp16 channels-last
+ * [B,D,H,W,cin]; w: fp32 [cout,cin,taps]; wx: optional fp32 [cout,cin_extra] 1x1 slab over
+ * extra16 [B,od,oh,ow,cin_extra].  impl: 0 tcgen05 kernel, 1 scalar restatement (test only). */
+CM_API int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int cin,
+                 const void* extra16, int cin_extra, const float* w, const float* wx,
+                 const float* bias, int cout, int terms, const float* resid, float* out32,
+                 void* out16, int impl, void* stream);
+CM_API int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, const float* gamma,
+                  const float* beta, int B, int pixels, float eps, int silu, void* out_norm16,
+                  void* out_raw16, void* stream);
+CM_API int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream);
+CM_API int cm_op_first_conv(const float* x, const float* past, const float* w, const float* bias,
+                     float* out, int B, int H, int W, int P, int F, int cin, int cout,
+                     void* stream);
+CM_API int cm_op_final_conv(const void* act16, const float* w, const float* bias, float* eps_out, int B,
+                     int H, int W, int L, int P, int cin, int cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWDMOD_B200_H */

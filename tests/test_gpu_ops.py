@@ -1,0 +1,209 @@
+"""Kernel-level parity (GPU): every hand-written kernel of the hot path, called through the
+C ABI (cm_op_*), against the PyTorch fp32 op it replaces (TF32 disabled).
+
+Tolerances: the tcgen05 conv takes fp16 operands; with `terms=2` (hi+lo split weights) the only
+rounding left is fp32 accumulation order (rel-L2 <= 2e-5 against F.conv3d on the same
+fp16-rounded activations); with `terms=1` weight rounding adds ~3e-4 (bound 1e-3).  Against the
+scalar restatement of the same packed operands (`impl=1`) it must agree to 1e-5.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import crowdmod_ddpm_4d_b200._native as n
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n.lib()
+    return n
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def describe_mismatch(got, ref, tile=128):
+    """Diagnostics that localise a wrong tile / column of the implicit GEMM."""
+    g = got.reshape(-1, got.shape[-1]).double()
+    r = ref.reshape(-1, ref.shape[-1]).double()
+    err = (g - r).abs()
+    rows = err.amax(dim=1)
+    cols = err.amax(dim=0)
+    nt = (rows.numel() + tile - 1) // tile
+    tiles = [rows[i * tile:(i + 1) * tile].max().item() for i in range(min(nt, 12))]
+    return (f"max|err|={err.max().item():.3e} ref_rms={r.pow(2).mean().sqrt().item():.3e} "
+            f"first tiles max err={['%.2e' % t for t in tiles]} "
+            f"col err (first 16)={['%.1e' % c for c in cols[:16].tolist()]} "
+            f"got[0,:4]={g[0,:4].tolist()} ref[0,:4]={r[0,:4].tolist()}")
+
+
+def torch_conv(mode, act16, extra16, w, wx, bias, resid):
+    x = act16.float().permute(0, 4, 1, 2, 3).contiguous()
+    if mode == 0:
+        y = F.conv3d(x, w, None, stride=1, padding=1)
+    elif mode == 1:
+        y = F.conv3d(x, w, None, stride=2, padding=1)
+    elif mode == 2:
+        y = F.conv3d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, stride=1, padding=1)
+    else:
+        y = F.conv3d(x, w, None)
+    if extra16 is not None:
+        e = extra16.float().permute(0, 4, 1, 2, 3).contiguous()
+        y = y + F.conv3d(e, wx[:, :, None, None, None], None)
+    if bias is not None:
+        y = y + bias[None, :, None, None, None]
+    y = y.permute(0, 2, 3, 4, 1).contiguous()
+    if resid is not None:
+        y = y + resid
+    return y
+
+
+def run_conv(nat, mode, B, D, H, W, cin, cout, cin_extra=0, terms=2, with_resid=False, impl=0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    act = torch.randn(B, D, H, W, cin, device="cuda", generator=g).half()
+    k = 1 if mode == 3 else 3
+    w = torch.randn(cout, cin, k, k, k, device="cuda", generator=g) / (cin * k ** 3) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    if mode == 1:
+        od, oh, ow = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    elif mode == 2:
+        od, oh, ow = 2 * D, 2 * H, 2 * W
+    else:
+        od, oh, ow = D, H, W
+    extra = wx = None
+    if cin_extra:
+        extra = torch.randn(B, od, oh, ow, cin_extra, device="cuda", generator=g).half()
+        wx = torch.randn(cout, cin_extra, device="cuda", generator=g) / cin_extra ** 0.5
+    resid = torch.randn(B, od, oh, ow, cout, device="cuda", generator=g) if with_resid else None
+    out32 = torch.full((B, od, oh, ow, cout), float("nan"), device="cuda")
+    out16 = torch.zeros(B, od, oh, ow, cout, device="cuda", dtype=torch.half)
+    rc = nat.lib().cm_op_conv3d(mode, nat.ptr(act), B, D, H, W, cin, nat.ptr(extra), cin_extra,
+                                nat.ptr(w), nat.ptr(wx), nat.ptr(bias), cout, terms,
+                                nat.ptr(resid), nat.ptr(out32), nat.ptr(out16), impl,
+                                nat.current_stream())
+    nat.check(rc)
+    torch.cuda.synchronize()
+    flag = nat.lib().cm_device_error()
+    ref = torch_conv(mode, act, extra, w, wx, bias, resid)
+    return out32, out16, ref, flag
+
+
+CONV_CASES = [
+    # (mode, B, D, H, W, cin, cout, cin_extra, resid)    -- names follow the ATC UNet layers
+    (0, 2, 12, 36, 8, 32, 32, 0, True),     # encoder_blocks.0.conv_2 (identity residual), BK=32
+    (0, 2, 12, 36, 8, 64, 32, 0, False),    # decoder_blocks.7.conv_1, BK=64 BN=32
+    (0, 2, 6, 18, 4, 64, 64, 32, False),    # encoder_blocks.2.conv_2 + match_input slab, BK=32
+    (0, 3, 3, 9, 2, 128, 128, 64, False),   # encoder_blocks.4.conv_2 + slab, partial last tile
+    (0, 2, 3, 9, 2, 256, 128, 0, False),    # decoder_blocks.0.conv_1, BN=128
+    (0, 1, 6, 18, 4, 192, 64, 0, False),    # decoder_blocks.3.conv_1
+    (0, 1, 12, 36, 8, 96, 32, 0, False),    # decoder_blocks.6.conv_1, BK=32
+    (1, 2, 12, 36, 8, 32, 32, 0, False),    # encoder_blocks.1.downsample (stride 2)
+    (1, 3, 6, 18, 4, 64, 64, 0, False),     # encoder_blocks.3.downsample
+    (2, 2, 3, 9, 2, 128, 128, 0, False),    # decoder_blocks.2.upsample (8 phase convs)
+    (2, 1, 6, 18, 4, 64, 64, 0, False),     # decoder_blocks.5.upsample
+    (3, 3, 3, 9, 2, 128, 384, 0, False),    # attention in_proj (N tiles = 3)
+    (3, 3, 3, 9, 2, 128, 128, 0, True),     # attention out_proj + residual
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d_r%d" % c)
+@pytest.mark.parametrize("terms", [2, 1])
+def test_conv_umma_vs_torch(nat, case, terms):
+    mode, B, D, H, W, cin, cout, cx, resid = case
+    out32, out16, ref, flag = run_conv(nat, mode, B, D, H, W, cin, cout, cx, terms, resid, impl=0)
+    assert flag == 0, f"device protocol error flag {flag}"
+    assert not torch.isnan(out32).any(), "unwritten outputs: " + describe_mismatch(out32.nan_to_num(1e9), ref)
+    e = rel_l2(out32, ref)
+    bound = 2e-5 if terms == 2 else 1e-3
+    assert e <= bound, f"rel-L2 {e:.3e} > {bound}: " + describe_mismatch(out32, ref)
+    assert rel_l2(out16.float(), ref) <= 1e-3
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:4] + CONV_CASES[7:10],
+                         ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d_r%d" % c)
+def test_conv_umma_vs_scalar_restatement(nat, case):
+    mode, B, D, H, W, cin, cout, cx, resid = case
+    a32, _, _, flag = run_conv(nat, mode, B, D, H, W, cin, cout, cx, 2, resid, impl=0)
+    b32, _, ref, _ = run_conv(nat, mode, B, D, H, W, cin, cout, cx, 2, resid, impl=1)
+    assert flag == 0
+    assert rel_l2(b32, ref) <= 2e-5, "scalar restatement itself is off: " + describe_mismatch(b32, ref)
+    assert rel_l2(a32, b32) <= 1e-5, describe_mismatch(a32, b32)
+
+
+@pytest.mark.parametrize("B,pixels,c0,c1,silu", [
+    (2, 3456, 32, 0, 1), (2, 3456, 64, 32, 1), (3, 432, 128, 64, 1), (2, 54, 128, 0, 0),
+    (2, 54, 128, 128, 1), (1, 5376, 64, 32, 1),
+])
+def test_gn_silu(nat, B, pixels, c0, c1, silu):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    C_ = c0 + c1
+    s0 = torch.randn(B, pixels, c0, device="cuda", generator=g) * 2 + 0.5
+    s1 = torch.randn(B, pixels, c1, device="cuda", generator=g) if c1 else None
+    gamma = torch.randn(C_, device="cuda", generator=g)
+    beta = torch.randn(C_, device="cuda", generator=g)
+    out = torch.zeros(B, pixels, C_, device="cuda", dtype=torch.half)
+    raw = torch.zeros(B, pixels, C_, device="cuda", dtype=torch.half)
+    nat.check(nat.lib().cm_op_gn_silu(nat.ptr(s0), c0, nat.ptr(s1), c1, nat.ptr(gamma), nat.ptr(beta),
+                                      B, pixels, 1e-5, silu, nat.ptr(out), nat.ptr(raw),
+                                      nat.current_stream()))
+    torch.cuda.synchronize()
+    x = torch.cat([s0, s1], dim=2) if c1 else s0
+    ref = F.group_norm(x.permute(0, 2, 1).contiguous(), 8, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    # fp16 output rounding: 2^-11 relative
+    assert rel_l2(out.float(), ref) <= 4e-4
+    assert (out.float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(raw, x.half())
+
+
+@pytest.mark.parametrize("B,S,C_", [(3, 54, 128), (2, 108, 256), (2, 12, 128), (1, 84, 128)])
+def test_attn_core(nat, B, S, C_):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    heads = 4
+    qkv = torch.randn(B, S, 3 * C_, device="cuda", generator=g)
+    ctx = torch.zeros(B, S, C_, device="cuda", dtype=torch.half)
+    nat.check(nat.lib().cm_op_attn_core(nat.ptr(qkv), nat.ptr(ctx), B, S, C_, heads, nat.current_stream()))
+    torch.cuda.synchronize()
+    dh = C_ // heads
+    q, k, v = [t.reshape(B, S, heads, dh).transpose(1, 2) for t in qkv.split(C_, dim=2)]
+    p = torch.softmax((q @ k.transpose(-1, -2)) / dh ** 0.5, dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(B, S, C_)
+    assert rel_l2(ctx.float(), ref) <= 4e-4
+
+
+@pytest.mark.parametrize("B,H,W,P,Fu,cin,cout", [(2, 12, 36, 5, 3, 3, 32), (1, 8, 12, 5, 3, 3, 64), (2, 4, 4, 2, 2, 4, 32)])
+def test_first_conv(nat, B, H, W, P, Fu, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, cin, H, W, Fu, device="cuda", generator=g)
+    past = torch.randn(B, cin, H, W, P, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    out = torch.zeros(B, H, W, P + Fu, cout, device="cuda")
+    nat.check(nat.lib().cm_op_first_conv(nat.ptr(x), nat.ptr(past), nat.ptr(w), nat.ptr(b), nat.ptr(out),
+                                         B, H, W, P, Fu, cin, cout, nat.current_stream()))
+    torch.cuda.synchronize()
+    ref = F.conv3d(torch.cat([past, x], dim=4), w, b, padding=1).permute(0, 2, 3, 4, 1)
+    assert rel_l2(out, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,P,Fu,cin,cout", [(2, 12, 36, 5, 3, 32, 3), (1, 8, 12, 8, 8, 64, 3), (2, 4, 4, 2, 2, 32, 4)])
+def test_final_conv(nat, B, H, W, P, Fu, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    L = P + Fu
+    act = torch.randn(B, H, W, L, cin, device="cuda", generator=g).half()
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    eps = torch.zeros(B, cout, H, W, Fu, device="cuda")
+    nat.check(nat.lib().cm_op_final_conv(nat.ptr(act), nat.ptr(w), nat.ptr(b), nat.ptr(eps), B, H, W, L, P,
+                                         cin, cout, nat.current_stream()))
+    torch.cuda.synchronize()
+    ref = F.conv3d(act.float().permute(0, 4, 1, 2, 3), w, b, padding=1)[..., P:]
+    assert rel_l2(eps, ref) <= 1e-5
