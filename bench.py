@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native DDPM sampling hot path.
+
+Metric (BASELINE.json): sampled sequences/sec for the FULL T-step reverse chain.
+Workload at N=1: config/ATC.yml — 1000-step DDPM sampling, batch 64 per GPU, grid 12x36,
+past 5 + future 3 frames, UNet base 32 / mult [1,2,4] / attention at the coarsest level,
+pretrained-shape random-init weights (torch.manual_seed(42)), synthetic macroprops.
+
+A "step" is ONE full reverse chain (T denoiser evaluations + T fused updates) over one batch.
+
+  python bench.py --gpus N --steps K --warmup W            (native arm; torchrun for N>1)
+  python bench.py --impl reference ...                     (CPU oracle port of the reference path)
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ATC = dict(input_channels=3, output_channels=3, num_res_blocks=1, base_channels=32,
+           base_channels_multiples=[1, 2, 4], apply_attention=[False, False, True, False],
+           dropout_rate=0.1, time_multiple=4, condition="Past")
+ROWS, COLS, PAST, FUT = 12, 36, 5, 3
+T_STEPS, SCALE = 1000, 0.5
+UNIT = "sequences/s"
+METRIC = "sampled sequences/sec (full T-step DDPM chain)"
+
+
+def synthetic_macroprops(n, channels, rows, cols, frames, seed, device="cpu"):
+    """occupancy Bernoulli(0.2); rho = mask*(1+Poisson(0.5)); v = mask*N(0,0.5^2)."""
+    g = torch.Generator().manual_seed(seed)
+    mask = (torch.rand(n, 1, rows, cols, frames, generator=g) < 0.2).float()
+    rho = mask * (1 + torch.poisson(torch.full_like(mask, 0.5), generator=g))
+    v = mask * torch.randn(n, channels - 1, rows, cols, frames, generator=g) * 0.5
+    return torch.cat([rho, v], dim=1).contiguous().to(device)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops_sustained": p.get("bf16_tflops_sustained", 1426.2),
+                "tflops_burst": p.get("bf16_tflops", 1688.0), "hbm_gbs": p.get("hbm_gbs", 6455.6),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for k, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(k)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_sample(n, steps, threads):
+    """Times `steps` denoiser+update iterations of the reference path's CPU restatement
+    (oracle/) at batch n; returns seconds per iteration."""
+    from oracle import ddpm_oracle as do
+    from oracle import unet_oracle as uo
+    from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    sd = UNet(**ATC).state_dict()
+    s = do.schedule(T_STEPS, SCALE)
+    past = do.synthetic_macroprops(n, 3, ROWS, COLS, PAST, 1234)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(n, 3, ROWS, COLS, FUT, generator=g)
+
+    def one(x, t):
+        tt = torch.full((n,), t, dtype=torch.long)
+        eps = uo.unet_forward(sd, x, tt, past, num_res_blocks=1, num_levels=3)
+        return do.ddpm_step(s, eps, x, t, torch.randn(x.shape, generator=g))
+
+    with torch.no_grad():
+        x = one(x, T_STEPS - 1)                       # warm-up
+        t0 = time.perf_counter()
+        for i in range(steps):
+            x = one(x, T_STEPS - 2 - i)
+        dt = (time.perf_counter() - t0) / steps
+    return dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.batch
+    it = args.ref_iters
+    times = []
+    for k in range(args.warmup + args.steps):
+        dt = cpu_oracle_sample(n, it, threads)
+        if k >= args.warmup:
+            times.append(dt)
+    s_per_iter = sum(times) / len(times)
+    chain_s = s_per_iter * T_STEPS
+    value = n / chain_s
+    sample = (f"{it} denoiser+DDPM.step iterations at batch {n} per step (of the {T_STEPS}-step chain), "
+              f"extrapolated x{T_STEPS}/{it}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": chain_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic macroprops, random-init weights (seed 42)",
+        "config": workload_config(n, args.gpus, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, gpus, terms):
+    return {"workload": "config/ATC.yml: full 1000-step DDPM sampling, batch 64 per GPU, UNet base 32 "
+                        "mult [1,2,4], grid 12x36, past 5 + future 3",
+            "samples_per_gpu": n, "global_samples": n * gpus, "timesteps": T_STEPS,
+            "parallelism": f"sample-sharded x{gpus}, no collective", "weight_terms": terms,
+            "l2_flush": "256 MiB buffer written between timed chains; per-step working set (~1 GB) > L2",
+            "noise": "in-kernel Philox (device-resident), x_T ~ N(0,I)"}
+
+
+def run_native(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from crowdmod_ddpm_4d_b200 import _native as nat
+    from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
+    from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM, ddpm_coefficients
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.batch
+    torch.manual_seed(42)
+    net = UNet(**ATC).to(dev).eval()
+    sampler = DDPM(timesteps=args.timesteps, scale=SCALE)
+    tsteps, coef = ddpm_coefficients(sampler)
+    past_host = synthetic_macroprops(n, 3, ROWS, COLS, PAST, 1234 + rank).pin_memory()
+    past = past_host.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    terms = int(os.environ.get("CROWDMOD_WEIGHT_TERMS", "2"))
+
+    def chain_device(seed):
+        x = torch.randn(n, 3, ROWS, COLS, FUT, device=dev, generator=gen)
+        net.sample_chain(past, x, tsteps, coef, mode=0, seed=seed, sample_offset=rank * n, use_graph=True)
+        return x
+
+    x0_host = torch.empty(n, 3, ROWS, COLS, FUT).pin_memory()
+
+    def chain_e2e(seed):
+        """The call a user makes: host past in, host x_0 out (H2D + D2H inside the timed region)."""
+        p = past_host.to(dev, non_blocking=True)
+        x = torch.randn(n, 3, ROWS, COLS, FUT, device=dev, generator=gen)
+        net.sample_chain(p, x, tsteps, coef, mode=0, seed=seed, sample_offset=rank * n, use_graph=True)
+        x0_host.copy_(x, non_blocking=True)
+        return x
+
+    # ---- warm-up (graph capture, descriptor build, clocks) ----
+    for w in range(max(args.warmup, 3)):
+        chain_device(1000 + w)
+    barrier()
+
+    # ---- timed: device-resident inputs ----
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k)
+        ev[k][0].record()
+        chain_device(k)
+        ev[k][1].record()
+        launches += net.last_chain_launches(ROWS, COLS, PAST, FUT)
+    barrier()
+    clk = clocks.stop() if clocks else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- timed: end to end through the public call with host buffers ----
+    chain_e2e(999)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k)
+        ev2[k][0].record()
+        chain_e2e(k)
+        ev2[k][1].record()
+    barrier()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        total = n * world * args.steps
+        value = total / (ms / 1e3)
+        e2e = total / (ms_e2e / 1e3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate",
+            "data": "synthetic macroprops, random-init weights (seed 42)",
+            "config": workload_config(n, world, terms),
+            "denoiser_step_ms": ms / args.steps / args.timesteps,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": past_host.numel() * 4,
+                    "d2h_bytes_per_step": x0_host.numel() * 4},
+            "gpu_launches": launches,
+            "clocks": clk,
+        }
+        line["roofline"] = roofline(net, nat, past, n, dev, ms / args.steps / args.timesteps)
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            s_it = cpu_oracle_sample(n, args.ref_iters, threads)
+            line["cpu_baseline"] = {
+                "value": n / (s_it * T_STEPS), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{args.ref_iters} denoiser+DDPM.step iterations at batch {n} on the host cores "
+                          f"(oracle/ restatement of the reference CPU path), extrapolated to {T_STEPS} steps"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(net, nat, past, n, dev, step_ms):
+    """Dominant kernel = the tcgen05 implicit-GEMM conv (tensor-bound).  achieved = algorithmic
+    FLOPs of all its launches in one denoiser step / their summed device time, timed live with
+    CUDA events around every launch (cm_unet_profile_forward)."""
+    pk = peaks()
+    plan = net._plan(ROWS, COLS, PAST, FUT)
+    lib = nat.lib()
+    nops = lib.cm_unet_op_count(plan.handle)
+    x = torch.randn(n, 3, ROWS, COLS, FUT, device=dev)
+    t = torch.full((n,), 500, device=dev, dtype=torch.long)
+    eps = torch.empty_like(x)
+    ms = (C.c_float * nops)()
+    best = None
+    for _ in range(5):
+        nat.check(lib.cm_unet_profile_forward(plan.handle, nat.ptr(x), nat.ptr(t), nat.ptr(past), nat.ptr(eps),
+                                              n, nat.current_stream(), ms, nops))
+        cur = list(ms)
+        if best is None or sum(cur) < sum(best):
+            best = cur
+    kinds = {0: "first_conv", 1: "gn_silu", 2: "conv_umma", 3: "attn_core", 4: "final_conv"}
+    agg = {}
+    tag = C.create_string_buffer(128)
+    ty = C.c_int()
+    fl = C.c_double()
+    for i in range(nops):
+        lib.cm_unet_op_info(plan.handle, i, tag, 128, C.byref(ty), C.byref(fl))
+        a = agg.setdefault(kinds[ty.value], {"ms": 0.0, "flops": 0.0, "launches": 0})
+        a["ms"] += best[i]
+        a["flops"] += fl.value * n
+        a["launches"] += 1
+    conv = agg["conv_umma"]
+    achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv_umma_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    total_ms = sum(best)
+    return {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv3d)",
+            "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+            "peak_source": pk["source"] + ", sustained bf16/fp16 dense",
+            "launches_per_step": conv["launches"], "avg_launch_us": conv["ms"] * 1e3 / conv["launches"],
+            "algorithmic_gflop_per_step": conv["flops"] / 1e9,
+            "share_of_step": conv["ms"] / total_ms,
+            "per_kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in agg.items()},
+            "eager_step_ms": total_ms, "graph_step_ms": step_ms,
+            "whole_step_tflops": (sum(v["flops"] for v in agg.values()) / 1e12) / (step_ms * 1e-3)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU (ATC.yml BATCH_SIZE)")
+    ap.add_argument("--timesteps", type=int, default=T_STEPS)
+    ap.add_argument("--ref-iters", type=int, default=8, help="CPU denoiser iterations per reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,11 @@ SIGNATURES = {
                                   C.c_int, C.c_void_p]),
     "cm_unet_launches_per_forward": (C.c_int, [C.c_void_p]),
     "cm_unet_flops_per_sample": (C.c_double, [C.c_void_p]),
+    "cm_unet_op_count": (C.c_int, [C.c_void_p]),
+    "cm_unet_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_double)]),
+    "cm_unet_profile_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "cm_ddpm_sample": (C.c_int, [C.c_void_p, C.POINTER(ChainArgs), C.c_void_p]),
     "cm_last_chain_launches": (C.c_int64, [C.c_void_p]),
     "cm_op_conv3d": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

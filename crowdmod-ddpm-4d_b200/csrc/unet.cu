@@ -418,9 +418,13 @@ struct RunCtx {
   FinalParams fin;       // eps_out / update parameters (act, w, geometry filled here)
 };
 
-int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches) {
+int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
+            cudaEvent_t* events = nullptr) {
   const cm_unet_config& c = u->cfg;
+  int op_index = 0;
   for (Op& op : u->ops) {
+    if (events) CM_CUDA(cudaEventRecord(events[op_index], st));
+    ++op_index;
     switch (op.type) {
       case OP_FIRST: {
         const Level& l0 = u->levels[0];
@@ -481,6 +485,7 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches) {
     }
     if (launches) ++*launches;
   }
+  if (events) CM_CUDA(cudaEventRecord(events[op_index], st));
   return 0;
 }
 
@@ -677,6 +682,61 @@ int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, const flo
   rc.fin = FinalParams{};
   rc.fin.eps_out = eps_out;
   return run_ops(u, rc, st, nullptr);
+}
+
+int cm_unet_op_count(const cm_unet* u) { return u ? (int)u->ops.size() : -1; }
+
+int cm_unet_op_info(const cm_unet* u, int idx, char* tag, int tag_cap, int* type, double* flops_per_sample) {
+  CM_CHECK(u && idx >= 0 && idx < (int)u->ops.size(), "bad op index %d", idx);
+  const Op& op = u->ops[idx];
+  if (tag && tag_cap > 0) snprintf(tag, tag_cap, "%s", op.tag.c_str());
+  if (type) *type = (int)op.type;
+  if (flops_per_sample) {
+    double fl = 0.0;
+    const cm_unet_config& c = u->cfg;
+    if (op.type == OP_CONV) {
+      const Level& lo = u->levels[u->tens[op.out].level];
+      const double taps = (op.mode == 3) ? 1.0 : 27.0;
+      fl = 2.0 * lo.pps() * op.cout * (taps * op.cin + op.cin_extra);
+    } else if (op.type == OP_ATTN) {
+      const Level& lv = u->levels[u->tens[op.qkv].level];
+      fl = 4.0 * (double)lv.pps() * lv.pps() * u->tens[op.ctx].C;
+    } else if (op.type == OP_FIRST) {
+      fl = 2.0 * u->levels[0].pps() * c.base_channels * 27.0 * c.in_channels;
+    } else if (op.type == OP_FINAL) {
+      fl = 2.0 * u->levels[0].pps() * c.out_channels * 27.0 * op.cin;
+    }
+    *flops_per_sample = fl;
+  }
+  return 0;
+}
+
+int cm_unet_profile_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
+                            float* eps_out, int batch, void* stream, float* ms_out, int cap) {
+  CM_CHECK(u && future && t && past && eps_out && ms_out, "null argument");
+  CM_CHECK(cap >= (int)u->ops.size(), "ms_out too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // warm pass builds descriptors / time embedding, then the measured pass brackets every op
+  if (int e = cm_unet_forward(u, future, t, past, eps_out, batch, stream)) return e;
+  std::vector<cudaEvent_t> ev(u->ops.size() + 1);
+  for (auto& e : ev) CM_CUDA(cudaEventCreate(&e));
+  RunCtx rc{};
+  rc.batch = batch;
+  rc.future = future;
+  rc.past = past;
+  rc.temb = u->temb_batch;
+  rc.t_dev = nullptr;
+  rc.temb_bstride = u->temb_ld;
+  rc.fin = FinalParams{};
+  rc.fin.eps_out = eps_out;
+  int e = run_ops(u, rc, st, nullptr, ev.data());
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (!e && se == cudaSuccess)
+    for (size_t i = 0; i < u->ops.size(); ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (e) return e;
+  CM_CUDA(se);
+  return 0;
 }
 
 int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {

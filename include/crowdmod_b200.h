@@ -76,6 +76,16 @@ CM_API int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, co
 CM_API int cm_unet_launches_per_forward(const cm_unet* u);
 CM_API double cm_unet_flops_per_sample(const cm_unet* u);
 
+/* Measurement support for bench.py: the plan's ops (tag, kind: 0 first conv, 1 GroupNorm+SiLU,
+ * 2 tcgen05 conv, 3 attention core, 4 final conv; algorithmic FLOPs per sample in the
+ * reference's dense formulation) and one forward with CUDA events around every launch
+ * (ms_out[i] = device time of op i on `stream`).  Synchronises. */
+CM_API int cm_unet_op_count(const cm_unet* u);
+CM_API int cm_unet_op_info(const cm_unet* u, int idx, char* tag, int tag_cap, int* type,
+                           double* flops_per_sample);
+CM_API int cm_unet_profile_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
+                                   float* eps_out, int batch, void* stream, float* ms_out, int cap);
+
 /* ---- reverse chain: replaces DDPM_model._generate_ddpm/_generate_ddim (ddpm.py:206-282)
  *      with DDPM.step (ddpm.py:25-38) fused into the last conv's epilogue ---- */
 typedef struct cm_chain_args {
