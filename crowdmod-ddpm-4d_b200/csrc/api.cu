@@ -1,6 +1,8 @@
 // Library-level C ABI: error reporting, device error flag, op-level entry points used by the
 // unit tests (each wraps one kernel of the hot path; they allocate temporaries and synchronise,
 // the model-level calls in unet.cu do not).
+#include <stdlib.h>
+
 #include <mutex>
 #include <string>
 
@@ -53,8 +55,8 @@ int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int ci
   __half* wp = nullptr;
   CM_CUDA(cudaMalloc(&wp, (size_t)terms * cout * ktot * sizeof(__half)));
   int rc = 0;
-  if (mode == 2) rc = pack_upsample_weights(w, wp, cout, cin, terms, st);
-  else rc = pack_conv_weights(w, wx, wp, cout, cin, cin_extra, mode == 3 ? 1 : 27, terms, st);
+  if (mode == 2) rc = pack_upsample_weights(w, wp, cout, cin, terms, 0, st);
+  else rc = pack_conv_weights(w, wx, wp, cout, cin, cin_extra, mode == 3 ? 1 : 27, terms, 0, st);
   ConvLaunch L;
   if (!rc) rc = conv_prepare(&L, mode, static_cast<const __half*>(act16), B, D, H, W, cin,
                              static_cast<const __half*>(extra16), cin_extra, wp, cout, terms);
@@ -63,8 +65,47 @@ int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int ci
     L.p.resid = resid;
     L.p.out32 = out32;
     L.p.out16 = static_cast<__half*>(out16);
-    if (impl == 0) rc = conv_enqueue(L, st);
-    else rc = conv_ref_enqueue(L.p, static_cast<const __half*>(act16),
+    if (impl == 0) {
+      rc = conv_enqueue(L, st);
+      if (getenv("CM_DBG_TRACE")) {
+        unsigned long long* tr = nullptr;
+        cudaMalloc(&tr, 512 * 8);
+        cudaMemset(tr, 0, 512 * 8);
+        L.p.trace = tr;
+        cudaStreamSynchronize(st);
+        conv_enqueue(L, st);
+        cudaStreamSynchronize(st);
+        unsigned long long h[512];
+        cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost);
+        const unsigned long long t0 = h[0];
+        fprintf(stderr, "CM_TRACE start=0 setup_done=%lld tmem_full=%lld epi_done=%lld end=%lld\n",
+                (long long)(h[4] - t0), (long long)(h[1] - t0), (long long)(h[2] - t0), (long long)(h[3] - t0));
+        for (int kb = 0; kb < 120 && h[8 + kb * 4]; ++kb)
+          fprintf(stderr, "CM_TRACE kb=%d prod_wait_done=%lld prod_issued=%lld mma_wait_done=%lld mma_committed=%lld\n", kb,
+                  (long long)(h[8 + kb * 4] - t0), (long long)(h[8 + kb * 4 + 1] - t0),
+                  (long long)(h[8 + kb * 4 + 2] - t0), (long long)(h[8 + kb * 4 + 3] - t0));
+        L.p.trace = nullptr;
+        cudaFree(tr);
+      }
+      if (const char* e = getenv("CM_DBG_REPS")) {   // bring-up timing: avg device time of `reps` launches
+        const int reps = atoi(e);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaStreamSynchronize(st);
+        cudaEventRecord(a, st);
+        for (int i = 0; i < reps && !rc; ++i) rc = conv_enqueue(L, st);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "CM_DBG conv mode=%d M=%d cin=%d cout=%d bn=%d bk=%d stages=%d grid=%d,%d,%d dbg=%d: %.2f us/launch\n",
+                mode, L.p.M, cin, cout, L.bn, L.bk, L.p.stages, L.grid.x, L.grid.y, L.grid.z, L.p.dbg,
+                ms * 1e3f / reps);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+      }
+    } else rc = conv_ref_enqueue(L.p, static_cast<const __half*>(act16),
                                static_cast<const __half*>(extra16), wp, B, D, H, W, st);
   }
   cudaError_t se = cudaStreamSynchronize(st);
@@ -82,7 +123,15 @@ int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, const fl
   g.gamma = gamma; g.beta = beta; g.B = B; g.pixels = pixels; g.eps = eps; g.silu = silu;
   g.out_norm = static_cast<__half*>(out_norm16);
   g.out_raw = static_cast<__half*>(out_raw16);
-  return gn_silu_enqueue(g, static_cast<cudaStream_t>(stream));
+  float* partial = nullptr;
+  CM_CUDA(cudaMalloc(&partial, (size_t)B * gn_chunks(pixels, c0 + c1) * 16 * sizeof(float)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = gn_silu_enqueue(g, partial, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(partial);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
 }
 
 int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream) {

@@ -111,6 +111,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Returns false on timeout.  ~2^22 polls of a HW-suspending try_wait is seconds, far beyond
 // any legitimate wait in these kernels.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 22); ++it) {
     if (mbar_try_wait(bar, parity)) return true;
   }
@@ -180,6 +182,28 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Lean form for the single issuing thread: descriptors as (lo, hi) 32-bit halves so that the
+// per-MMA work is two integer adds (the hi halves are kernel constants).
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                              uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t kmajor_desc_hi(int row_bytes) {
+  return static_cast<uint32_t>(((8 * row_bytes) >> 4) & 0x3FFF) | (1u << 14) |
+         (static_cast<uint32_t>(row_bytes == 128 ? 2 : 4) << 29);
+}
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+}
+
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cm {
@@ -71,14 +72,17 @@ int make_weight_map(CUtensorMap* map, const __half* base, size_t rows, size_t kt
 
 template <int BN, int BK>
 int launch_t(const ConvLaunch& L, cudaStream_t st) {
-  conv_umma_kernel<BN, BK><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
+  if (L.p.terms == 2) conv_umma_kernel<BN, BK, 2><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
+  else conv_umma_kernel<BN, BK, 1><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN, int BK>
 int set_attr_t() {
-  CM_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CM_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, BK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024));
   return 0;
 }
@@ -120,10 +124,6 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
   memset(L, 0, sizeof(*L));
   ConvParams& p = L->p;
   const int bk = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
-  const int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
-  L->bk = bk;
-  L->bn = bn;
-
   int stride = 1, k = 3, od = D, oh = H, ow = W;
   if (mode == 1) {
     stride = 2;
@@ -136,6 +136,15 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
     k = 1;
   }
   p.nphase = (mode == 2) ? 8 : 1;
+  // N tile: as wide as possible (A is re-read once per N tile) unless that leaves most SMs idle
+  // (coarse levels have only a few dozen M tiles): then trade A re-reads for more CTAs.
+  int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
+  {
+    const long m_tiles = ((long)B * od * oh * ow + CONV_BM - 1) / CONV_BM * p.nphase;
+    while (bn > 32 && m_tiles * (cout / bn) < 120) bn >>= 1;
+  }
+  L->bk = bk;
+  L->bn = bn;
   for (int ph = 0; ph < p.nphase; ++ph) {
     int lw, lh, ld;
     if (mode == 2) {
@@ -177,9 +186,12 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
 
   const int stage_bytes = CONV_BM * bk * 2 + terms * bn * bk * 2;
   int stages = 4;
+  if (const char* e = getenv("CM_DBG_STAGES")) stages = atoi(e);
+  if (const char* e = getenv("CM_DBG_SKIP")) p.dbg = atoi(e);
+  if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
   while (stages > 2 && (size_t)stages * stage_bytes + 2048 > 200 * 1024) --stages;
   p.stages = stages;
-  L->smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  L->smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*colv*/;
   L->grid = dim3((p.M + CONV_BM - 1) / CONV_BM, cout / bn, p.nphase);
   L->flops = 2.0 * p.M * cout * (double)(k * k * k * cin + cin_extra) * p.nphase;
   return 0;

@@ -18,6 +18,12 @@
 
 namespace cm {
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 constexpr int CONV_BM = 128;        // UMMA M (cta_group::1)
 constexpr int CONV_THREADS = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int CONV_MAX_STAGES = 6;
@@ -50,9 +56,11 @@ struct ConvParams {
   int out_ld;
   int scatter;           // 1: rows are low-res pixels, written to (2z+pz, 2p+pp, 2q+pq)
   int* err_flag;
+  unsigned long long* trace;   // bring-up: per-k-block timestamps of CTA (0,0,0) (CM_DBG_TRACE)
+  int dbg;               // bring-up knobs (CM_DBG_SKIP): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int TERMS>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams P) {
   constexpr int ROWB = BK * 2;                  // bytes per smem row (swizzle span)
@@ -65,12 +73,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const int S = P.stages;
-  const int terms = P.terms;
+  constexpr int terms = TERMS;
   const int stage_bytes = A_BYTES + terms * B_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
   uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + CONV_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* colv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 128);   // [BN] per-column epilogue constants
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,9 +110,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool tr = P.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (tr && threadIdx.x == 0) P.trace[0] = gtime_ns();
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) ====
+    {
       const int m0 = m_tile * CONV_BM;
       const int n0 = m0 / P.pps;
       int r = m0 - n0 * P.pps;
@@ -115,63 +126,95 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       const int h0 = p0 * P.conv_stride + P.lower[phase][1];
       const int d0 = z0 * P.conv_stride + P.lower[phase][2];
       const int kbase = phase * P.kphase;
-      const uint32_t tx = A_BYTES + terms * B_BYTES;
+      const uint32_t tx = ((P.dbg & 1) ? 0 : A_BYTES) + ((P.dbg & 2) ? 0 : terms * B_BYTES);
+      int s = 0, tw = 0, th = 0, td = 0, cc = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
         if (!mbar_wait(&empty_bar[s], ph ^ 1, P.err_flag, 101)) break;
         uint8_t* sa = smem + s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx);
-        if (kb < nkb_main) {
-          const int tap = kb / ncm;
-          const int cc = kb - tap * ncm;
-          const int tw = tap % P.kw;
-          const int th = (tap / P.kw) % P.kh;
-          const int td = tap / (P.kw * P.kh);
-          tma_load_im2col_5d(&P.amap[phase], &full_bar[s], sa, cc * BK, w0, h0, d0, n0,
-                             (uint16_t)tw, (uint16_t)th, (uint16_t)td);
-        } else {
-          const int cc = kb - nkb_main;
-          tma_load_im2col_5d(&P.xmap, &full_bar[s], sa, cc * BK, q0, p0, z0, n0, 0, 0, 0);
+        if (elect_one()) {
+          if (tr && kb < 120) P.trace[8 + kb * 4 + 0] = gtime_ns();
+          if (tx) mbar_expect_tx(&full_bar[s], tx); else mbar_arrive(&full_bar[s]);
+          if (P.dbg & 1) {
+          } else if (kb < nkb_main) {
+            tma_load_im2col_5d(&P.amap[phase], &full_bar[s], sa, cc * BK, w0, h0, d0, n0,
+                               (uint16_t)tw, (uint16_t)th, (uint16_t)td);
+          } else {
+            tma_load_im2col_5d(&P.xmap, &full_bar[s], sa, (kb - nkb_main) * BK, q0, p0, z0, n0, 0, 0, 0);
+          }
+          if (!(P.dbg & 2)) {
+#pragma unroll
+            for (int t = 0; t < terms; ++t)
+              tma_load_2d(&P.bmap, &full_bar[s], sa + A_BYTES + t * B_BYTES, kbase + kb * BK,
+                          n_tile * BN + t * P.cout);
+          }
+          if (tr && kb < 120) P.trace[8 + kb * 4 + 1] = gtime_ns();
         }
-        for (int t = 0; t < terms; ++t)
-          tma_load_2d(&P.bmap, &full_bar[s], sa + A_BYTES + t * B_BYTES, kbase + kb * BK,
-                      n_tile * BN + t * P.cout);
+        // advance (channel chunk, tap) counters and the stage ring without div/mod
+        if (++cc == ncm) {
+          cc = 0;
+          if (++tw == P.kw) {
+            tw = 0;
+            if (++th == P.kh) { th = 0; ++td; }
+          }
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      bool ok = true;
-      for (int kb = 0; kb < nkb && ok; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        ok = mbar_wait(&full_bar[s], ph, P.err_flag, 102);
-        if (!ok) break;
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====
+    {
+      constexpr uint32_t DESC_HI = kmajor_desc_hi(ROWB);
+      const uint32_t lo0 = kmajor_desc_lo(smem_u32(smem));
+      const uint32_t lo_stage = static_cast<uint32_t>(stage_bytes) >> 4;
+      int s = 0;
+      uint32_t ph = 0, acc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (!mbar_wait(&full_bar[s], ph, P.err_flag, 102)) break;
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_base = a_base + A_BYTES;
+        if (elect_one()) {
+          if (tr && kb < 120) P.trace[8 + kb * 4 + 2] = gtime_ns();
+          const uint32_t a_lo = lo0 + s * lo_stage;
+          if (!(P.dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t adesc = make_kmajor_desc(a_base + k * 32, ROWB);
-          for (int t = 0; t < terms; ++t) {
-            const uint64_t bdesc = make_kmajor_desc(b_base + t * B_BYTES + k * 32, ROWB);
-            umma_f16(tmem_base, adesc, bdesc, IDESC, (kb | k | t) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+              for (int t = 0; t < terms; ++t) {
+                umma_f16_lohi(tmem_base, a_lo + 2 * k, a_lo + ((A_BYTES + t * B_BYTES) >> 4) + 2 * k,
+                              DESC_HI, IDESC, acc);
+                acc = 1;
+              }
+            }
           }
+          if (P.dbg & 64) mbar_arrive(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs retire
+          if (tr && kb < 120) P.trace[8 + kb * 4 + 3] = gtime_ns();
         }
-        umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs retire
+        if (++s == S) { s = 0; ph ^= 1; }
       }
-      umma_commit(tmem_full);         // accumulator complete
+      if (elect_one()) umma_commit(tmem_full);       // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // Everything that does not depend on the accumulator is fetched while the mainloop runs:
+    // per-column bias (+ match bias + batch-uniform time-embedding row) into shared memory,
+    // the first residual chunk into registers.
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int m = m_tile * CONV_BM + row;
     const bool valid = m < P.M;
-    mbar_wait(tmem_full, 0, P.err_flag, 103);
-    tc_fence_after();
-
+    const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
+    const bool temb_uniform = P.temb != nullptr && P.temb_bstride == 0;
+    {
+      const int trow = (P.temb && P.t_dev) ? *P.t_dev : 0;
+      for (int c = et; c < BN; c += 128) {
+        const int n = n_tile * BN + c;
+        float v = P.bias ? P.bias[n] : 0.f;
+        if (P.bias2) v += P.bias2[n];
+        if (temb_uniform) v += P.temb[static_cast<size_t>(trow) * P.temb_ld + n];
+        colv[c] = v;
+      }
+    }
     int b = 0;
     size_t orow = 0;
     if (valid) {
@@ -189,48 +232,63 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         orow = static_cast<size_t>(m);
       }
     }
-    const float* temb_row = nullptr;
-    if (P.temb) {
-      const int trow = P.t_dev ? *P.t_dev : 0;
-      temb_row = P.temb + static_cast<size_t>(trow) * P.temb_ld +
-                 static_cast<size_t>(b) * P.temb_bstride;
+    const float* temb_row = nullptr;     // per-sample rows (training): added per element
+    if (P.temb && !temb_uniform)
+      temb_row = P.temb + static_cast<size_t>(b) * P.temb_bstride + n_tile * BN;
+    const float* rp = (P.resid && valid) ? P.resid + static_cast<size_t>(m) * P.cout + n_tile * BN : nullptr;
+    float4 rnext[4];
+    if (rp) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rnext[i] = *reinterpret_cast<const float4*>(rp + 4 * i);
     }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // colv visible to the 4 epilogue warps
+
+    if (P.dbg & 16) {
+      if (lane == 0) {
+        while (!mbar_try_wait(tmem_full, 0)) __nanosleep(500);
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(tmem_full, 0, P.err_flag, 103);
+    }
+    tc_fence_after();
+    if (tr && warp == 2 && lane == 0) P.trace[1] = gtime_ns();
+
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < BN / 16; ++c) {
-      float v[16];
-      tmem_ld16(t_lane + c * 16, v);
-      if (!valid) continue;
-      const int n = n_tile * BN + c * 16;
-      if (P.bias) {
+      float4 rcur[4];
+      if (rp) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(P.bias + n + i);
-          v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
+        for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+        if (c + 1 < BN / 16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rnext[i] = *reinterpret_cast<const float4*>(rp + (c + 1) * 16 + 4 * i);
         }
       }
-      if (P.bias2) {
+      float v[16];
+      tmem_ld16(t_lane + c * 16, v);
+      if (!valid || (P.dbg & 8)) continue;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(P.bias2 + n + i);
-          v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
-        }
+      for (int i = 0; i < 16; i += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(colv + c * 16 + i);
+        v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
       }
       if (temb_row) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(temb_row + n + i);
+          const float4 t4 = *reinterpret_cast<const float4*>(temb_row + c * 16 + i);
           v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
         }
       }
-      if (P.resid) {
-        const float* rp = P.resid + static_cast<size_t>(m) * P.cout + n;
+      if (rp) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(rp + i);
-          v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
+        for (int i = 0; i < 4; ++i) {
+          v[4 * i] += rcur[i].x; v[4 * i + 1] += rcur[i].y; v[4 * i + 2] += rcur[i].z; v[4 * i + 3] += rcur[i].w;
         }
       }
+      const int n = n_tile * BN + c * 16;
       if (P.out32) {
         float* op = P.out32 + orow * P.out_ld + n;
 #pragma unroll
@@ -256,9 +314,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     }
   }
 
+  if (tr && warp == 2 && lane == 0) P.trace[2] = gtime_ns();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, BN);
+  if (tr && threadIdx.x == 0) P.trace[3] = gtime_ns();
 }
 
 // -------------------------------- host side --------------------------------

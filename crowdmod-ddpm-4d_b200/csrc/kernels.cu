@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "conv_umma.cuh"
 
+
 namespace cm {
 
 // =============================================================================================
@@ -10,7 +11,7 @@ namespace cm {
 // =============================================================================================
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const float* __restrict__ wx,
                                          __half* __restrict__ dst, int cout, int cin, int cinx,
-                                         int taps, int terms) {
+                                         int taps, int terms, int perm) {
   const size_t ktot = (size_t)taps * cin + cinx;
   const size_t total = (size_t)cout * ktot;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
@@ -21,7 +22,12 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const floa
     if (k < (size_t)taps * cin) {
       const int tap = (int)(k / cin);
       const int ci = (int)(k - (size_t)tap * cin);
-      v = w[((size_t)n * cin + ci) * taps + tap];
+      // packed tap order follows the activation dims (d, h, w).  perm=1: the source weight is
+      // the reference's nn.Conv3d over (rows, cols, time) while activations are stored
+      // [B, time, rows, cols, C]  ->  source tap = (h*3 + w)*3 + d
+      int st = tap;
+      if (perm && taps == 27) st = (((tap / 3) % 3) * 3 + (tap % 3)) * 3 + tap / 9;
+      v = w[((size_t)n * cin + ci) * taps + st];
     } else {
       v = wx[(size_t)n * cinx + (k - (size_t)taps * cin)];
     }
@@ -32,16 +38,16 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const floa
 }
 
 int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, int cin, int cinx,
-                      int taps, int terms, cudaStream_t st) {
+                      int taps, int terms, int perm, cudaStream_t st) {
   const size_t total = (size_t)cout * ((size_t)taps * cin + cinx);
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, wx, dst, cout, cin, cinx, taps, terms);
+  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, wx, dst, cout, cin, cinx, taps, terms, perm);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void pack_upsample_weights_kernel(const float* __restrict__ w, __half* __restrict__ dst,
-                                             int cout, int cin, int terms) {
+                                             int cout, int cin, int terms, int perm) {
   const size_t ktot = (size_t)64 * cin;
   const size_t total = (size_t)cout * ktot;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
@@ -67,18 +73,19 @@ __global__ void pack_upsample_weights_kernel(const float* __restrict__ w, __half
     float v = 0.f;
     for (int kd = lo[2]; kd <= hi[2]; ++kd)
       for (int kh = lo[1]; kh <= hi[1]; ++kh)
-        for (int kw = lo[0]; kw <= hi[0]; ++kw) v += wp[(kd * 3 + kh) * 3 + kw];
+        for (int kw = lo[0]; kw <= hi[0]; ++kw)
+          v += perm ? wp[(kh * 3 + kw) * 3 + kd] : wp[(kd * 3 + kh) * 3 + kw];
     const __half h = __float2half_rn(v);
     dst[(size_t)n * ktot + k] = h;
     if (terms == 2) dst[((size_t)cout + n) * ktot + k] = __float2half_rn(v - __half2float(h));
   }
 }
 
-int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms,
+int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms, int perm,
                           cudaStream_t st) {
   const size_t total = (size_t)cout * 64 * cin;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_upsample_weights_kernel<<<blocks, 256, 0, st>>>(w, dst, cout, cin, terms);
+  pack_upsample_weights_kernel<<<blocks, 256, 0, st>>>(w, dst, cout, cin, terms, perm);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -96,175 +103,265 @@ int cast_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t st) {
 }
 
 // =============================================================================================
-// GroupNorm(8) + SiLU -> fp16
-// One CTA per (sample, group).  Exact two-pass statistics (mean, then centred second moment)
-// with the slab cached in registers (first GN_CACHE float4 per thread; the tail, if any, is
-// re-read from L2).
+// GroupNorm(8) + SiLU -> fp16, as two fully parallel, fully coalesced kernels:
+//   gn_stats_kernel : CTA = (sample, pixel slice), all channels.  Exact two-pass (mean, centred
+//                     M2) statistics of the slice per group from a register-cached copy.
+//   gn_apply_kernel : combines the slice statistics of its sample with Chan's formula in a
+//                     fixed order (bit-reproducible), then normalise + affine + SiLU (+ Dropout3d
+//                     scale) -> fp16 operand (and optional raw fp16 copy for match_input).
+// Thread count is a multiple of C/4, so a thread always handles the same 4 channels (same
+// group, gamma, beta) and consecutive threads touch consecutive 16 bytes.
 // =============================================================================================
-constexpr int GN_CACHE = 8;
+constexpr int GN_CACHE = 8;          // float4 cached per thread
+constexpr int GN_MAX_CHUNKS = 64;
 
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();   // protect `red` reuse
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  float t = (lane < nw) ? red[lane] : 0.f;
-  t = warp_sum(t);
-  return t;   // every thread holds the block total
+struct GnGeom {
+  int Q, vpp, cg, C, T, chunks;
+};
+
+__device__ __forceinline__ void gn_slice(const GnParams& p, int chunks, int chunk, int* px0, int* px1) {
+  *px0 = (int)(((long long)p.pixels * chunk) / chunks);
+  *px1 = (int)(((long long)p.pixels * (chunk + 1)) / chunks);
 }
 
-__global__ void __launch_bounds__(1024) gn_silu_kernel(const GnParams p) {
-  __shared__ float red[32];
-  const int b = blockIdx.x >> 3, g = blockIdx.x & 7;
-  const int C = p.c0 + p.c1;
-  const int cg = C >> 3;
-  const int vpp = cg >> 2;                       // float4 per pixel of this group
-  const int nvec = p.pixels * vpp;
-  const int nt = blockDim.x;
-  const size_t pix0 = (size_t)b * p.pixels;
+// per-group sums of the per-thread partials of one CTA -> out8[g] valid in all threads after sync
+__device__ __forceinline__ void gn_group_reduce(float v, float* part, float* out8, int T, int Q, int vpp) {
+  const int tid = threadIdx.x;
+  part[tid] = v;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+  for (int gi = warp; gi < 8; gi += nwarps) {
+    const int RP = T / Q;
+    float a = 0.f;
+    for (int idx = lane; idx < RP * vpp; idx += 32) {
+      const int rr = idx / vpp, o = idx - rr * vpp;
+      a += part[rr * Q + gi * vpp + o];
+    }
+    a = warp_sum(a);
+    if (lane == 0) out8[gi] = a;
+  }
+  __syncthreads();
+}
 
-  auto load = [&](int i) -> float4 {
-    const int px = i / vpp;
-    const int c = g * cg + (i - px * vpp) * 4;
-    const float* src = (c < p.c0) ? p.src0 + (pix0 + px) * p.c0 + c
-                                  : p.src1 + (pix0 + px) * p.c1 + (c - p.c0);
-    return *reinterpret_cast<const float4*>(src);
-  };
+__global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p, int chunks, float* __restrict__ partial) {
+  __shared__ float part[512];
+  __shared__ float red[2][8];
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int C = p.c0 + p.c1, cg_ch = C >> 3, vpp = cg_ch >> 2, Q = C >> 2;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int c = (tid % Q) * 4;
+  int px0, px1;
+  gn_slice(p, chunks, chunk, &px0, &px1);
+  const int nvec = (px1 - px0) * Q;
+  const size_t pix_base = (size_t)b * p.pixels + px0;
+  const bool from0 = c < p.c0;
+  const float* src = from0 ? p.src0 + pix_base * p.c0 + c : p.src1 + pix_base * p.c1 + (c - p.c0);
+  const int src_ld = from0 ? p.c0 : p.c1;
 
   float4 cache[GN_CACHE];
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < GN_CACHE; ++j) {
-    const int i = threadIdx.x + j * nt;
+    const int i = tid + j * T;
     if (i < nvec) {
-      cache[j] = load(i);
+      cache[j] = *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld);
       s += (cache[j].x + cache[j].y) + (cache[j].z + cache[j].w);
     }
   }
-  for (int i = threadIdx.x + GN_CACHE * nt; i < nvec; i += nt) {
-    const float4 v = load(i);
+  for (int i = tid + GN_CACHE * T; i < nvec; i += T) {
+    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld);
     s += (v.x + v.y) + (v.z + v.w);
   }
-  const float inv_n = 1.0f / (float)(nvec * 4);
-  const float mean = block_sum(s, red) * inv_n;
-
-  float q = 0.f;
+  gn_group_reduce(s, part, red[0], T, Q, vpp);
+  const int g = c / cg_ch;
+  const float n_slice = (float)(px1 - px0) * (float)cg_ch;
+  const float mean = red[0][g] / n_slice;
+  float qs = 0.f;
 #pragma unroll
   for (int j = 0; j < GN_CACHE; ++j) {
-    const int i = threadIdx.x + j * nt;
+    const int i = tid + j * T;
     if (i < nvec) {
       const float dx = cache[j].x - mean, dy = cache[j].y - mean, dz = cache[j].z - mean,
                   dw = cache[j].w - mean;
-      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      qs += (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
   }
-  for (int i = threadIdx.x + GN_CACHE * nt; i < nvec; i += nt) {
-    const float4 v = load(i);
+  for (int i = tid + GN_CACHE * T; i < nvec; i += T) {
+    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld);
     const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    qs += (dx * dx + dy * dy) + (dz * dz + dw * dw);
   }
-  const float var = block_sum(q, red) * inv_n;
-  const float rstd = 1.0f / sqrtf(var + p.eps);
-  if (p.stats && threadIdx.x == 0) {
-    p.stats[(b * 8 + g) * 2 + 0] = mean;
-    p.stats[(b * 8 + g) * 2 + 1] = rstd;
+  gn_group_reduce(qs, part, red[1], T, Q, vpp);
+  if (tid < 8) {
+    float* o = partial + (((size_t)b * chunks + chunk) * 8 + tid) * 2;
+    o[0] = red[0][tid] / n_slice;   // slice mean
+    o[1] = red[1][tid];             // slice M2
   }
+}
 
-  auto emit = [&](int i, const float4& v) {
-    const int px = i / vpp;
-    const int c = g * cg + (i - px * vpp) * 4;
-    const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
-    const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
-    float y0 = (v.x - mean) * rstd * ga.x + be.x;
-    float y1 = (v.y - mean) * rstd * ga.y + be.y;
-    float y2 = (v.z - mean) * rstd * ga.z + be.z;
-    float y3 = (v.w - mean) * rstd * ga.w + be.w;
-    if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-    if (p.drop_scale) {
-      const float4 ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * C + c);
-      y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
+__global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p, int chunks, const float* __restrict__ partial) {
+  __shared__ float stat[2][8];
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int c = (tid % Q) * 4;
+  if (tid < 8) {
+    // Chan et al. combination of the slice statistics, fixed order
+    const float* pp = partial + ((size_t)b * chunks * 8 + tid) * 2;
+    float n_tot = 0.f, mean = 0.f, m2 = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      int a0, a1;
+      gn_slice(p, chunks, k, &a0, &a1);
+      const float nk = (float)(a1 - a0) * (float)cg_ch;
+      const float mk = pp[(size_t)k * 16], m2k = pp[(size_t)k * 16 + 1];
+      const float nn = n_tot + nk;
+      const float delta = mk - mean;
+      mean += delta * (nk / nn);
+      m2 += m2k + delta * delta * (n_tot * nk / nn);
+      n_tot = nn;
     }
-    const size_t o = (pix0 + px) * C + c;
+    stat[0][tid] = mean;
+    stat[1][tid] = 1.0f / sqrtf(m2 / n_tot + p.eps);
+    if (p.stats && chunk == 0) {
+      p.stats[(b * 8 + tid) * 2 + 0] = mean;
+      p.stats[(b * 8 + tid) * 2 + 1] = stat[1][tid];
+    }
+  }
+  __syncthreads();
+  int px0, px1;
+  gn_slice(p, chunks, chunk, &px0, &px1);
+  const int nvec = (px1 - px0) * Q;
+  const size_t pix_base = (size_t)b * p.pixels + px0;
+  const bool from0 = c < p.c0;
+  const float* src = from0 ? p.src0 + pix_base * p.c0 + c : p.src1 + pix_base * p.c1 + (c - p.c0);
+  const int src_ld = from0 ? p.c0 : p.c1;
+  const int g = c / cg_ch;
+  const float mean = stat[0][g], rstd = stat[1][g];
+  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * C + c);
+  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z,
+                                be.w - mean * sc.w);
+  __half* on = p.out_norm + pix_base * C + c;
+  __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
+#pragma unroll 4
+  for (int i = tid; i < nvec; i += T) {
+    const int row = i / Q;
+    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)row * src_ld);
+    float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z),
+          y3 = fmaf(v.w, sc.w, sh.w);
+    if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+    y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
+    const size_t o = (size_t)row * C;
     __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(p.out_norm + o) = u;
-    if (p.out_raw) {
+    *reinterpret_cast<uint2*>(on + o) = u;
+    if (orw) {
       __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
       u.x = *reinterpret_cast<uint32_t*>(&r0);
       u.y = *reinterpret_cast<uint32_t*>(&r1);
-      *reinterpret_cast<uint2*>(p.out_raw + o) = u;
+      *reinterpret_cast<uint2*>(orw + o) = u;
     }
-  };
-#pragma unroll
-  for (int j = 0; j < GN_CACHE; ++j) {
-    const int i = threadIdx.x + j * nt;
-    if (i < nvec) emit(i, cache[j]);
   }
-  for (int i = threadIdx.x + GN_CACHE * nt; i < nvec; i += nt) emit(i, load(i));
 }
 
-int gn_silu_enqueue(const GnParams& p, cudaStream_t st) {
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+int gn_chunks(int pixels, int C) {
+  const int Q = C / 4;
+  long nvec = (long)pixels * Q;
+  int chunks = (int)((nvec + 2047) / 2048);
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+  if (chunks > pixels) chunks = pixels;
+  return chunks < 1 ? 1 : chunks;
+}
+
+int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st) {
   const int C = p.c0 + p.c1;
   CM_CHECK(C % 32 == 0 && p.c0 % 4 == 0, "GroupNorm channels must be a multiple of 32 (C=%d)", C);
-  const int nvec = p.pixels * (C / 32);
-  int threads = ((nvec + GN_CACHE - 1) / GN_CACHE + 31) / 32 * 32;
-  if (threads < 64) threads = 64;
-  if (threads > 1024) threads = 1024;
-  gn_silu_kernel<<<p.B * 8, threads, 0, st>>>(p);
+  CM_CHECK(partial != nullptr, "GroupNorm scratch missing");
+  const int Q = C / 4;
+  const int L = Q / gcd_i(Q, 32) * 32;                 // lcm(Q, 32)
+  CM_CHECK(L <= 512, "GroupNorm: too many channels (C=%d)", C);
+  const int chunks = gn_chunks(p.pixels, C);
+  int T = (256 + L - 1) / L * L;
+  if (T > 512) T = 512 / L * L;
+  gn_stats_kernel<<<p.B * chunks, T, 0, st>>>(p, chunks, partial);
+  CM_CUDA(cudaGetLastError());
+  gn_apply_kernel<<<p.B * chunks, T, 0, st>>>(p, chunks, partial);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
 
 // =============================================================================================
-// first conv (K = 27*cin is tiny; memory-bound): one thread per output pixel, all couts.
+// first conv (K = 27*cin is tiny; memory-bound).  One CTA = a 4x4 block of grid sites x all L
+// frames; the haloed fp32 input patch and the weights are staged in shared memory once, then
+// every thread produces all couts of one output pixel (128 contiguous bytes per 32 couts).
 // =============================================================================================
+constexpr int FC_TS = 4;   // sites per tile edge
+
 template <int CIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ x, const float* __restrict__ past,
                   const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ out, int B, int H, int W, int P, int F, int cout) {
-  extern __shared__ float ws[];   // [27*CIN][cout], k = ci*27 + tap
+  extern __shared__ float sm[];
   constexpr int K = 27 * CIN;
+  const int L = P + F;
+  const int Lp = L + 2;
+  float* ws = sm;                                   // [K][cout], k = ci*27 + tap
+  float* patch = sm + K * cout;                     // [CIN][TS+2][TS+2][L+2]
+  const int tiles_w = (W + FC_TS - 1) / FC_TS, tiles_h = (H + FC_TS - 1) / FC_TS;
+  int bid = blockIdx.x;
+  const int tw_i = bid % tiles_w;
+  bid /= tiles_w;
+  const int th_i = bid % tiles_h;
+  const int b = bid / tiles_h;
+  const int h0 = th_i * FC_TS, w0 = tw_i * FC_TS;
+
   for (int idx = threadIdx.x; idx < K * cout; idx += blockDim.x) {
     const int k = idx / cout, co = idx - k * cout;
     ws[idx] = w[(size_t)co * K + k];
   }
+  const int patch_n = CIN * (FC_TS + 2) * (FC_TS + 2) * Lp;
+  for (int idx = threadIdx.x; idx < patch_n; idx += blockDim.x) {
+    int r = idx;
+    const int ll = r % Lp - 1;
+    r /= Lp;
+    const int ww = w0 + r % (FC_TS + 2) - 1;
+    r /= (FC_TS + 2);
+    const int hh = h0 + r % (FC_TS + 2) - 1;
+    const int ci = r / (FC_TS + 2);
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W && ll >= 0 && ll < L) {
+      const size_t plane = ((size_t)(b * CIN + ci) * H + hh) * W + ww;
+      v = (ll < P) ? past[plane * P + ll] : x[plane * F + (ll - P)];
+    }
+    patch[idx] = v;
+  }
   __syncthreads();
-  const int L = P + F;
-  const size_t total = (size_t)B * H * W * L;
-  const size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (m >= total) return;
-  int l = (int)(m % L);
-  size_t r = m / L;
-  const int wc = (int)(r % W);
-  r /= W;
-  const int h = (int)(r % H);
-  const int b = (int)(r / H);
 
+  const int l = threadIdx.x % L;
+  const int site = threadIdx.x / L;
+  const int sh = site / FC_TS, sw = site % FC_TS;
+  const int h = h0 + sh, wc = w0 + sw;
+  if (h >= H || wc >= W) return;
   float in[K];
 #pragma unroll
-  for (int ci = 0; ci < CIN; ++ci) {
+  for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-    for (int td = 0; td < 3; ++td) {
+    for (int td = 0; td < 3; ++td)
 #pragma unroll
-      for (int th = 0; th < 3; ++th) {
+      for (int th = 0; th < 3; ++th)
 #pragma unroll
-        for (int tw = 0; tw < 3; ++tw) {
-          const int hh = h + td - 1, ww = wc + th - 1, ll = l + tw - 1;
-          float v = 0.f;
-          if (hh >= 0 && hh < H && ww >= 0 && ww < W && ll >= 0 && ll < L) {
-            const size_t plane = ((size_t)(b * CIN + ci) * H + hh) * W + ww;
-            v = (ll < P) ? past[plane * P + ll] : x[plane * F + (ll - P)];
-          }
-          in[ci * 27 + (td * 3 + th) * 3 + tw] = v;
-        }
-      }
-    }
-  }
+        for (int tw = 0; tw < 3; ++tw)
+          in[ci * 27 + (td * 3 + th) * 3 + tw] =
+              patch[((ci * (FC_TS + 2) + sh + td) * (FC_TS + 2) + sw + th) * Lp + l + tw];
+  const size_t m = (((size_t)b * L + l) * H + h) * W + wc;      // internal layout [B, L, H, W, C]
   for (int co0 = 0; co0 < cout; co0 += 32) {
     float acc[32];
 #pragma unroll
@@ -294,13 +391,15 @@ int first_conv_enqueue(const float* x, const float* past, const float* w, const 
                        cudaStream_t st) {
   CM_CHECK(cin >= 1 && cin <= 4, "first conv supports 1..4 input channels (got %d)", cin);
   CM_CHECK(cout % 32 == 0, "first conv cout must be a multiple of 32");
-  const size_t total = (size_t)B * H * W * (P + F);
-  const int blocks = (int)((total + 127) / 128);
-  const size_t smem = (size_t)27 * cin * cout * sizeof(float);
+  const int L = P + F;
+  const int threads = FC_TS * FC_TS * L;
+  CM_CHECK(threads <= 256, "first conv: past+future frames must be <= 16 (got %d)", L);
+  const int blocks = B * ((H + FC_TS - 1) / FC_TS) * ((W + FC_TS - 1) / FC_TS);
+  const size_t smem = ((size_t)27 * cin * cout + (size_t)cin * (FC_TS + 2) * (FC_TS + 2) * (L + 2)) * sizeof(float);
 #define CM_FIRST(CI)                                                                           \
-  case CI: {                                                                                   \
-    first_conv_kernel<CI><<<blocks, 128, smem, st>>>(x, past, w, bias, out, B, H, W, P, F, cout); \
-  } break;
+  case CI:                                                                                     \
+    first_conv_kernel<CI><<<blocks, threads, smem, st>>>(x, past, w, bias, out, B, H, W, P, F, cout); \
+    break;
   switch (cin) {
     CM_FIRST(1) CM_FIRST(2) CM_FIRST(3) CM_FIRST(4)
   }
@@ -354,7 +453,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
           const int ll = l + tw - 1;
           if (ll < 0 || ll >= p.L) continue;
           const int tap = (td * 3 + th) * 3 + tw;
-          const __half* ap = p.act + ((((size_t)b * p.H + hh) * p.W + ww) * p.L + ll) * cin;
+          const __half* ap = p.act + ((((size_t)b * p.L + ll) * p.H + hh) * p.W + ww) * cin;
           for (int c0 = sub * 8; c0 < cin; c0 += 32) {
             const uint4 u = *reinterpret_cast<const uint4*>(ap + c0);
             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
@@ -502,15 +601,17 @@ int temb_enqueue(const TembParams& p, cudaStream_t st) {
 // =============================================================================================
 // attention core (S <= a few hundred tokens: whole K/V of one (sample, head) lives in smem)
 // =============================================================================================
-__global__ void __launch_bounds__(128)
+constexpr int ATTN_WARPS = 8;
+
+__global__ void __launch_bounds__(ATTN_WARPS * 32)
 attn_core_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx, int S, int C, int heads) {
   extern __shared__ float sm[];
   const int dh = C / heads;
   const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
-  float* Ks = sm;                       // [S][dh+1]
+  float* Ks = sm;                          // [S][dh+1]
   float* Vs = Ks + (size_t)S * (dh + 1);   // [S][dh]
-  float* Qs = Vs + (size_t)S * dh;      // [4][dh]
-  float* Pw = Qs + 4 * dh;              // [4][S]
+  float* Qs = Vs + (size_t)S * dh;         // [ATTN_WARPS][dh]
+  float* Pw = Qs + ATTN_WARPS * dh;        // [ATTN_WARPS][S]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* base = qkv + (size_t)b * S * 3 * C;
   for (int idx = threadIdx.x; idx < S * dh; idx += blockDim.x) {
@@ -522,14 +623,20 @@ attn_core_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx, int S,
   const float scale = rsqrtf((float)dh);
   float* q = Qs + warp * dh;
   float* pw = Pw + warp * S;
-  for (int i = warp; i < S; i += 4) {
+  for (int i = warp; i < S; i += ATTN_WARPS) {
     for (int d = lane; d < dh; d += 32) q[d] = base[(size_t)i * 3 * C + hd * dh + d] * scale;
     __syncwarp();
     float mx = -INFINITY;
     for (int j = lane; j < S; j += 32) {
       const float* kr = Ks + j * (dh + 1);
-      float a = 0.f;
-      for (int d = 0; d < dh; ++d) a = fmaf(q[d], kr[d], a);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int d = 0; d < dh; d += 4) {
+        a0 = fmaf(q[d], kr[d], a0);
+        a1 = fmaf(q[d + 1], kr[d + 1], a1);
+        a2 = fmaf(q[d + 2], kr[d + 2], a2);
+        a3 = fmaf(q[d + 3], kr[d + 3], a3);
+      }
+      const float a = (a0 + a1) + (a2 + a3);
       pw[j] = a;
       mx = fmaxf(mx, a);
     }
@@ -544,9 +651,14 @@ attn_core_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx, int S,
     __syncwarp();
     const float inv = 1.0f / sum;
     for (int d = lane; d < dh; d += 32) {
-      float a = 0.f;
-      for (int j = 0; j < S; ++j) a = fmaf(pw[j], Vs[j * dh + d], a);
-      ctx[((size_t)b * S + i) * C + hd * dh + d] = __float2half_rn(a * inv);
+      float a0 = 0.f, a1 = 0.f;
+      int j = 0;
+      for (; j + 1 < S; j += 2) {
+        a0 = fmaf(pw[j], Vs[j * dh + d], a0);
+        a1 = fmaf(pw[j + 1], Vs[(j + 1) * dh + d], a1);
+      }
+      if (j < S) a0 = fmaf(pw[j], Vs[j * dh + d], a0);
+      ctx[((size_t)b * S + i) * C + hd * dh + d] = __float2half_rn((a0 + a1) * inv);
     }
     __syncwarp();
   }
@@ -554,11 +666,12 @@ attn_core_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx, int S,
 
 int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int heads,
                       cudaStream_t st) {
-  CM_CHECK(C % heads == 0, "embed dim %d not divisible by heads %d", C, heads);
+  CM_CHECK(C % heads == 0 && (C / heads) % 4 == 0, "embed dim %d / heads %d unsupported", C, heads);
   const int dh = C / heads;
-  const size_t smem = ((size_t)S * (dh + 1) + (size_t)S * dh + 4 * dh + 4 * (size_t)S) * sizeof(float);
+  const size_t smem = ((size_t)S * (dh + 1) + (size_t)S * dh + ATTN_WARPS * dh + ATTN_WARPS * (size_t)S) *
+                      sizeof(float);
   CM_CHECK(smem <= 200 * 1024, "attention tile too large for shared memory (S=%d dh=%d)", S, dh);
-  attn_core_kernel<<<B * heads, 128, smem, st>>>(qkv, ctx, S, C, heads);
+  attn_core_kernel<<<B * heads, ATTN_WARPS * 32, smem, st>>>(qkv, ctx, S, C, heads);
   CM_CUDA(cudaGetLastError());
   return 0;
 }

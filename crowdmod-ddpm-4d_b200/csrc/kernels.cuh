@@ -8,11 +8,13 @@ namespace cm {
 // ---- weight packing (fp32 torch layouts -> fp16 K-major rows, optional hi+lo split) ----
 // w: [cout][cin][taps] (nn.Conv3d weight flattened; taps = 27 or 1), wx: [cout][cinx] or null.
 // dst: [terms*cout][taps*cin + cinx], column = tap*cin + ci, then 27*cin + cx.
+// perm = 1: w is a reference nn.Conv3d weight over (rows, cols, time) and the activations are
+// stored [B, time, rows, cols, C]; perm = 0: w taps are ordered like the activation dims.
 int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, int cin, int cinx,
-                      int taps, int terms, cudaStream_t st);
+                      int taps, int terms, int perm, cudaStream_t st);
 // nearest-x2 + k3 conv folded into 8 phase convs with 2x2x2 combined taps
 // (layers.py:92-94).  dst: [terms*cout][64*cin], column = phase*8*cin + tap8*cin + ci.
-int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms,
+int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms, int perm,
                           cudaStream_t st);
 
 // ---- GroupNorm(8) [+SiLU] [+Dropout3d scale] -> fp16 operand (layers.py:30,41,57,70; :9,14) ----
@@ -30,18 +32,20 @@ struct GnParams {
   __half* out_raw;          // optional raw fp16 copy of the (concatenated) input
   float* stats;             // optional [B][8][2] (mean, rstd) for backward
 };
-int gn_silu_enqueue(const GnParams& p, cudaStream_t st);
+// `partial`: scratch of B * gn_chunks(pixels, C) * 16 floats (slice statistics)
+int gn_chunks(int pixels, int C);
+int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st);
 
 // ---- first conv: 3(+)->base channels straight from the API layout (unet.py:32,138,144) ----
 // x: [B][cin][H][W][F] fp32, past: [B][cin][H][W][P] fp32 (virtual concat along time),
-// w: [cout][cin][3][3][3], out: fp32 channels-last [B][H][W][P+F][cout].
+// w: [cout][cin][3][3][3], out: fp32 channels-last, time-major [B][P+F][H][W][cout].
 int first_conv_enqueue(const float* x, const float* past, const float* w, const float* bias,
                        float* out, int B, int H, int W, int P, int F, int cin, int cout,
                        cudaStream_t st);
 
 // ---- final conv base->3 fused with the DDPM/DDIM update (unet.py:118-122,165-167; ddpm.py:25-38,262-265) ----
 struct FinalParams {
-  const __half* act;     // fp16 channels-last [B][H][W][L][cin], already GN+SiLU'ed
+  const __half* act;     // fp16 channels-last, time-major [B][L][H][W][cin], already GN+SiLU'ed
   const float* w;        // [cout][cin][27] fp32
   const float* bias;
   int B, H, W, L, P;     // L = P + F; only frames l >= P are produced

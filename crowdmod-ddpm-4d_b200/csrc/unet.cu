@@ -54,7 +54,8 @@ struct Op {
 };
 
 struct Level {
-  int D, H, W;   // grid rows, grid cols, frames
+  int D, H, W;   // frames, grid rows, grid cols: activations are stored [B, frames, rows, cols, C]
+                 // (cols innermost: TMA im2col cost grows with the number of W-rows a tile spans)
   int pps() const { return D * H * W; }
 };
 
@@ -88,6 +89,7 @@ struct cm_unet {
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   float* temb_batch = nullptr;          // [batch][temb_ld]
+  float* gn_partial = nullptr;          // [batch][GN chunks][8][2] slice statistics (reused by every GN)
   int* d_step = nullptr;                // [0] step index, [1] current timestep
   int* d_tsteps = nullptr;
   float* d_coef = nullptr;
@@ -244,7 +246,7 @@ int build_plan(cm_unet* u) {
   CM_CHECK(c.rows % div == 0 && c.cols % div == 0 && L % div == 0,
            "rows/cols/(past+future) must be divisible by 2^(levels-1)=%d (skip concat, unet.py:160)", div);
   u->levels.resize(c.num_levels);
-  for (int l = 0; l < c.num_levels; ++l) u->levels[l] = {c.rows >> l, c.cols >> l, L >> l};
+  for (int l = 0; l < c.num_levels; ++l) u->levels[l] = {L >> l, c.rows >> l, c.cols >> l};
 
   const int base = c.base_channels, E = base * c.time_multiple;
   // state_dict order: time_embeddings, first, encoder, bottleneck, decoder, final (unet.py:27-122)
@@ -364,6 +366,8 @@ int reserve(cm_unet* u, int batch) {
   }
   const size_t temb_off = off;
   off = align_up(off + (size_t)batch * u->temb_ld * 4, 1024);
+  const size_t gnp_off = off;
+  off = align_up(off + (size_t)batch * 64 * 16 * 4, 1024);
   CM_CUDA(cudaMalloc(&u->arena, off));
   CM_CUDA(cudaMemset(u->arena, 0, off));
   u->arena_bytes = off;
@@ -373,6 +377,7 @@ int reserve(cm_unet* u, int batch) {
     t.p16 = t.need16 ? reinterpret_cast<__half*>(u->arena + o16[i]) : nullptr;
   }
   u->temb_batch = reinterpret_cast<float*>(u->arena + temb_off);
+  u->gn_partial = reinterpret_cast<float*>(u->arena + gnp_off);
   if (!u->d_step) CM_CUDA(cudaMalloc(&u->d_step, 2 * sizeof(int)));
   u->reserved_batch = batch;
   return 0;
@@ -430,7 +435,7 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         const Level& l0 = u->levels[0];
         if (int e = first_conv_enqueue(rc.future, rc.past, u->params[u->p_first_w].ptr,
                                        u->params[u->p_first_b].ptr, u->tens[op.out].p32, rc.batch,
-                                       l0.D, l0.H, c.past_len, c.future_len, c.in_channels,
+                                       l0.H, l0.W, c.past_len, c.future_len, c.in_channels,
                                        c.base_channels, st))
           return e;
       } break;
@@ -448,7 +453,8 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         g.silu = op.silu;
         g.out_norm = u->tens[op.out_norm].p16;
         g.out_raw = op.out_raw >= 0 ? u->tens[op.out_raw].p16 : nullptr;
-        if (int e = gn_silu_enqueue(g, st)) return e;
+        if (int e = gn_silu_enqueue(g, u->gn_partial, st)) return e;
+        if (launches) ++*launches;   // two kernels
       } break;
       case OP_CONV: {
         ConvLaunch L = op.launch;
@@ -474,9 +480,9 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         f.w = u->params[u->p_final_w].ptr;
         f.bias = u->params[u->p_final_b].ptr;
         f.B = rc.batch;
-        f.H = l0.D;
-        f.W = l0.H;
-        f.L = l0.W;
+        f.H = l0.H;
+        f.W = l0.W;
+        f.L = l0.D;
         f.P = c.past_len;
         f.cin = op.cin;
         f.cout = c.out_channels;
@@ -584,11 +590,11 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
     __half* dst = u->wpack + op.wpack_off;
     const float* w = u->params[op.w].ptr;
     if (op.mode == 2) {
-      if (int e = pack_upsample_weights(w, dst, op.cout, op.cin, terms, st)) return e;
+      if (int e = pack_upsample_weights(w, dst, op.cout, op.cin, terms, 1, st)) return e;
     } else {
       const float* wx = op.wx >= 0 ? u->params[op.wx].ptr : nullptr;
       if (int e = pack_conv_weights(w, wx, dst, op.cout, op.cin, op.cin_extra, op.mode == 3 ? 1 : 27,
-                                    terms, st))
+                                    terms, 1, st))
         return e;
     }
   }
@@ -644,7 +650,12 @@ int cm_unet_reserve(cm_unet* u, int batch, int64_t* bytes) {
   return 0;
 }
 
-int cm_unet_launches_per_forward(const cm_unet* u) { return u ? (int)u->ops.size() + 1 : -1; }
+int cm_unet_launches_per_forward(const cm_unet* u) {
+  if (!u) return -1;
+  int n = 1;   // time-embedding kernel
+  for (const Op& op : u->ops) n += (op.type == OP_GN) ? 2 : 1;
+  return n;
+}
 double cm_unet_flops_per_sample(const cm_unet* u) { return u ? u->flops_per_sample : 0.0; }
 int64_t cm_last_chain_launches(const cm_unet* u) { return u ? u->last_chain_launches : -1; }
 
@@ -824,7 +835,7 @@ int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
     cudaGraphDestroy(g);
     u->graph_key = *a;
   } else {
-    per_step = (int64_t)u->ops.size() + 1;
+    per_step = (int64_t)cm_unet_launches_per_forward(u);   // ops (GroupNorm = 2 kernels) + step advance
   }
   for (int i = 0; i < a->nsteps; ++i) CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
   u->last_chain_launches = per_step * a->nsteps;

@@ -11,7 +11,7 @@
  *
  * Tensor conventions (reference utils/dataset.py:48-53, models/backbones/unet.py:133-138):
  *   API tensors   : fp32, contiguous, [B, C, H(rows), W(cols), L(time)], time fastest.
- *   internal      : channels-last [B, H, W, L, C]; fp32 residual stream, fp16 MMA operands.
+ *   internal      : channels-last, time-major [B, L, H, W, C]; fp32 residual stream, fp16 MMA operands.
  */
 #ifndef CROWDMOD_B200_H
 #define CROWDMOD_B200_H

@@ -186,11 +186,11 @@ def test_first_conv(nat, B, H, W, P, Fu, cin, cout):
     past = torch.randn(B, cin, H, W, P, device="cuda", generator=g)
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
     b = torch.randn(cout, device="cuda", generator=g)
-    out = torch.zeros(B, H, W, P + Fu, cout, device="cuda")
+    out = torch.zeros(B, P + Fu, H, W, cout, device="cuda")
     nat.check(nat.lib().cm_op_first_conv(nat.ptr(x), nat.ptr(past), nat.ptr(w), nat.ptr(b), nat.ptr(out),
                                          B, H, W, P, Fu, cin, cout, nat.current_stream()))
     torch.cuda.synchronize()
-    ref = F.conv3d(torch.cat([past, x], dim=4), w, b, padding=1).permute(0, 2, 3, 4, 1)
+    ref = F.conv3d(torch.cat([past, x], dim=4), w, b, padding=1).permute(0, 4, 2, 3, 1)   # [B, L, H, W, C]
     assert rel_l2(out, ref) <= 1e-5
 
 
@@ -198,12 +198,12 @@ def test_first_conv(nat, B, H, W, P, Fu, cin, cout):
 def test_final_conv(nat, B, H, W, P, Fu, cin, cout):
     g = torch.Generator(device="cuda").manual_seed(4)
     L = P + Fu
-    act = torch.randn(B, H, W, L, cin, device="cuda", generator=g).half()
+    act = torch.randn(B, L, H, W, cin, device="cuda", generator=g).half()   # internal [B, L, H, W, C]
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
     b = torch.randn(cout, device="cuda", generator=g)
     eps = torch.zeros(B, cout, H, W, Fu, device="cuda")
     nat.check(nat.lib().cm_op_final_conv(nat.ptr(act), nat.ptr(w), nat.ptr(b), nat.ptr(eps), B, H, W, L, P,
                                          cin, cout, nat.current_stream()))
     torch.cuda.synchronize()
-    ref = F.conv3d(act.float().permute(0, 4, 1, 2, 3), w, b, padding=1)[..., P:]
+    ref = F.conv3d(act.float().permute(0, 4, 2, 3, 1), w, b, padding=1)[..., P:]
     assert rel_l2(eps, ref) <= 1e-5
