@@ -123,15 +123,7 @@ int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, const fl
   g.gamma = gamma; g.beta = beta; g.B = B; g.pixels = pixels; g.eps = eps; g.silu = silu;
   g.out_norm = static_cast<__half*>(out_norm16);
   g.out_raw = static_cast<__half*>(out_raw16);
-  float* partial = nullptr;
-  CM_CUDA(cudaMalloc(&partial, (size_t)B * gn_chunks(pixels, c0 + c1) * 16 * sizeof(float)));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = gn_silu_enqueue(g, partial, st);
-  cudaError_t se = cudaStreamSynchronize(st);
-  cudaFree(partial);
-  if (rc) return rc;
-  CM_CUDA(se);
-  return 0;
+  return gn_silu_enqueue(g, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream) {

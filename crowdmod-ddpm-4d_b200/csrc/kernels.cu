@@ -3,6 +3,8 @@
 #include "kernels.cuh"
 #include "conv_umma.cuh"
 
+#include <cooperative_groups.h>
+
 
 namespace cm {
 
@@ -143,77 +145,101 @@ __device__ __forceinline__ void gn_group_reduce(float v, float* part, float* out
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p, int chunks, float* __restrict__ partial) {
-  __shared__ float part[512];
-  __shared__ float red[2][8];
-  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+// Single-launch variant: one thread-block cluster (GN_CLUSTER CTAs) per sample; the slice
+// statistics are exchanged through distributed shared memory instead of global scratch, so a
+// GroupNorm is ONE kernel (the per-launch latency floor matters: there are 27 per step).
+constexpr int GN_CLUSTER = 8;
+
+__global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float part[2][384];
+  __shared__ float slice_stat[8][2];       // this CTA's (mean, M2) per group, read by peers
+  __shared__ float all_stat[GN_CLUSTER][8][2];
+  __shared__ float stat[2][8];
+  const int CS = (int)cluster.num_blocks();
+  const int chunk = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS;
   const int C = p.c0 + p.c1, cg_ch = C >> 3, vpp = cg_ch >> 2, Q = C >> 2;
   const int T = blockDim.x, tid = threadIdx.x;
   const int c = (tid % Q) * 4;
+  const int g = c / cg_ch;
   int px0, px1;
-  gn_slice(p, chunks, chunk, &px0, &px1);
+  gn_slice(p, CS, chunk, &px0, &px1);
   const int nvec = (px1 - px0) * Q;
   const size_t pix_base = (size_t)b * p.pixels + px0;
   const bool from0 = c < p.c0;
   const float* src = from0 ? p.src0 + pix_base * p.c0 + c : p.src1 + pix_base * p.c1 + (c - p.c0);
   const int src_ld = from0 ? p.c0 : p.c1;
 
+  // Single pass over the slice with SHIFTED sums: k = first element of this group in the slice
+  // (a sample of the distribution, so (mean - k)^2 ~ var and the subtraction below is benign).
+  float kshift = 0.f;
+  if (nvec > 0) {
+    const int cgf = g * cg_ch;
+    kshift = (cgf < p.c0) ? p.src0[pix_base * p.c0 + cgf] : p.src1[pix_base * p.c1 + (cgf - p.c0)];
+  }
   float4 cache[GN_CACHE];
-  float s = 0.f;
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < GN_CACHE; ++j) {
     const int i = tid + j * T;
     if (i < nvec) {
       cache[j] = *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld);
-      s += (cache[j].x + cache[j].y) + (cache[j].z + cache[j].w);
+      const float dx = cache[j].x - kshift, dy = cache[j].y - kshift, dz = cache[j].z - kshift,
+                  dw = cache[j].w - kshift;
+      s1 += (dx + dy) + (dz + dw);
+      s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
   }
   for (int i = tid + GN_CACHE * T; i < nvec; i += T) {
     const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld);
-    s += (v.x + v.y) + (v.z + v.w);
+    const float dx = v.x - kshift, dy = v.y - kshift, dz = v.z - kshift, dw = v.w - kshift;
+    s1 += (dx + dy) + (dz + dw);
+    s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
   }
-  gn_group_reduce(s, part, red[0], T, Q, vpp);
-  const int g = c / cg_ch;
-  const float n_slice = (float)(px1 - px0) * (float)cg_ch;
-  const float mean = red[0][g] / n_slice;
-  float qs = 0.f;
-#pragma unroll
-  for (int j = 0; j < GN_CACHE; ++j) {
-    const int i = tid + j * T;
-    if (i < nvec) {
-      const float dx = cache[j].x - mean, dy = cache[j].y - mean, dz = cache[j].z - mean,
-                  dw = cache[j].w - mean;
-      qs += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  part[0][tid] = s1;
+  part[1][tid] = s2;
+  __syncthreads();
+  {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+    for (int gi = warp; gi < 8; gi += nwarps) {
+      const int RP = T / Q;
+      float a1 = 0.f, a2 = 0.f;
+      for (int idx = lane; idx < RP * vpp; idx += 32) {
+        const int rr = idx / vpp, o = idx - rr * vpp;
+        a1 += part[0][rr * Q + gi * vpp + o];
+        a2 += part[1][rr * Q + gi * vpp + o];
+      }
+      a1 = warp_sum(a1);
+      a2 = warp_sum(a2);
+      if (lane == 0) {
+        const float n_slice = fmaxf((float)(px1 - px0) * (float)cg_ch, 1.f);
+        const float d = a1 / n_slice;                       // slice mean - k
+        // every thread of group gi used the same k: recover it from the first channel of the group
+        const int cgf = gi * cg_ch;
+        float k = 0.f;
+        if (nvec > 0) k = (cgf < p.c0) ? p.src0[pix_base * p.c0 + cgf] : p.src1[pix_base * p.c1 + (cgf - p.c0)];
+        slice_stat[gi][0] = k + d;                          // slice mean
+        slice_stat[gi][1] = fmaxf(a2 - a1 * d, 0.f);        // slice M2 = S2 - n d^2
+      }
     }
   }
-  for (int i = tid + GN_CACHE * T; i < nvec; i += T) {
-    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld);
-    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-    qs += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  cluster.sync();
+  for (int idx = tid; idx < CS * 16; idx += T) {   // parallel DSMEM gather of every slice's statistics
+    const int k = idx >> 4, e = idx & 15;
+    (&all_stat[k][0][0])[e] = cluster.map_shared_rank(&slice_stat[0][0], k)[e];
   }
-  gn_group_reduce(qs, part, red[1], T, Q, vpp);
+  __syncthreads();
   if (tid < 8) {
-    float* o = partial + (((size_t)b * chunks + chunk) * 8 + tid) * 2;
-    o[0] = red[0][tid] / n_slice;   // slice mean
-    o[1] = red[1][tid];             // slice M2
-  }
-}
-
-__global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p, int chunks, const float* __restrict__ partial) {
-  __shared__ float stat[2][8];
-  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2;
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int c = (tid % Q) * 4;
-  if (tid < 8) {
-    // Chan et al. combination of the slice statistics, fixed order
-    const float* pp = partial + ((size_t)b * chunks * 8 + tid) * 2;
+    // Chan et al. combination over the cluster's slices, fixed order (bit-reproducible)
     float n_tot = 0.f, mean = 0.f, m2 = 0.f;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = 0; k < CS; ++k) {
       int a0, a1;
-      gn_slice(p, chunks, k, &a0, &a1);
+      gn_slice(p, CS, k, &a0, &a1);
       const float nk = (float)(a1 - a0) * (float)cg_ch;
-      const float mk = pp[(size_t)k * 16], m2k = pp[(size_t)k * 16 + 1];
+      if (nk == 0.f) continue;
+      const float mk = all_stat[k][tid][0], m2k = all_stat[k][tid][1];
       const float nn = n_tot + nk;
       const float delta = mk - mean;
       mean += delta * (nk / nn);
@@ -228,14 +254,6 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p, int chu
     }
   }
   __syncthreads();
-  int px0, px1;
-  gn_slice(p, chunks, chunk, &px0, &px1);
-  const int nvec = (px1 - px0) * Q;
-  const size_t pix_base = (size_t)b * p.pixels + px0;
-  const bool from0 = c < p.c0;
-  const float* src = from0 ? p.src0 + pix_base * p.c0 + c : p.src1 + pix_base * p.c1 + (c - p.c0);
-  const int src_ld = from0 ? p.c0 : p.c1;
-  const int g = c / cg_ch;
   const float mean = stat[0][g], rstd = stat[1][g];
   const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
   const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
@@ -246,15 +264,12 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p, int chu
                                 be.w - mean * sc.w);
   __half* on = p.out_norm + pix_base * C + c;
   __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
-#pragma unroll 4
-  for (int i = tid; i < nvec; i += T) {
-    const int row = i / Q;
-    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)row * src_ld);
+  auto emit = [&](int i, const float4& v) {
     float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z),
           y3 = fmaf(v.w, sc.w, sh.w);
     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
     y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
-    const size_t o = (size_t)row * C;
+    const size_t o = (size_t)(i / Q) * C;
     __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -266,34 +281,49 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p, int chu
       u.y = *reinterpret_cast<uint32_t*>(&r1);
       *reinterpret_cast<uint2*>(orw + o) = u;
     }
+  };
+#pragma unroll
+  for (int j = 0; j < GN_CACHE; ++j) {
+    const int i = tid + j * T;
+    if (i < nvec) emit(i, cache[j]);
   }
+  for (int i = tid + GN_CACHE * T; i < nvec; i += T)
+    emit(i, *reinterpret_cast<const float4*>(src + (size_t)(i / Q) * src_ld));
+  cluster.sync();   // peers may still be reading slice_stat through DSMEM
 }
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-int gn_chunks(int pixels, int C) {
-  const int Q = C / 4;
-  long nvec = (long)pixels * Q;
-  int chunks = (int)((nvec + 2047) / 2048);
-  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  if (chunks > pixels) chunks = pixels;
-  return chunks < 1 ? 1 : chunks;
-}
+int gn_chunks(int pixels, int C) { (void)pixels; (void)C; return GN_CLUSTER; }
 
 int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st) {
+  (void)partial;
   const int C = p.c0 + p.c1;
   CM_CHECK(C % 32 == 0 && p.c0 % 4 == 0, "GroupNorm channels must be a multiple of 32 (C=%d)", C);
-  CM_CHECK(partial != nullptr, "GroupNorm scratch missing");
   const int Q = C / 4;
   const int L = Q / gcd_i(Q, 32) * 32;                 // lcm(Q, 32)
-  CM_CHECK(L <= 512, "GroupNorm: too many channels (C=%d)", C);
-  const int chunks = gn_chunks(p.pixels, C);
-  int T = (256 + L - 1) / L * L;
-  if (T > 512) T = 512 / L * L;
-  gn_stats_kernel<<<p.B * chunks, T, 0, st>>>(p, chunks, partial);
-  CM_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<p.B * chunks, T, 0, st>>>(p, chunks, partial);
-  CM_CUDA(cudaGetLastError());
+  CM_CHECK(L <= 384, "GroupNorm: too many channels (C=%d)", C);
+  int CS = GN_CLUSTER;
+  while (CS > 1 && p.pixels < 2 * CS) CS >>= 1;
+  // threads: a multiple of lcm(C/4, 32); ~GN_CACHE cached vectors per thread, 512 at most
+  const long nvec_cta = ((long)(p.pixels + CS - 1) / CS) * Q;
+  int T = (int)(((nvec_cta + GN_CACHE - 1) / GN_CACHE + L - 1) / L * L);
+  if (T < L) T = L;
+  if (T < 128 && 128 % L == 0) T = 128;
+  if (T > 384) T = 384 / L * L;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.B * CS);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CM_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, p));
   return 0;
 }
 

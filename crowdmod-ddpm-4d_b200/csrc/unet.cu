@@ -454,7 +454,6 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         g.out_norm = u->tens[op.out_norm].p16;
         g.out_raw = op.out_raw >= 0 ? u->tens[op.out_raw].p16 : nullptr;
         if (int e = gn_silu_enqueue(g, u->gn_partial, st)) return e;
-        if (launches) ++*launches;   // two kernels
       } break;
       case OP_CONV: {
         ConvLaunch L = op.launch;
@@ -653,7 +652,7 @@ int cm_unet_reserve(cm_unet* u, int batch, int64_t* bytes) {
 int cm_unet_launches_per_forward(const cm_unet* u) {
   if (!u) return -1;
   int n = 1;   // time-embedding kernel
-  for (const Op& op : u->ops) n += (op.type == OP_GN) ? 2 : 1;
+  n += (int)u->ops.size();
   return n;
 }
 double cm_unet_flops_per_sample(const cm_unet* u) { return u ? u->flops_per_sample : 0.0; }
