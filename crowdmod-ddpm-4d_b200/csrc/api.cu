@@ -7,8 +7,10 @@
 #include <string>
 
 #include "../../include/crowdmod_b200.h"
+#include "backward.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "wgrad_umma.cuh"
 
 namespace cm {
 
@@ -148,6 +150,86 @@ int cm_op_final_conv(const void* act16, const float* w, const float* bias, float
   f.w = w; f.bias = bias; f.B = B; f.H = H; f.W = W; f.L = L; f.P = P; f.cin = cin; f.cout = cout;
   f.eps_out = eps_out;
   return final_conv_enqueue(f, static_cast<cudaStream_t>(stream));
+}
+
+
+int cm_op_conv3d_dgrad(int mode, const void* dout16, int B, int D, int H, int W, int cin,
+                       const float* w, int cout, int terms, float* dx32, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = kernels_init()) return e;
+  if (int e = backward_init()) return e;
+  CM_CHECK(mode >= 0 && mode <= 3, "bad forward conv mode %d", mode);
+  int od = D, oh = H, ow = W;   // forward output grid
+  if (mode == 1) { od = (D - 1) / 2 + 1; oh = (H - 1) / 2 + 1; ow = (W - 1) / 2 + 1; }
+  else if (mode == 2) { od = 2 * D; oh = 2 * H; ow = 2 * W; }
+  const size_t ktot = dgrad_packed_k(mode, cout);
+  __half* wp = nullptr;
+  CM_CUDA(cudaMalloc(&wp, (size_t)terms * cin * ktot * sizeof(__half) + 16));
+  int rc = pack_dgrad_weights(mode, w, wp, cout, cin, terms, 0, st);
+  ConvLaunch L;
+  if (!rc) rc = conv_prepare(&L, dgrad_mode_of(mode), static_cast<const __half*>(dout16), B, od, oh, ow, cout,
+                             nullptr, 0, wp, cin, terms);
+  if (!rc) {
+    L.p.out32 = dx32;
+    rc = conv_enqueue(L, st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(wp);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
+}
+
+int cm_op_conv3d_wgrad(int mode, const void* act16, int B, int D, int H, int W, int cin,
+                       const void* extra16, int cin_extra, const void* dout16, int cout, float* dw,
+                       float* dwx, int impl, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = kernels_init()) return e;
+  if (int e = backward_init()) return e;
+  CM_CHECK(mode >= 0 && mode <= 3, "bad forward conv mode %d", mode);
+  const size_t gel = wgrad_g_elems(mode, cin, cin_extra, cout);
+  float* G = nullptr;
+  CM_CUDA(cudaMalloc(&G, gel * sizeof(float)));
+  CM_CUDA(cudaMemsetAsync(G, 0, gel * sizeof(float), st));
+  int rc = 0;
+  if (impl == 0) {
+    WgradLaunch L;
+    rc = wgrad_prepare(&L, mode, static_cast<const __half*>(act16), B, D, H, W, cin,
+                       static_cast<const __half*>(extra16), cin_extra, static_cast<const __half*>(dout16),
+                       cout, G);
+    if (!rc) rc = wgrad_enqueue(L, st);
+    if (!rc) {
+      if (const char* e = getenv("CM_DBG_REPS")) {
+        const int reps = atoi(e);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaStreamSynchronize(st);
+        cudaEventRecord(a, st);
+        for (int i = 0; i < reps && !rc; ++i) rc = wgrad_enqueue(L, st);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "CM_DBG wgrad mode=%d M=%d cin=%d cout=%d bkc=%d bn=%d splits=%d grid=%d,%d,%d: %.2f us/launch (%.1f TF/s)\n",
+                mode, L.p.M, cin, cout, L.bkc, L.bn, L.p.splits, L.grid.x, L.grid.y, L.grid.z, ms * 1e3f / reps,
+                L.flops / (ms * 1e-3 / reps) * 1e-12);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        cudaMemsetAsync(G, 0, gel * sizeof(float), st);
+        rc = wgrad_enqueue(L, st);
+      }
+    }
+  } else {
+    rc = wgrad_ref_enqueue(mode, static_cast<const __half*>(act16), static_cast<const __half*>(extra16),
+                           static_cast<const __half*>(dout16), G, B, D, H, W, cin, cin_extra, cout, st);
+  }
+  if (!rc) rc = unpack_wgrad_enqueue(mode, G, dw, dwx, cout, cin, cin_extra, 0, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(G);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,914 @@
+// Backward-pass kernels of the UNet hot path (training).  Contracts in backward.cuh; the
+// reference ops they differentiate are cited there and per kernel below.
+#include "backward.cuh"
+
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace cm {
+
+int wgrad_init();   // conv_umma.cu
+
+namespace {
+
+__device__ __forceinline__ int src_tap(int tap, int perm) {
+  // tap = (d*3 + h)*3 + w in activation-dim order (time, rows, cols); the reference's
+  // nn.Conv3d weight is over (rows, cols, time): source index = (h*3 + w)*3 + d.
+  return perm ? (((tap / 3) % 3) * 3 + (tap % 3)) * 3 + tap / 9 : tap;
+}
+
+__device__ __forceinline__ float silu_grad(float y) {
+  const float s = 1.0f / (1.0f + __expf(-y));
+  return s * (1.0f + y * (1.0f - s));
+}
+
+inline int grid_for(size_t total, int threads, int cap) {
+  size_t b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b < (size_t)cap ? b : (size_t)cap);
+}
+
+// threads per CTA for a [pixels][C] channels-last sweep in float4 units: a multiple of Q = C/4 so
+// that every thread keeps the same channel quad.
+inline int sweep_threads(int Q) {
+  int T = Q * (256 / Q > 0 ? 256 / Q : 1);
+  return T;
+}
+
+}  // namespace
+
+// =============================================================================================
+// dgrad weight packing
+// =============================================================================================
+int dgrad_mode_of(int fwd_mode) {
+  switch (fwd_mode) {
+    case 0: return 0;
+    case 1: return 2;
+    case 2: return 4;
+    default: return 3;
+  }
+}
+size_t dgrad_packed_k(int fwd_mode, int cout_f) {
+  switch (fwd_mode) {
+    case 0: return (size_t)27 * cout_f;
+    case 1:
+    case 2: return (size_t)64 * cout_f;
+    default: return (size_t)cout_f;
+  }
+}
+
+__global__ void pack_dgrad_kernel(int fwd_mode, const float* __restrict__ w, __half* __restrict__ dst,
+                                  int cout_f, int cin_f, int terms, int perm, size_t ktot) {
+  const size_t total = (size_t)cin_f * ktot;
+  const int taps_src = (fwd_mode == 3) ? 1 : 27;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / ktot);            // row = forward input channel
+    const int k = (int)(idx - (size_t)n * ktot);
+    float v = 0.f;
+    if (fwd_mode == 0) {
+      const int tap = k / cout_f, co = k - tap * cout_f;
+      v = w[((size_t)co * cin_f + n) * 27 + src_tap(26 - tap, perm)];
+    } else if (fwd_mode == 3) {
+      v = w[(size_t)k * cin_f + n];
+    } else if (fwd_mode == 1) {
+      // k3 s2 p1 forward: dX[2j]   = W[1]^T dY[j]
+      //                   dX[2j+1] = W[2]^T dY[j] + W[0]^T dY[j+1]
+      // expressed in the 8-phase / 2x2x2-tap scheme of conv mode 2 (phase bit p: taps at
+      // j-1, j when p = 0; j, j+1 when p = 1).
+      const int phase = k / (8 * cout_f);
+      const int r = k - phase * 8 * cout_f;
+      const int tap8 = r / cout_f, co = r - tap8 * cout_f;
+      int t[3];
+      bool live = true;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {             // d = 0: w, 1: h, 2: d
+        const int p = (phase >> d) & 1, a = (tap8 >> d) & 1;
+        if (p == 0) { t[d] = 1; live = live && (a == 1); }
+        else t[d] = a ? 0 : 2;
+      }
+      if (live) v = w[((size_t)co * cin_f + n) * 27 + src_tap((t[2] * 3 + t[1]) * 3 + t[0], perm)];
+    } else {
+      // nearest-x2 + k3 p1 forward: dX[j] = sum_s Ws[s]^T dY[2j - 1 + s], s = 0..3 with
+      // Ws = {W2, W1+W2, W0+W1, W0} per dimension (k4 s2 conv, conv mode 4).
+      const int tap = k / cout_f, co = k - tap * cout_f;
+      const int s[3] = {tap & 3, (tap >> 2) & 3, tap >> 4};   // w, h, d
+      int lo[3], hi[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = (s[d] == 0) ? 2 : (s[d] == 1 ? 1 : 0);
+        hi[d] = (s[d] == 0) ? 2 : (s[d] == 1 ? 2 : (s[d] == 2 ? 1 : 0));
+      }
+      const float* wp = w + ((size_t)co * cin_f + n) * 27;
+      for (int kd = lo[2]; kd <= hi[2]; ++kd)
+        for (int kh = lo[1]; kh <= hi[1]; ++kh)
+          for (int kw = lo[0]; kw <= hi[0]; ++kw) v += wp[src_tap((kd * 3 + kh) * 3 + kw, perm)];
+    }
+    (void)taps_src;
+    const __half h = __float2half_rn(v);
+    dst[(size_t)n * ktot + k] = h;
+    if (terms == 2) dst[((size_t)cin_f + n) * ktot + k] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+int pack_dgrad_weights(int fwd_mode, const float* w, __half* dst, int cout_f, int cin_f, int terms,
+                       int perm, cudaStream_t st) {
+  const size_t ktot = dgrad_packed_k(fwd_mode, cout_f);
+  const size_t total = (size_t)cin_f * ktot;
+  pack_dgrad_kernel<<<grid_for(total, 256, 4096), 256, 0, st>>>(fwd_mode, w, dst, cout_f, cin_f, terms,
+                                                               perm, ktot);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// loss scale
+// =============================================================================================
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));   // non-negative floats order as uints
+}
+__global__ void scale_from_max_kernel(unsigned int* __restrict__ mx, float target, float* __restrict__ scale) {
+  const float m = __uint_as_float(*mx);
+  float s = 1.f;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(target / m, &e);           // target/m = f * 2^e, f in [0.5, 1)
+    e = e - 1;
+    e = e > 60 ? 60 : (e < -60 ? -60 : e);
+    s = ldexpf(1.f, e);
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+  *mx = 0u;                            // ready for the next call
+}
+int auto_scale_enqueue(const float* x, size_t n, float target, float* scale_dev, unsigned int* max_scratch,
+                       cudaStream_t st) {
+  absmax_kernel<<<grid_for(n, 256, 592), 256, 0, st>>>(x, n, max_scratch);
+  scale_from_max_kernel<<<1, 1, 0, st>>>(max_scratch, target, scale_dev);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// dOut preparation: fp32 -> fp16 operand (+ residual fan-out, per-sample channel sums)
+// =============================================================================================
+__global__ void __launch_bounds__(1024)
+cast_colsum_kernel(const float* __restrict__ src, __half* __restrict__ dst16, float* __restrict__ acc_dst,
+                   int acc_init, float* __restrict__ colsum, int colsum_ld, int pixels, int C, int chunks,
+                   int* __restrict__ err_flag) {
+  extern __shared__ float red[];   // [T][4]
+  const int Q = C >> 2, T = blockDim.x, tid = threadIdx.x;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int px0 = (int)(((long long)pixels * chunk) / chunks);
+  const int px1 = (int)(((long long)pixels * (chunk + 1)) / chunks);
+  const int nvec = (px1 - px0) * Q;
+  const size_t base = ((size_t)b * pixels + px0) * C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool sat = false;
+  for (int i = tid; i < nvec; i += T) {
+    const float4 v = *reinterpret_cast<const float4*>(src + base + (size_t)i * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (dst16) {
+      const float lim = 65504.f;
+      float4 c = make_float4(fminf(fmaxf(v.x, -lim), lim), fminf(fmaxf(v.y, -lim), lim),
+                             fminf(fmaxf(v.z, -lim), lim), fminf(fmaxf(v.w, -lim), lim));
+      sat = sat || c.x != v.x || c.y != v.y || c.z != v.z || c.w != v.w;
+      __half2 h0 = __floats2half2_rn(c.x, c.y), h1 = __floats2half2_rn(c.z, c.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(dst16 + base + (size_t)i * 4) = u;
+    }
+    if (acc_dst) {
+      float4* ap = reinterpret_cast<float4*>(acc_dst + base + (size_t)i * 4);
+      if (acc_init) *ap = v;
+      else {
+        float4 a = *ap;
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        *ap = a;
+      }
+    }
+  }
+  if (sat && err_flag) atomicExch(err_flag, 301);   // fp16 overflow of a scaled gradient
+  if (!colsum) return;
+  reinterpret_cast<float4*>(red)[tid] = s;
+  __syncthreads();
+  if (tid < Q) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = tid; r < T; r += Q) {
+      const float4 v = reinterpret_cast<float4*>(red)[r];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float* cp = colsum + (size_t)b * colsum_ld + tid * 4;
+    atomicAdd(cp + 0, a.x);
+    atomicAdd(cp + 1, a.y);
+    atomicAdd(cp + 2, a.z);
+    atomicAdd(cp + 3, a.w);
+  }
+}
+
+int cast_colsum_enqueue(const float* src, __half* dst16, float* acc_dst, int acc_init, float* colsum,
+                        int colsum_ld, int B, int pixels, int C, cudaStream_t st) {
+  CM_CHECK(C % 4 == 0 && C / 4 <= 1024, "cast_colsum: bad channel count %d", C);
+  const int Q = C / 4;
+  const int T = sweep_threads(Q);
+  int chunks = 592 / B;
+  if (chunks < 1) chunks = 1;
+  if (chunks > (pixels + 7) / 8) chunks = (pixels + 7) / 8;
+  if (chunks < 1) chunks = 1;
+  cast_colsum_kernel<<<dim3(chunks, B), T, (size_t)T * 16, st>>>(src, dst16, acc_dst, acc_init, colsum,
+                                                                colsum_ld, pixels, C, chunks,
+                                                                device_error_flag());
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void rowsum_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int ld,
+                              int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int b = 0; b < B; ++b) a += in[(size_t)b * ld + c];
+  out[c] = accumulate ? out[c] + a : a;
+}
+int rowsum_enqueue(const float* in, float* out, int B, int C, int ld, int accumulate, cudaStream_t st) {
+  rowsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(in, out, B, C, ld, accumulate);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// G -> nn.Conv3d weight-gradient layout
+// =============================================================================================
+__global__ void unpack_wgrad_kernel(int fwd_mode, const float* __restrict__ G, float* __restrict__ dw,
+                                    float* __restrict__ dwx, int cout, int cin, int cinx, int perm) {
+  const int taps = (fwd_mode == 3) ? 1 : 27;
+  const size_t n_main = (size_t)cout * cin * taps;
+  const size_t total = n_main + (size_t)cout * cinx;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    if (idx >= n_main) {
+      const size_t r = idx - n_main;
+      const int co = (int)(r / cinx), cx = (int)(r - (size_t)co * cinx);
+      dwx[r] = G[((size_t)taps * cin + cx) * cout + co];
+      continue;
+    }
+    const int st = (int)(idx % taps);            // source tap index (reference weight layout)
+    const size_t r = idx / taps;
+    const int ci = (int)(r % cin), co = (int)(r / cin);
+    float v = 0.f;
+    if (fwd_mode == 3) {
+      v = G[(size_t)ci * cout + co];
+    } else {
+      // source tap -> activation-order tap (d, h, w)
+      int td, th, tw;
+      if (perm) { td = st % 3; tw = (st / 3) % 3; th = st / 9; }
+      else { tw = st % 3; th = (st / 3) % 3; td = st / 9; }
+      if (fwd_mode != 2) {
+        v = G[((size_t)((td * 3 + th) * 3 + tw) * cin + ci) * cout + co];
+      } else {
+        // fold the 8 phases x 8 taps: original tap k of one dim lives in (p, a) pairs
+        //   k=0: (0,0),(1,0)   k=1: (0,1),(1,0)   k=2: (0,1),(1,1)
+        const int kk[3] = {tw, th, td};
+        const size_t krows = (size_t)8 * cin;
+        for (int sel = 0; sel < 8; ++sel) {
+          int phase = 0, tap8 = 0;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int which = (sel >> d) & 1;
+            int p, a;
+            if (kk[d] == 0) { p = which; a = 0; }
+            else if (kk[d] == 1) { p = which; a = which ? 0 : 1; }
+            else { p = which; a = 1; }
+            phase |= p << d;
+            tap8 |= a << d;
+          }
+          v += G[((size_t)phase * krows + (size_t)tap8 * cin + ci) * cout + co];
+        }
+      }
+    }
+    dw[idx] = v;
+  }
+}
+
+int unpack_wgrad_enqueue(int fwd_mode, const float* G, float* dw, float* dwx, int cout, int cin,
+                         int cinx, int perm, cudaStream_t st) {
+  const size_t total = (size_t)cout * cin * (fwd_mode == 3 ? 1 : 27) + (size_t)cout * cinx;
+  unpack_wgrad_kernel<<<grid_for(total, 256, 4096), 256, 0, st>>>(fwd_mode, G, dw, dwx, cout, cin, cinx,
+                                                                 perm);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// scalar restatement of the weight gradient (same fp16 operands, same G layout; test oracle)
+// =============================================================================================
+__global__ void wgrad_ref_kernel(int fwd_mode, const __half* __restrict__ act, const __half* __restrict__ extra,
+                                 const __half* __restrict__ dout, float* __restrict__ G, int B, int D, int H,
+                                 int W, int cin, int cinx, int cout) {
+  int k = 3, stride = 1, od = D, oh = H, ow = W, nphase = 1;
+  if (fwd_mode == 1) { stride = 2; od = (D - 1) / 2 + 1; oh = (H - 1) / 2 + 1; ow = (W - 1) / 2 + 1; }
+  else if (fwd_mode == 2) { k = 2; nphase = 8; }
+  else if (fwd_mode == 3) k = 1;
+  const int taps = k * k * k;
+  const size_t krows = (size_t)taps * cin + cinx;
+  const size_t total = (size_t)nphase * krows * cout;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % cout);
+    size_t r = idx / cout;
+    const int krow = (int)(r % krows);
+    const int phase = (int)(r / krows);
+    float acc = 0.f;
+    const bool main = krow < taps * cin;
+    const int tap = main ? krow / cin : 0;
+    const int ci = main ? krow - tap * cin : krow - taps * cin;
+    const int tw = tap % k, th = (tap / k) % k, td = tap / (k * k);
+    int lw = -1, lh = -1, ld = -1;
+    if (fwd_mode == 2) { lw = (phase & 1) ? 0 : -1; lh = (phase & 2) ? 0 : -1; ld = (phase & 4) ? 0 : -1; }
+    else if (fwd_mode == 3) lw = lh = ld = 0;
+    for (int b = 0; b < B; ++b)
+      for (int z = 0; z < od; ++z)
+        for (int p = 0; p < oh; ++p)
+          for (int q = 0; q < ow; ++q) {
+            float a;
+            if (main) {
+              const int w = q * stride + lw + tw, h = p * stride + lh + th, d = z * stride + ld + td;
+              if (w < 0 || w >= W || h < 0 || h >= H || d < 0 || d >= D) continue;
+              a = __half2float(act[((((size_t)b * D + d) * H + h) * W + w) * cin + ci]);
+            } else {
+              a = __half2float(extra[((((size_t)b * od + z) * oh + p) * ow + q) * cinx + ci]);
+            }
+            size_t orow;
+            if (fwd_mode == 2)
+              orow = (((size_t)b * (2 * od) + (2 * z + ((phase >> 2) & 1))) * (2 * oh) + (2 * p + ((phase >> 1) & 1))) *
+                         (2 * ow) + (2 * q + (phase & 1));
+            else
+              orow = (((size_t)b * od + z) * oh + p) * ow + q;
+            acc = fmaf(a, __half2float(dout[orow * cout + co]), acc);
+          }
+    G[idx] = acc;
+  }
+}
+
+int wgrad_ref_enqueue(int fwd_mode, const __half* act16, const __half* extra16, const __half* dout16,
+                      float* G, int B, int D, int H, int W, int cin, int cinx, int cout,
+                      cudaStream_t st) {
+  wgrad_ref_kernel<<<1024, 128, 0, st>>>(fwd_mode, act16, extra16, dout16, G, B, D, H, W, cin, cinx, cout);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// GroupNorm(8) [+SiLU] [+Dropout3d scale] backward
+//   xhat = (x - mean) rstd, y = xhat*gamma + beta, z = silu(y) (optional), out = z * drop
+//   dy = dout*drop*silu'(y);  S1[b,c] = sum_p dy, S2[b,c] = sum_p dy*xhat
+//   dgamma = sum_b S2, dbeta = sum_b S1
+//   per (b, group): m1 = sum_c gamma_c S1 / N, m2 = sum_c gamma_c S2 / N   (N = pixels * C/8)
+//   dx = rstd * (dy*gamma - m1 - xhat*m2) (+ draw)
+// =============================================================================================
+struct GnBwdGeom {
+  int Q, T, chunks;
+};
+
+__device__ __forceinline__ float4 gn_bwd_dy(const GnBwdParams& p, const float4 x, const float4 dn,
+                                            const float mean, const float rstd, const float4 ga,
+                                            const float4 be, const float4 ds, float4* xhat) {
+  float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+  float4 dy = make_float4(dn.x * ds.x, dn.y * ds.y, dn.z * ds.z, dn.w * ds.w);
+  if (p.silu) {
+    dy.x *= silu_grad(fmaf(xh.x, ga.x, be.x));
+    dy.y *= silu_grad(fmaf(xh.y, ga.y, be.y));
+    dy.z *= silu_grad(fmaf(xh.z, ga.z, be.z));
+    dy.w *= silu_grad(fmaf(xh.w, ga.w, be.w));
+  }
+  *xhat = xh;
+  return dy;
+}
+
+// pass 1: partial[b][chunk][c][2]
+__global__ void __launch_bounds__(1024) gn_bwd_sums_kernel(const GnBwdParams p, int chunks, float* __restrict__ partial) {
+  extern __shared__ float red[];   // [T][8]
+  const int C = p.c0 + p.c1, Q = C >> 2, cg_ch = C >> 3, T = blockDim.x, tid = threadIdx.x;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int px0 = (int)(((long long)p.pixels * chunk) / chunks);
+  const int px1 = (int)(((long long)p.pixels * (chunk + 1)) / chunks);
+  const int c = (tid % Q) * 4;
+  const int g = c / cg_ch;
+  const float mean = p.stats[(b * 8 + g) * 2], rstd = p.stats[(b * 8 + g) * 2 + 1];
+  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
+  const bool from0 = c < p.c0;
+  const float* src = from0 ? p.src0 + c : p.src1 + (c - p.c0);
+  const int src_ld = from0 ? p.c0 : p.c1;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const int rows_per_iter = T / Q;
+  for (int px = px0 + tid / Q; px < px1; px += rows_per_iter) {
+    const size_t pix = (size_t)b * p.pixels + px;
+    const float4 x = *reinterpret_cast<const float4*>(src + pix * src_ld);
+    const float4 dn = *reinterpret_cast<const float4*>(p.dnorm + pix * C + c);
+    float4 xh;
+    const float4 dy = gn_bwd_dy(p, x, dn, mean, rstd, ga, be, ds, &xh);
+    s1.x += dy.x; s1.y += dy.y; s1.z += dy.z; s1.w += dy.w;
+    s2.x += dy.x * xh.x; s2.y += dy.y * xh.y; s2.z += dy.z * xh.z; s2.w += dy.w * xh.w;
+  }
+  reinterpret_cast<float4*>(red)[tid * 2] = s1;
+  reinterpret_cast<float4*>(red)[tid * 2 + 1] = s2;
+  __syncthreads();
+  if (tid < Q) {
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+    for (int r = tid; r < T; r += Q) {
+      const float4 v1 = reinterpret_cast<float4*>(red)[r * 2], v2 = reinterpret_cast<float4*>(red)[r * 2 + 1];
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+    }
+    float* o = partial + (((size_t)b * chunks + chunk) * C + c) * 2;
+    o[0] = a1.x; o[1] = a2.x; o[2] = a1.y; o[3] = a2.y; o[4] = a1.z; o[5] = a2.z; o[6] = a1.w; o[7] = a2.w;
+  }
+}
+
+// pass 2: combine partials (fixed order), group means, dx
+__global__ void __launch_bounds__(1024) gn_bwd_apply_kernel(const GnBwdParams p, int chunks, const float* __restrict__ partial) {
+  extern __shared__ float sm[];    // [C][2] gamma-weighted channel sums | [8][2] group means
+  const int C = p.c0 + p.c1, Q = C >> 2, cg_ch = C >> 3, T = blockDim.x, tid = threadIdx.x;
+  float* gs = sm;
+  float* gm = sm + 2 * C;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  for (int cc = tid; cc < C; cc += T) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* o = partial + (((size_t)b * chunks + k) * C + cc) * 2;
+      a1 += o[0];
+      a2 += o[1];
+    }
+    if (chunk == 0) {
+      p.chsum[((size_t)b * C + cc) * 2] = a1;
+      p.chsum[((size_t)b * C + cc) * 2 + 1] = a2;
+    }
+    const float gmm = p.gamma[cc];
+    gs[cc * 2] = a1 * gmm;
+    gs[cc * 2 + 1] = a2 * gmm;
+  }
+  __syncthreads();
+  if (tid < 16) {
+    const int g = tid >> 1, which = tid & 1;
+    float a = 0.f;
+    for (int k = 0; k < cg_ch; ++k) a += gs[(g * cg_ch + k) * 2 + which];
+    gm[tid] = a / ((float)p.pixels * (float)cg_ch);
+  }
+  __syncthreads();
+  const int px0 = (int)(((long long)p.pixels * chunk) / chunks);
+  const int px1 = (int)(((long long)p.pixels * (chunk + 1)) / chunks);
+  const int c = (tid % Q) * 4;
+  const int g = c / cg_ch;
+  const float mean = p.stats[(b * 8 + g) * 2], rstd = p.stats[(b * 8 + g) * 2 + 1];
+  const float m1 = gm[g * 2], m2 = gm[g * 2 + 1];
+  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
+  const bool from0 = c < p.c0;
+  const float* src = from0 ? p.src0 + c : p.src1 + (c - p.c0);
+  float* dsrc = from0 ? p.dsrc0 + c : p.dsrc1 + (c - p.c0);
+  const int src_ld = from0 ? p.c0 : p.c1;
+  const int init = from0 ? p.init0 : p.init1;
+  const int rows_per_iter = T / Q;
+  for (int px = px0 + tid / Q; px < px1; px += rows_per_iter) {
+    const size_t pix = (size_t)b * p.pixels + px;
+    const float4 x = *reinterpret_cast<const float4*>(src + pix * src_ld);
+    const float4 dn = *reinterpret_cast<const float4*>(p.dnorm + pix * C + c);
+    float4 xh;
+    const float4 dy = gn_bwd_dy(p, x, dn, mean, rstd, ga, be, ds, &xh);
+    float4 dx = make_float4(rstd * (dy.x * ga.x - m1 - xh.x * m2), rstd * (dy.y * ga.y - m1 - xh.y * m2),
+                            rstd * (dy.z * ga.z - m1 - xh.z * m2), rstd * (dy.w * ga.w - m1 - xh.w * m2));
+    if (p.draw) {
+      const float4 r = *reinterpret_cast<const float4*>(p.draw + pix * C + c);
+      dx.x += r.x; dx.y += r.y; dx.z += r.z; dx.w += r.w;
+    }
+    float4* dp = reinterpret_cast<float4*>(dsrc + pix * src_ld);
+    if (!init) {
+      const float4 o = *dp;
+      dx.x += o.x; dx.y += o.y; dx.z += o.z; dx.w += o.w;
+    }
+    *dp = dx;
+  }
+}
+
+__global__ void gn_bwd_params_kernel(const float* __restrict__ chsum, int B, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a1 = 0.f, a2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    a1 += chsum[((size_t)b * C + c) * 2];
+    a2 += chsum[((size_t)b * C + c) * 2 + 1];
+  }
+  dbeta[c] = a1;
+  dgamma[c] = a2;
+}
+
+int gn_bwd_chunks(int B, int pixels) {
+  int chunks = 592 / B;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 32) chunks = 32;
+  if (chunks > (pixels + 3) / 4) chunks = (pixels + 3) / 4;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+int gn_backward_enqueue(const GnBwdParams& p, float* partial, cudaStream_t st) {
+  const int C = p.c0 + p.c1;
+  CM_CHECK(C % 32 == 0 && p.c0 % 4 == 0, "GroupNorm backward: channels must be a multiple of 32 (C=%d)", C);
+  const int Q = C / 4;
+  CM_CHECK(Q <= 1024, "GroupNorm backward: too many channels (C=%d)", C);
+  const int T = sweep_threads(Q);
+  const int chunks = gn_bwd_chunks(p.B, p.pixels);
+  gn_bwd_sums_kernel<<<dim3(chunks, p.B), T, (size_t)T * 32, st>>>(p, chunks, partial);
+  gn_bwd_apply_kernel<<<dim3(chunks, p.B), T, (size_t)(2 * C + 16) * 4, st>>>(p, chunks, partial);
+  gn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(p.chsum, p.B, C, p.dgamma, p.dbeta);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// attention core backward (one CTA per (sample, head); everything in shared memory)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+attn_core_backward_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                          float* __restrict__ dqkv, int S, int C, int heads) {
+  extern __shared__ float sm[];
+  const int dh = C / heads, ld = dh + 1;
+  const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
+  float* Qs = sm;
+  float* Ks = Qs + (size_t)S * ld;
+  float* Vs = Ks + (size_t)S * ld;
+  float* Os = Vs + (size_t)S * ld;          // dO
+  float* Ps = Os + (size_t)S * ld;          // [S][S+1]: P, then dS in place
+  const int pld = S + 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const float* base = qkv + (size_t)b * S * 3 * C + hd * dh;
+  const float* dob = dctx + (size_t)b * S * C + hd * dh;
+  for (int idx = tid; idx < S * dh; idx += blockDim.x) {
+    const int j = idx / dh, d = idx - j * dh;
+    Qs[j * ld + d] = base[(size_t)j * 3 * C + d];
+    Ks[j * ld + d] = base[(size_t)j * 3 * C + C + d];
+    Vs[j * ld + d] = base[(size_t)j * 3 * C + 2 * C + d];
+    Os[j * ld + d] = dob[(size_t)j * C + d];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)dh);
+  for (int i = warp; i < S; i += nwarps) {
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      float a = 0.f;
+      for (int d = 0; d < dh; ++d) a = fmaf(Qs[i * ld + d], Ks[j * ld + d], a);
+      a *= scale;
+      Ps[i * pld + j] = a;
+      mx = fmaxf(mx, a);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float e = expf(Ps[i * pld + j] - mx);
+      Ps[i * pld + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < S; j += 32) Ps[i * pld + j] *= inv;
+  }
+  __syncthreads();
+  float* dq = dqkv + (size_t)b * S * 3 * C + hd * dh;
+  // dV[j][d] = sum_i P[i][j] dO[i][d]
+  for (int idx = tid; idx < S * dh; idx += blockDim.x) {
+    const int j = idx / dh, d = idx - j * dh;
+    float a = 0.f;
+    for (int i = 0; i < S; ++i) a = fmaf(Ps[i * pld + j], Os[i * ld + d], a);
+    dq[(size_t)j * 3 * C + 2 * C + d] = a;
+  }
+  __syncthreads();
+  // dS = P o (dP - rowsum(dP o P)), dP[i][j] = dO[i] . V[j]
+  for (int i = warp; i < S; i += nwarps) {
+    float part = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      float a = 0.f;
+      for (int d = 0; d < dh; ++d) a = fmaf(Os[i * ld + d], Vs[j * ld + d], a);
+      part = fmaf(a, Ps[i * pld + j], part);
+    }
+    const float Di = warp_sum(part);
+    for (int j = lane; j < S; j += 32) {
+      float a = 0.f;
+      for (int d = 0; d < dh; ++d) a = fmaf(Os[i * ld + d], Vs[j * ld + d], a);
+      Ps[i * pld + j] = Ps[i * pld + j] * (a - Di) * scale;   // scale folded in (dQ, dK both carry it)
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < S * dh; idx += blockDim.x) {
+    const int i = idx / dh, d = idx - i * dh;
+    float aq = 0.f, ak = 0.f;
+    for (int j = 0; j < S; ++j) {
+      aq = fmaf(Ps[i * pld + j], Ks[j * ld + d], aq);      // dQ[i][d] = sum_j dS[i][j] K[j][d]
+      ak = fmaf(Ps[j * pld + i], Qs[j * ld + d], ak);      // dK[i][d] = sum_j dS[j][i] Q[j][d]
+    }
+    dq[(size_t)i * 3 * C + d] = aq;
+    dq[(size_t)i * 3 * C + C + d] = ak;
+  }
+}
+
+static size_t attn_bwd_smem(int S, int dh) {
+  return ((size_t)4 * S * (dh + 1) + (size_t)S * (S + 1)) * sizeof(float);
+}
+
+int attn_core_backward_enqueue(const float* qkv, const float* dctx, float* dqkv, int B, int S, int C,
+                               int heads, cudaStream_t st) {
+  CM_CHECK(C % heads == 0, "embed dim %d / heads %d unsupported", C, heads);
+  const size_t smem = attn_bwd_smem(S, C / heads);
+  CM_CHECK(smem <= 200 * 1024, "attention backward tile too large for shared memory (S=%d dh=%d)", S, C / heads);
+  attn_core_backward_kernel<<<B * heads, 256, smem, st>>>(qkv, dctx, dqkv, S, C, heads);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// final conv backward (unet.py:121,165-167): only future frames carry gradient
+// =============================================================================================
+template <int COUT>
+__global__ void __launch_bounds__(256)
+final_conv_dact_kernel(const float* __restrict__ deps, const float* __restrict__ scale_dev,
+                       const float* __restrict__ w, float* __restrict__ dact, int B, int H, int W, int L,
+                       int P, int cin) {
+  extern __shared__ float ws[];   // [27][cin][COUT]
+  for (int idx = threadIdx.x; idx < 27 * cin * COUT; idx += blockDim.x) {
+    const int co = idx % COUT;
+    const int r = idx / COUT;
+    const int ci = r % cin, tap = r / cin;
+    ws[idx] = w[((size_t)co * cin + ci) * 27 + tap];
+  }
+  __syncthreads();
+  const float scale = scale_dev ? scale_dev[0] : 1.f;
+  const int F = L - P;
+  const int slices = cin / 8;
+  const size_t total = (size_t)B * L * H * W * slices;
+  const size_t plane = (size_t)H * W * F;
+  for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total;
+       gid += (size_t)gridDim.x * blockDim.x) {
+    const int sl = (int)(gid % slices);
+    size_t pix = gid / slices;                       // internal layout [B][L][H][W]
+    const int wc = (int)(pix % W);
+    size_t r = pix / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int l = (int)(r % L);
+    const int b = (int)(r / L);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // forward: out[o] += w[tap] * in[o + tap - 1]  ->  in[i] receives from o = i - tap + 1
+    for (int td = 0; td < 3; ++td) {
+      const int oh = h - td + 1;
+      if (oh < 0 || oh >= H) continue;
+      for (int th = 0; th < 3; ++th) {
+        const int ow = wc - th + 1;
+        if (ow < 0 || ow >= W) continue;
+        for (int tw = 0; tw < 3; ++tw) {
+          const int ol = l - tw + 1;
+          if (ol < P || ol >= L) continue;
+          const int tap = (td * 3 + th) * 3 + tw;
+          float d[COUT];
+#pragma unroll
+          for (int co = 0; co < COUT; ++co)
+            d[co] = deps[((size_t)b * COUT + co) * plane + ((size_t)oh * W + ow) * F + (ol - P)] * scale;
+          const float* wp = ws + ((size_t)tap * cin + sl * 8) * COUT;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[e] = fmaf(wp[e * COUT + co], d[co], acc[e]);
+        }
+      }
+    }
+    float4* op = reinterpret_cast<float4*>(dact + pix * cin + sl * 8);
+    op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256)
+final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict__ scale_dev,
+                        const __half* __restrict__ act, float* __restrict__ dw, float* __restrict__ db,
+                        int B, int H, int W, int L, int P, int cin, int pix_per_cta) {
+  constexpr int MAXP = 8;                      // (tap, ci) pairs per thread: 27*cin <= 2048
+  const float scale = scale_dev ? scale_dev[0] : 1.f;
+  const int F = L - P;
+  const int npairs = 27 * cin;
+  const size_t total = (size_t)B * H * W * F;
+  const size_t plane = (size_t)H * W * F;
+  float acc[MAXP][COUT];
+  float bacc[COUT];
+#pragma unroll
+  for (int k = 0; k < MAXP; ++k)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[k][co] = 0.f;
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) bacc[co] = 0.f;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
+  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
+  for (size_t pix = p0; pix < p1; ++pix) {
+    const int f = (int)(pix % F);
+    size_t r = pix / F;
+    const int wc = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    const int l = P + f;
+    float d[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      d[co] = deps[((size_t)b * COUT + co) * plane + ((size_t)h * W + wc) * F + f] * scale;
+      bacc[co] += d[co];
+    }
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+      const int pr = threadIdx.x + k * 256;
+      if (pr >= npairs) break;
+      const int tap = pr / cin, ci = pr - tap * cin;
+      const int hh = h + tap / 9 - 1, ww = wc + (tap / 3) % 3 - 1, ll = l + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W || ll < 0 || ll >= L) continue;
+      const float a = __half2float(act[((((size_t)b * L + ll) * H + hh) * W + ww) * cin + ci]);
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[k][co] = fmaf(a, d[co], acc[k][co]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXP; ++k) {
+    const int pr = threadIdx.x + k * 256;
+    if (pr >= npairs) break;
+    const int tap = pr / cin, ci = pr - tap * cin;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) atomicAdd(dw + ((size_t)co * cin + ci) * 27 + tap, acc[k][co]);
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) atomicAdd(db + co, bacc[co]);
+  }
+}
+
+int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act,
+                                const float* w, float* dact, float* dw, float* db, int B, int H, int W,
+                                int L, int P, int cin, int cout, cudaStream_t st) {
+  CM_CHECK(cout >= 1 && cout <= 4, "final conv supports 1..4 output channels (got %d)", cout);
+  CM_CHECK(cin % 32 == 0 && 27 * cin <= 2048, "final conv backward: cin must be a multiple of 32, <= 64");
+  const size_t total = (size_t)B * L * H * W * (cin / 8);
+  const int blocks = grid_for(total, 256, 148 * 16);
+  const size_t smem = (size_t)27 * cin * cout * sizeof(float);
+  const size_t opix = (size_t)B * H * W * (L - P);
+  const int ppc = (int)((opix + 591) / 592);
+  const int wblocks = (int)((opix + ppc - 1) / ppc);
+#define CM_FB(CO)                                                                                   \
+  case CO:                                                                                          \
+    final_conv_dact_kernel<CO><<<blocks, 256, smem, st>>>(deps, scale_dev, w, dact, B, H, W, L, P, cin); \
+    final_conv_wgrad_kernel<CO><<<wblocks, 256, 0, st>>>(deps, scale_dev, act, dw, db, B, H, W, L, P, cin, ppc); \
+    break;
+  switch (cout) { CM_FB(1) CM_FB(2) CM_FB(3) CM_FB(4) }
+#undef CM_FB
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// first conv weight / bias gradient (unet.py:32); 256 threads = cout x (256/cout) k-groups
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+first_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ past,
+                        const float* __restrict__ dout, float* __restrict__ dw, float* __restrict__ db,
+                        int B, int H, int W, int P, int F, int cin, int cout, int pix_per_cta) {
+  constexpr int MAXK = 28;
+  const int L = P + F, K = 27 * cin;
+  const int ngroups = 256 / cout;
+  const int kper = (K + ngroups - 1) / ngroups;
+  const int co = threadIdx.x % cout, grp = threadIdx.x / cout;
+  const int k0 = grp * kper;
+  float acc[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) acc[k] = 0.f;
+  float bacc = 0.f;
+  const size_t total = (size_t)B * L * H * W;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
+  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
+  for (size_t pix = p0; pix < p1; ++pix) {          // internal layout [B][L][H][W]
+    const int wc = (int)(pix % W);
+    size_t r = pix / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int l = (int)(r % L);
+    const int b = (int)(r / L);
+    const float d = (grp < ngroups) ? dout[pix * cout + co] : 0.f;
+    bacc += d;
+#pragma unroll
+    for (int kk = 0; kk < MAXK; ++kk) {
+      const int k = k0 + kk;
+      if (kk >= kper || k >= K) break;
+      const int ci = k / 27, tap = k - ci * 27;
+      const int hh = h + tap / 9 - 1, ww = wc + (tap / 3) % 3 - 1, ll = l + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W || ll < 0 || ll >= L) continue;
+      const size_t pl = ((size_t)(b * cin + ci) * H + hh) * W + ww;
+      const float a = (ll < P) ? past[pl * P + ll] : x[pl * F + (ll - P)];
+      acc[kk] = fmaf(a, d, acc[kk]);
+    }
+  }
+  if (grp >= ngroups) return;
+#pragma unroll
+  for (int kk = 0; kk < MAXK; ++kk) {
+    const int k = k0 + kk;
+    if (kk >= kper || k >= K) break;
+    atomicAdd(dw + (size_t)co * K + k, acc[kk]);
+  }
+  if (grp == 0) atomicAdd(db + co, bacc);
+}
+
+int first_conv_wgrad_enqueue(const float* x, const float* past, const float* dout, float* dw, float* db,
+                             int B, int H, int W, int P, int F, int cin, int cout, cudaStream_t st) {
+  CM_CHECK(cout <= 256 && cout % 32 == 0, "first conv wgrad: cout must be a multiple of 32, <= 256");
+  const int ngroups = 256 / cout;
+  CM_CHECK((27 * cin + ngroups - 1) / ngroups <= 28, "first conv wgrad: 27*cin/(256/cout) must be <= 28");
+  const size_t total = (size_t)B * (P + F) * H * W;
+  const int ppc = (int)((total + 1183) / 1184);
+  const int blocks = (int)((total + ppc - 1) / ppc);
+  first_conv_wgrad_kernel<<<blocks, 256, 0, st>>>(x, past, dout, dw, db, B, H, W, P, F, cin, cout, ppc);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// tiny helpers for the time-embedding MLP backward
+// =============================================================================================
+__global__ void small_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int sam, int sak,
+                                  const float* __restrict__ Bm, int sbk, int sbn, float* __restrict__ Cm,
+                                  int ldc, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int m = idx / N, n = idx - m * N;
+  float a = 0.f;
+  for (int k = 0; k < K; ++k) a = fmaf(A[(size_t)m * sam + (size_t)k * sak], Bm[(size_t)k * sbk + (size_t)n * sbn], a);
+  float* o = Cm + (size_t)m * ldc + n;
+  *o = accumulate ? *o + a : a;
+}
+int small_gemm_enqueue(int M, int N, int K, const float* A, int sam, int sak, const float* Bm, int sbk,
+                       int sbn, float* Cm, int ldc, int accumulate, cudaStream_t st) {
+  small_gemm_kernel<<<(M * N + 127) / 128, 128, 0, st>>>(M, N, K, A, sam, sak, Bm, sbk, sbn, Cm, ldc,
+                                                         accumulate);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void silu_backward_kernel(const float* __restrict__ pre, const float* __restrict__ dpost,
+                                     float* __restrict__ dpre, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dpre[i] = dpost[i] * silu_grad(pre[i]);
+}
+int silu_backward_enqueue(const float* pre, const float* dpost, float* dpre, size_t n, cudaStream_t st) {
+  silu_backward_kernel<<<grid_for(n, 256, 1024), 256, 0, st>>>(pre, dpost, dpre, n);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void silu_forward_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = silu_f(x[i]);
+}
+int silu_forward_enqueue(const float* x, float* y, size_t n, cudaStream_t st) {
+  silu_forward_kernel<<<grid_for(n, 256, 1024), 256, 0, st>>>(x, y, n);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void scale_inplace_kernel(float* __restrict__ x, size_t n, const float* __restrict__ f) {
+  const float s = *f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] *= s;
+}
+int scale_inplace_enqueue(float* x, size_t n, const float* factor_dev, cudaStream_t st) {
+  scale_inplace_kernel<<<grid_for(n, 256, 2048), 256, 0, st>>>(x, n, factor_dev);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int backward_init() {
+  static bool done = false;
+  if (done) return 0;
+  CM_CUDA(cudaFuncSetAttribute(attn_core_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               200 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(final_conv_dact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(final_conv_dact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(final_conv_dact_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(final_conv_dact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  if (int rc = wgrad_init()) return rc;
+  done = true;
+  return 0;
+}
+
+}  // namespace cm

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 implicit-GEMM conv: tensor-map construction and launch.
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "wgrad_umma.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -29,16 +30,19 @@ int load_driver_syms() {
   return 0;
 }
 
+}  // namespace
+
 // Activation tensor [B, D, H, W, C] fp16 -> 5-D im2col map, dims ordered (C, W, H, D, N).
 int make_act_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int bk,
-                 int lower_w, int lower_h, int lower_d, int stride) {
+                 int lower_w, int lower_h, int lower_d, int stride, int upper_delta) {
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                            (cuuint64_t)D * H * W * C * 2};
-  // For every conv shape used here (k3 p1 s1|s2, 2x2x2 phase taps, 1x1x1) the upper corner
-  // (upper_pad - (k-1)) equals the lower corner (-lower_pad).
+  // For the forward conv shapes (k3 p1 s1|s2, 2x2x2 phase taps, 1x1x1) the upper corner
+  // (upper_pad - (k-1)) equals the lower corner (-lower_pad); the k4 s2 dgrad of UpSample needs
+  // upper = lower - 1 (upper_delta = -1).
   int lower[3] = {lower_w, lower_h, lower_d};
-  int upper[3] = {lower_w, lower_h, lower_d};
+  int upper[3] = {lower_w + upper_delta, lower_h + upper_delta, lower_d + upper_delta};
   cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides,
@@ -55,6 +59,8 @@ int make_act_map(CUtensorMap* map, const __half* base, int B, int D, int H, int 
   }
   return 0;
 }
+
+namespace {
 
 int make_weight_map(CUtensorMap* map, const __half* base, size_t rows, size_t ktot, int bk, int bn) {
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
@@ -107,7 +113,8 @@ size_t conv_packed_k(int mode, int cin, int cin_extra) {
   switch (mode) {
     case 0:
     case 1: return (size_t)27 * cin + cin_extra;
-    case 2: return (size_t)64 * cin;
+    case 2:
+    case 4: return (size_t)64 * cin;
     default: return (size_t)cin + cin_extra;
   }
 }
@@ -115,7 +122,7 @@ size_t conv_packed_k(int mode, int cin, int cin_extra) {
 int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
                  const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms) {
   if (int rc = load_driver_syms()) return rc;
-  CM_CHECK(mode >= 0 && mode <= 3, "bad conv mode %d", mode);
+  CM_CHECK(mode >= 0 && mode <= 4, "bad conv mode %d", mode);
   CM_CHECK(cin % 32 == 0 && cin_extra % 32 == 0, "channels must be multiples of 32 (cin=%d extra=%d)",
            cin, cin_extra);
   CM_CHECK(cout % 32 == 0, "cout must be a multiple of 32 (%d)", cout);
@@ -134,6 +141,12 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
     k = 2;
   } else if (mode == 3) {
     k = 1;
+  } else if (mode == 4) {   // k4 s2, pad (1,2): data gradient of nearest-x2 + k3 (UpSample)
+    stride = 2;
+    k = 4;
+    od = D / 2;
+    oh = H / 2;
+    ow = W / 2;
   }
   p.nphase = (mode == 2) ? 8 : 1;
   // N tile: as wide as possible (A is re-read once per N tile) unless that leaves most SMs idle
@@ -159,11 +172,11 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
     p.lower[ph][0] = (signed char)lw;
     p.lower[ph][1] = (signed char)lh;
     p.lower[ph][2] = (signed char)ld;
-    if (int rc = make_act_map(&p.amap[ph], act, B, D, H, W, cin, bk, lw, lh, ld, stride)) return rc;
+    if (int rc = make_act_map(&p.amap[ph], act, B, D, H, W, cin, bk, lw, lh, ld, stride, mode == 4 ? -1 : 0)) return rc;
   }
   if (cin_extra) {
     CM_CHECK(extra != nullptr, "extra source pointer missing");
-    if (int rc = make_act_map(&p.xmap, extra, B, od, oh, ow, cin_extra, bk, 0, 0, 0, 1)) return rc;
+    if (int rc = make_act_map(&p.xmap, extra, B, od, oh, ow, cin_extra, bk, 0, 0, 0, 1, 0)) return rc;
   }
   const size_t ktot = conv_packed_k(mode, cin, cin_extra);
   if (int rc = make_weight_map(&p.bmap, wpacked, (size_t)terms * cout, ktot, bk, bn)) return rc;
@@ -207,6 +220,154 @@ int conv_enqueue(const ConvLaunch& L, cudaStream_t st) {
     if (L.bn == 64) return launch_t<64, 32>(L, st);
     return launch_t<32, 32>(L, st);
   }
+}
+
+
+// ================================ weight gradient (wgrad_umma.cuh) ================================
+namespace {
+
+template <int BKC, int BNC, int BN>
+int wg_launch_t(const WgradLaunch& L, cudaStream_t st) {
+  wgrad_umma_kernel<BKC, BNC, BN><<<L.grid, WG_THREADS, L.smem, st>>>(L.p);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int BKC, int BNC, int BN>
+int wg_attr_t() {
+  CM_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<BKC, BNC, BN>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return 0;
+}
+template <int BKC>
+int wg_dispatch(const WgradLaunch& L, cudaStream_t st) {
+  if (L.bnc == 32) return wg_launch_t<BKC, 32, 32>(L, st);
+  switch (L.bn) {
+    case 64: return wg_launch_t<BKC, 64, 64>(L, st);
+    case 128: return wg_launch_t<BKC, 64, 128>(L, st);
+    default: return wg_launch_t<BKC, 64, 256>(L, st);
+  }
+}
+
+}  // namespace
+
+int wgrad_init() {
+  static bool done = false;
+  if (done) return 0;
+  if (int rc = load_driver_syms()) return rc;
+  if (int rc = wg_attr_t<32, 32, 32>()) return rc;
+  if (int rc = wg_attr_t<32, 64, 64>()) return rc;
+  if (int rc = wg_attr_t<32, 64, 128>()) return rc;
+  if (int rc = wg_attr_t<32, 64, 256>()) return rc;
+  if (int rc = wg_attr_t<64, 32, 32>()) return rc;
+  if (int rc = wg_attr_t<64, 64, 64>()) return rc;
+  if (int rc = wg_attr_t<64, 64, 128>()) return rc;
+  if (int rc = wg_attr_t<64, 64, 256>()) return rc;
+  done = true;
+  return 0;
+}
+
+size_t wgrad_g_elems(int mode, int cin, int cin_extra, int cout) {
+  return conv_packed_k(mode, cin, cin_extra) * (size_t)cout;
+}
+
+int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
+                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G) {
+  if (int rc = load_driver_syms()) return rc;
+  CM_CHECK(mode >= 0 && mode <= 3, "bad wgrad mode %d", mode);
+  CM_CHECK(cin % 32 == 0 && cin_extra % 32 == 0 && cout % 32 == 0,
+           "channels must be multiples of 32 (cin=%d extra=%d cout=%d)", cin, cin_extra, cout);
+  CM_CHECK(!(mode == 2 && cin_extra), "upsample conv takes no extra source");
+  memset(L, 0, sizeof(*L));
+  WgradParams& p = L->p;
+  const int bkc = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
+  const int bnc = (cout % 64 == 0) ? 64 : 32;
+  int bn = 32;
+  if (bnc == 64) bn = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  int stride = 1, k = 3, od = D, oh = H, ow = W;
+  if (mode == 1) {
+    stride = 2;
+    od = (D - 1) / 2 + 1;
+    oh = (H - 1) / 2 + 1;
+    ow = (W - 1) / 2 + 1;
+  } else if (mode == 2) {
+    k = 2;
+  } else if (mode == 3) {
+    k = 1;
+  }
+  p.nphase = (mode == 2) ? 8 : 1;
+  p.gstride = (mode == 2) ? 2 : 1;
+  for (int ph = 0; ph < p.nphase; ++ph) {
+    int lw = -1, lh = -1, ld = -1;
+    if (mode == 2) {
+      lw = (ph & 1) ? 0 : -1;
+      lh = (ph & 2) ? 0 : -1;
+      ld = (ph & 4) ? 0 : -1;
+    } else if (mode == 3) {
+      lw = lh = ld = 0;
+    }
+    p.lower[ph][0] = (signed char)lw;
+    p.lower[ph][1] = (signed char)lh;
+    p.lower[ph][2] = (signed char)ld;
+    if (int rc = make_act_map(&p.amap[ph], act, B, D, H, W, cin, bkc, lw, lh, ld, stride, 0)) return rc;
+    if (mode == 2) {
+      // dOut lives on the 2x grid; phase ph owns the pixels (2z+pz, 2p+pp, 2q+pq)
+      const int gw = ph & 1, gh = (ph >> 1) & 1, gd = (ph >> 2) & 1;
+      p.glower[ph][0] = (signed char)gw;
+      p.glower[ph][1] = (signed char)gh;
+      p.glower[ph][2] = (signed char)gd;
+      if (int rc = make_act_map(&p.gmap[ph], dout, B, 2 * D, 2 * H, 2 * W, cout, bnc, gw, gh, gd, 2, -1))
+        return rc;
+    } else {
+      if (int rc = make_act_map(&p.gmap[ph], dout, B, od, oh, ow, cout, bnc, 0, 0, 0, 1, 0)) return rc;
+    }
+  }
+  if (cin_extra) {
+    CM_CHECK(extra != nullptr, "extra source pointer missing");
+    if (int rc = make_act_map(&p.xmap, extra, B, od, oh, ow, cin_extra, bkc, 0, 0, 0, 1, 0)) return rc;
+  }
+  p.M = B * od * oh * ow;
+  p.od = od;
+  p.oh = oh;
+  p.ow = ow;
+  p.pps = od * oh * ow;
+  p.conv_stride = stride;
+  p.kd = p.kh = p.kw = k;
+  p.cin_main = cin;
+  p.cin_extra = cin_extra;
+  p.cout = cout;
+  p.ncm = cin / bkc;
+  p.atoms_main = k * k * k * p.ncm;
+  p.atoms_total = p.atoms_main + cin_extra / bkc;
+  p.apt = 128 / bkc;
+  p.n_tiles = cout / bn;
+  p.kb_total = (p.M + WG_KT - 1) / WG_KT;
+  p.krows = k * k * k * cin + cin_extra;
+  p.G = G;
+  p.err_flag = device_error_flag();
+  const int m_tiles = (p.atoms_total + p.apt - 1) / p.apt;
+  // split the pixel reduction so that ~2 waves of CTAs cover the 148 SMs
+  int splits = (2 * 148) / (m_tiles * p.n_tiles * p.nphase);
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty CTA
+  p.splits = splits;
+  const int stage_bytes = 128 * WG_KT * 2 + bn * WG_KT * 2;
+  int stages = WG_MAX_STAGES;
+  while (stages > 2 && (size_t)stages * stage_bytes + 2048 > 200 * 1024) --stages;
+  p.stages = stages;
+  L->bkc = bkc;
+  L->bnc = bnc;
+  L->bn = bn;
+  L->smem = (size_t)stages * stage_bytes + 1024 + 256;
+  L->grid = dim3(m_tiles, p.n_tiles * splits, p.nphase);
+  L->flops = 2.0 * p.M * cout * (double)p.krows * p.nphase;
+  return 0;
+}
+
+int wgrad_enqueue(const WgradLaunch& L, cudaStream_t st) {
+  if (L.bkc == 64) return wg_dispatch<64>(L, st);
+  return wg_dispatch<32>(L, st);
 }
 
 }  // namespace cm

@@ -235,7 +235,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     const float* temb_row = nullptr;     // per-sample rows (training): added per element
     if (P.temb && !temb_uniform)
       temb_row = P.temb + static_cast<size_t>(b) * P.temb_bstride + n_tile * BN;
-    const float* rp = (P.resid && valid) ? P.resid + static_cast<size_t>(m) * P.cout + n_tile * BN : nullptr;
+    const float* rp = (P.resid && valid) ? P.resid + orow * P.cout + n_tile * BN : nullptr;   // orow == m unless scattering
     float4 rnext[4];
     if (rp) {
 #pragma unroll

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
   const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
   const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
   float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * C + c);
+  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
   const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z,
                                 be.w - mean * sc.w);
@@ -591,13 +591,17 @@ __global__ void __launch_bounds__(256) temb_kernel(const TembParams p) {
   float* s2 = s1 + p.E;
   const int row = blockIdx.x;
   const long long t = p.t ? p.t[row] : (long long)row;
-  for (int i = threadIdx.x; i < p.base; i += blockDim.x) e[i] = p.table[(size_t)t * p.base + i];
+  for (int i = threadIdx.x; i < p.base; i += blockDim.x) {
+    e[i] = p.table[(size_t)t * p.base + i];
+    if (p.save_e) p.save_e[(size_t)row * p.base + i] = e[i];
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < p.E; j += blockDim.x) {
     float a = p.b1[j];
     const float* wr = p.w1 + (size_t)j * p.base;
     for (int i = 0; i < p.base; ++i) a = fmaf(wr[i], e[i], a);
     s1[j] = silu_f(a);
+    if (p.save_h1) p.save_h1[(size_t)row * p.E + j] = a;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < p.E; j += blockDim.x) {
@@ -605,6 +609,7 @@ __global__ void __launch_bounds__(256) temb_kernel(const TembParams p) {
     const float* wr = p.w2 + (size_t)j * p.E;
     for (int i = 0; i < p.E; ++i) a = fmaf(wr[i], s1[i], a);
     s2[j] = silu_f(a);   // every consumer applies SiLU first (layers.py:62)
+    if (p.save_h2) p.save_h2[(size_t)row * p.E + j] = a;
   }
   __syncthreads();
   for (int k = 0; k < p.nblocks; ++k) {
@@ -785,13 +790,13 @@ __global__ void conv_ref_kernel(const ConvParams p, const __half* __restrict__ a
       const int trow = p.t_dev ? *p.t_dev : 0;
       acc += p.temb[(size_t)trow * p.temb_ld + (size_t)b * p.temb_bstride + n];
     }
-    if (p.resid) acc += p.resid[(size_t)m * p.cout + n];
     size_t orow = m;
     if (p.scatter) {
       const int pq = phase & 1, pp = (phase >> 1) & 1, pz = (phase >> 2) & 1;
       orow = (((size_t)b * (2 * p.od) + (2 * z + pz)) * (2 * p.oh) + (2 * pp_ + pp)) * (2 * p.ow) +
              (2 * q + pq);
     }
+    if (p.resid) acc += p.resid[orow * p.cout + n];
     if (p.out32) p.out32[orow * p.out_ld + n] = acc;
     if (p.out16) p.out16[orow * p.out_ld + n] = __float2half_rn(acc);
   }

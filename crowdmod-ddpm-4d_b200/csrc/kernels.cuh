@@ -27,7 +27,8 @@ struct GnParams {
   int B, pixels;
   float eps;
   int silu;
-  const float* drop_scale;  // [B][C] per-(sample,channel) multiplier or nullptr
+  const float* drop_scale;  // [B][drop_ld] (+ channel) per-(sample,channel) multiplier or nullptr
+  int drop_ld;
   __half* out_norm;         // [B][pixels][C]
   __half* out_raw;          // optional raw fp16 copy of the (concatenated) input
   float* stats;             // optional [B][8][2] (mean, rstd) for backward
@@ -78,6 +79,8 @@ struct TembParams {
   int rows;
   float* out;              // [rows][ld]
   int ld;
+  // training: optional saves for the backward pass ([rows][base], [rows][E], [rows][E])
+  float* save_e; float* save_h1; float* save_h2;
 };
 int temb_enqueue(const TembParams& p, cudaStream_t st);
 

@@ -13,8 +13,10 @@
 #include <vector>
 
 #include "../../include/crowdmod_b200.h"
+#include "backward.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "wgrad_umma.cuh"
 
 namespace cm {
 
@@ -51,6 +53,14 @@ struct Op {
   ConvLaunch launch;
   // ATTN
   int qkv = -1, ctx = -1, heads = 4;
+  // training (backward) bookkeeping
+  int gn_index = -1;        // GN: slot of the saved (mean, rstd) statistics
+  int drop_off = -1;        // GN normalize_2: column offset of the block's Dropout3d scales
+  size_t dpack_off = 0, dxpack_off = 0;   // CONV: dgrad weight caches (main / fused 1x1 source)
+  size_t g_off = 0;         // CONV: offset of the packed-K weight-gradient scratch
+  size_t colsum_off = 0;    // CONV: per-sample channel sums of dOut ([B][cout])
+  ConvLaunch dlaunch, dxlaunch;
+  WgradLaunch wlaunch;
 };
 
 struct Level {
@@ -98,7 +108,40 @@ struct cm_unet {
   cudaGraphExec_t graph_exec = nullptr;
   cm_chain_args graph_key{};
   int64_t last_chain_launches = 0;
+  int64_t last_backward_launches = 0;
   double flops_per_sample = 0.0;
+  // ---- training state (cm_unet_train_forward / cm_unet_backward) ----
+  int n_gn = 0;
+  size_t dpack_elems = 0, g_elems = 0, colsum_per_sample = 0;
+  int max_gn_channels = 0;
+  __half* dpack = nullptr;              // dgrad weight caches
+  bool dpacked = false;
+  std::vector<size_t> grad_off;         // flat gradient buffer: offset of parameter i
+  size_t grad_total = 0;
+  int train_reserved = 0, train_prepared = 0;
+  uint8_t* tarena = nullptr;
+  size_t tarena_bytes = 0;
+  std::vector<float*> g32;              // per tensor: fp32 gradient [B][pixels][C]
+  std::vector<__half*> g16;             // conv outputs: fp16 copy of the gradient (MMA operand)
+  float* gn_stats = nullptr;            // [n_gn][B][8][2]
+  float* gn_bwd_partial = nullptr;      // [B][32][Cmax][2]
+  float* gn_chsum = nullptr;            // [B][Cmax][2]
+  uint8_t* zero_region = nullptr;       // G scratch | colsums | dtemb | max word, zeroed per backward
+  size_t zero_bytes = 0;
+  float* G = nullptr;
+  float* colsum = nullptr;
+  float* dtemb = nullptr;
+  unsigned int* max_word = nullptr;
+  float* tsave_e = nullptr;             // time-MLP saves / scratch, all [B][E] except e: [B][base]
+  float* tsave_h1 = nullptr; float* tsave_h2 = nullptr;
+  float* ts1 = nullptr; float* ts2 = nullptr; float* tds2 = nullptr; float* tdh2 = nullptr;
+  float* tds1 = nullptr; float* tdh1 = nullptr;
+  float* loss_scale = nullptr;          // device {S, 1/S}
+  // the forward whose activations currently sit in the arena
+  int live_train_batch = 0;
+  const float* live_future = nullptr;
+  const float* live_past = nullptr;
+  const float* live_drop = nullptr;
 
   int add_param(const std::string& name, std::vector<int64_t> shape) {
     ParamEntry e;
@@ -122,7 +165,7 @@ namespace {
 // ---- plan construction ---------------------------------------------------------------------
 
 int add_gn(cm_unet* u, const std::string& prefix, int src0, int src1, int silu, bool want_raw,
-           int* out_norm, int* out_raw) {
+           int* out_norm, int* out_raw, int drop_off = -1) {
   const int C = u->tens[src0].C + (src1 >= 0 ? u->tens[src1].C : 0);
   Op op;
   op.type = OP_GN;
@@ -132,6 +175,9 @@ int add_gn(cm_unet* u, const std::string& prefix, int src0, int src1, int silu, 
   op.gamma = u->add_param(prefix + ".weight", {C});
   op.beta = u->add_param(prefix + ".bias", {C});
   op.silu = silu;
+  op.gn_index = u->n_gn++;
+  op.drop_off = drop_off;
+  if (C > u->max_gn_channels) u->max_gn_channels = C;
   u->tens[src0].need32 = true;
   if (src1 >= 0) u->tens[src1].need32 = true;
   op.out_norm = u->add_tensor(u->tens[src0].level, C);
@@ -171,6 +217,14 @@ int add_conv(cm_unet* u, const std::string& tag, int mode, int in, int extra, in
   op.out = u->add_tensor(out_level, cout);
   op.wpack_off = u->wpack_elems;
   u->wpack_elems += (size_t)u->cfg.weight_terms * cout * conv_packed_k(mode, op.cin, op.cin_extra);
+  op.dpack_off = u->dpack_elems;
+  u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin * dgrad_packed_k(mode, cout);
+  op.dxpack_off = u->dpack_elems;
+  u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin_extra * cout;
+  op.g_off = u->g_elems;
+  u->g_elems += wgrad_g_elems(mode, op.cin, op.cin_extra, cout);
+  op.colsum_off = u->colsum_per_sample;
+  u->colsum_per_sample += cout;
   u->ops.push_back(op);
   return op.out;
 }
@@ -195,7 +249,7 @@ int add_resblock(cm_unet* u, const std::string& prefix, int src0, int src1, int 
   u->temb_ld += cout;
   const int h1 = add_conv(u, prefix + ".conv_1", 0, a1, -1, w1, -1, b1, -1, temb_off, -1, cout, level);
   int a2;
-  add_gn(u, prefix + ".normalize_2", h1, -1, 1, false, &a2, nullptr);
+  add_gn(u, prefix + ".normalize_2", h1, -1, 1, false, &a2, nullptr, temb_off);   // Dropout3d (layers.py:70)
   const int w2 = u->add_param(prefix + ".conv_2.weight", {cout, cout, 3, 3, 3});
   const int b2 = u->add_param(prefix + ".conv_2.bias", {cout});
   int wm = -1, bm = -1;
@@ -335,6 +389,13 @@ int build_plan(cm_unet* u) {
     }
   }
   u->flops_per_sample = fl;
+  u->grad_off.resize(u->params.size());
+  size_t go = 0;
+  for (size_t i = 0; i < u->params.size(); ++i) {
+    u->grad_off[i] = go;
+    go += (size_t)((u->params[i].numel() + 3) / 4 * 4);   // keep every gradient 16-byte aligned
+  }
+  u->grad_total = go;
   return 0;
 }
 
@@ -356,6 +417,8 @@ int reserve(cm_unet* u, int batch) {
   }
   if (u->arena) CM_CUDA(cudaFree(u->arena));
   u->arena = nullptr;
+  u->train_prepared = 0;   // backward launches bake forward-arena pointers
+  u->live_train_batch = 0;
   size_t off = 0;
   std::vector<size_t> o32(u->tens.size(), 0), o16(u->tens.size(), 0);
   for (size_t i = 0; i < u->tens.size(); ++i) {
@@ -421,6 +484,8 @@ struct RunCtx {
   const int* t_dev;      // device timestep (table mode) or nullptr
   int temb_bstride;
   FinalParams fin;       // eps_out / update parameters (act, w, geometry filled here)
+  bool train = false;    // save GroupNorm statistics, apply Dropout3d scales
+  const float* drop_scale = nullptr;   // [batch][temb_ld] or nullptr
 };
 
 int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
@@ -453,6 +518,13 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         g.silu = op.silu;
         g.out_norm = u->tens[op.out_norm].p16;
         g.out_raw = op.out_raw >= 0 ? u->tens[op.out_raw].p16 : nullptr;
+        if (rc.train) {
+          g.stats = u->gn_stats + (size_t)op.gn_index * rc.batch * 16;
+          if (rc.drop_scale && op.drop_off >= 0) {
+            g.drop_scale = rc.drop_scale + op.drop_off;
+            g.drop_ld = u->temb_ld;
+          }
+        }
         if (int e = gn_silu_enqueue(g, u->gn_partial, st)) return e;
       } break;
       case OP_CONV: {
@@ -509,6 +581,289 @@ int ensure_ready(cm_unet* u, int batch) {
   return 0;
 }
 
+
+// ---- training: workspace, dgrad caches, backward launches -------------------------------------
+
+int reserve_train(cm_unet* u, int batch) {
+  if (batch <= u->train_reserved) return 0;
+  if (u->tarena) CM_CUDA(cudaFree(u->tarena));
+  u->tarena = nullptr;
+  u->train_prepared = 0;
+  const int E = u->cfg.base_channels * u->cfg.time_multiple;
+  const int Cmax = u->max_gn_channels;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  std::vector<size_t> o32(u->tens.size()), o16(u->tens.size(), (size_t)-1);
+  std::vector<char> is_conv_out(u->tens.size(), 0);
+  for (const Op& op : u->ops)
+    if (op.type == OP_CONV) is_conv_out[op.out] = 1;
+  for (size_t i = 0; i < u->tens.size(); ++i) {
+    const Tens& t = u->tens[i];
+    const size_t n = (size_t)batch * u->levels[t.level].pps() * t.C;
+    o32[i] = take(n * 4);
+    if (is_conv_out[i]) o16[i] = take(n * 2);
+  }
+  const size_t o_stats = take((size_t)u->n_gn * batch * 16 * 4);
+  const size_t o_part = take((size_t)batch * 32 * Cmax * 2 * 4);
+  const size_t o_chsum = take((size_t)batch * Cmax * 2 * 4);
+  const size_t o_zero = off;
+  const size_t o_G = take(u->g_elems * 4);
+  const size_t o_colsum = take((size_t)batch * u->colsum_per_sample * 4);
+  const size_t o_dtemb = take((size_t)batch * u->temb_ld * 4);
+  const size_t o_max = take(16);
+  const size_t zero_end = off;
+  const size_t o_e = take((size_t)batch * u->cfg.base_channels * 4);
+  size_t o_t[8];
+  for (int k = 0; k < 8; ++k) o_t[k] = take((size_t)batch * E * 4);
+  const size_t o_scale = take(16);
+  CM_CUDA(cudaMalloc(&u->tarena, off));
+  CM_CUDA(cudaMemset(u->tarena, 0, off));
+  u->tarena_bytes = off;
+  u->g32.assign(u->tens.size(), nullptr);
+  u->g16.assign(u->tens.size(), nullptr);
+  for (size_t i = 0; i < u->tens.size(); ++i) {
+    u->g32[i] = reinterpret_cast<float*>(u->tarena + o32[i]);
+    if (o16[i] != (size_t)-1) u->g16[i] = reinterpret_cast<__half*>(u->tarena + o16[i]);
+  }
+  u->gn_stats = reinterpret_cast<float*>(u->tarena + o_stats);
+  u->gn_bwd_partial = reinterpret_cast<float*>(u->tarena + o_part);
+  u->gn_chsum = reinterpret_cast<float*>(u->tarena + o_chsum);
+  u->zero_region = u->tarena + o_zero;
+  u->zero_bytes = zero_end - o_zero;
+  u->G = reinterpret_cast<float*>(u->tarena + o_G);
+  u->colsum = reinterpret_cast<float*>(u->tarena + o_colsum);
+  u->dtemb = reinterpret_cast<float*>(u->tarena + o_dtemb);
+  u->max_word = reinterpret_cast<unsigned int*>(u->tarena + o_max);
+  u->tsave_e = reinterpret_cast<float*>(u->tarena + o_e);
+  float** tp[8] = {&u->tsave_h1, &u->tsave_h2, &u->ts1, &u->ts2, &u->tds2, &u->tdh2, &u->tds1, &u->tdh1};
+  for (int k = 0; k < 8; ++k) *tp[k] = reinterpret_cast<float*>(u->tarena + o_t[k]);
+  u->loss_scale = reinterpret_cast<float*>(u->tarena + o_scale);
+  u->train_reserved = batch;
+  return 0;
+}
+
+int pack_dgrad(cm_unet* u, cudaStream_t st) {
+  if (u->dpacked) return 0;
+  const int terms = u->cfg.weight_terms;
+  if (!u->dpack) CM_CUDA(cudaMalloc(&u->dpack, (u->dpack_elems + 8) * sizeof(__half)));
+  for (Op& op : u->ops) {
+    if (op.type != OP_CONV) continue;
+    if (int e = pack_dgrad_weights(op.mode, u->params[op.w].ptr, u->dpack + op.dpack_off, op.cout, op.cin,
+                                   terms, 1, st))
+      return e;
+    if (op.cin_extra)
+      if (int e = pack_dgrad_weights(3, u->params[op.wx].ptr, u->dpack + op.dxpack_off, op.cout,
+                                     op.cin_extra, terms, 1, st))
+        return e;
+  }
+  u->dpacked = true;
+  return 0;
+}
+
+int prepare_train(cm_unet* u, int batch) {
+  if (u->train_prepared == batch) return 0;
+  for (Op& op : u->ops) {
+    if (op.type != OP_CONV) continue;
+    const Level& li = u->levels[op.in_level];
+    const Level& lo = u->levels[u->tens[op.out].level];
+    // data gradient of the main source: a conv over dOut (geometry of the OUTPUT grid)
+    if (int rc = conv_prepare(&op.dlaunch, dgrad_mode_of(op.mode), u->g16[op.out], batch, lo.D, lo.H, lo.W,
+                              op.cout, nullptr, 0, u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
+      return rc;
+    op.dlaunch.p.out32 = u->g32[op.in];
+    if (op.cin_extra) {
+      if (int rc = conv_prepare(&op.dxlaunch, 3, u->g16[op.out], batch, lo.D, lo.H, lo.W, op.cout, nullptr, 0,
+                                u->dpack + op.dxpack_off, op.cin_extra, u->cfg.weight_terms))
+        return rc;
+      op.dxlaunch.p.out32 = u->g32[op.extra];
+    }
+    const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
+    if (int rc = wgrad_prepare(&op.wlaunch, op.mode, u->tens[op.in].p16, batch, li.D, li.H, li.W, op.cin, extra,
+                               op.cin_extra, u->g16[op.out], op.cout, u->G + op.g_off))
+      return rc;
+  }
+  u->train_prepared = batch;
+  return 0;
+}
+
+void fill_temb(cm_unet* u, TembParams& tp, const int64_t* t, int batch) {
+  tp = TembParams{};
+  tp.table = u->params[u->p_table].ptr;
+  tp.w1 = u->params[u->p_w1].ptr;
+  tp.b1 = u->params[u->p_b1].ptr;
+  tp.w2 = u->params[u->p_w2].ptr;
+  tp.b2 = u->params[u->p_b2].ptr;
+  tp.wd = u->d_wd;
+  tp.bd = u->d_bd;
+  tp.couts = u->d_couts;
+  tp.offs = u->d_offs;
+  tp.nblocks = (int)u->temb_couts.size();
+  tp.base = u->cfg.base_channels;
+  tp.E = u->cfg.base_channels * u->cfg.time_multiple;
+  tp.t = reinterpret_cast<const long long*>(t);
+  tp.rows = batch;
+  tp.out = u->temb_batch;
+  tp.ld = u->temb_ld;
+}
+
+// Reverse walk of the plan.  Every gradient carries the loss scale S (u->loss_scale[0]); the flat
+// parameter-gradient buffer is multiplied by 1/S at the end.
+int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, int64_t* launches) {
+  const cm_unet_config& c = u->cfg;
+  const int B = u->live_train_batch;
+  const int E = c.base_channels * c.time_multiple;
+  auto gp = [&](int pidx) { return grads + u->grad_off[pidx]; };
+  int64_t nl = 0;
+  CM_CUDA(cudaMemsetAsync(grads, 0, u->grad_total * sizeof(float), st));
+  CM_CUDA(cudaMemsetAsync(u->zero_region, 0, u->zero_bytes, st));
+  const Level& l0 = u->levels[0];
+  const size_t n_eps = (size_t)B * c.out_channels * l0.H * l0.W * c.future_len;
+  if (int e = auto_scale_enqueue(d_eps, n_eps, 64.f, u->loss_scale, u->max_word, st)) return e;
+  nl += 2;
+  std::vector<char> written(u->tens.size(), 0);
+  for (int oi = (int)u->ops.size() - 1; oi >= 0; --oi) {
+    Op& op = u->ops[oi];
+    switch (op.type) {
+      case OP_FINAL: {
+        if (int e = final_conv_backward_enqueue(d_eps, u->loss_scale, u->tens[op.in].p16,
+                                                u->params[u->p_final_w].ptr, u->g32[op.in], gp(u->p_final_w),
+                                                gp(u->p_final_b), B, l0.H, l0.W, l0.D, c.past_len, op.cin,
+                                                c.out_channels, st))
+          return e;
+        written[op.in] = 1;
+        nl += 2;
+      } break;
+      case OP_GN: {
+        GnBwdParams g{};
+        g.src0 = u->tens[op.src0].p32;
+        g.c0 = u->tens[op.src0].C;
+        g.src1 = op.src1 >= 0 ? u->tens[op.src1].p32 : nullptr;
+        g.c1 = op.src1 >= 0 ? u->tens[op.src1].C : 0;
+        g.gamma = u->params[op.gamma].ptr;
+        g.beta = u->params[op.beta].ptr;
+        g.stats = u->gn_stats + (size_t)op.gn_index * B * 16;
+        CM_CHECK(written[op.out_norm], "backward: gradient of '%s' output missing", op.tag.c_str());
+        g.dnorm = u->g32[op.out_norm];
+        g.draw = op.out_raw >= 0 ? u->g32[op.out_raw] : nullptr;
+        if (u->live_drop && op.drop_off >= 0) {
+          g.drop_scale = u->live_drop + op.drop_off;
+          g.drop_ld = u->temb_ld;
+        }
+        g.B = B;
+        g.pixels = u->levels[u->tens[op.src0].level].pps();
+        g.silu = op.silu;
+        g.dsrc0 = u->g32[op.src0];
+        g.init0 = !written[op.src0];
+        written[op.src0] = 1;
+        if (op.src1 >= 0) {
+          g.dsrc1 = u->g32[op.src1];
+          g.init1 = !written[op.src1];
+          written[op.src1] = 1;
+        }
+        g.chsum = u->gn_chsum;
+        g.dgamma = gp(op.gamma);
+        g.dbeta = gp(op.beta);
+        if (int e = gn_backward_enqueue(g, u->gn_bwd_partial, st)) return e;
+        nl += 3;
+      } break;
+      case OP_CONV: {
+        CM_CHECK(written[op.out], "backward: gradient of '%s' output missing", op.tag.c_str());
+        const int pix = u->levels[u->tens[op.out].level].pps();
+        float* cs = op.temb_off >= 0 ? u->dtemb + op.temb_off : u->colsum + (size_t)B * op.colsum_off;
+        const int cs_ld = op.temb_off >= 0 ? u->temb_ld : op.cout;
+        float* fan = nullptr;
+        int fan_init = 0;
+        if (op.resid >= 0) {
+          fan = u->g32[op.resid];
+          fan_init = !written[op.resid];
+          written[op.resid] = 1;
+        }
+        if (int e = cast_colsum_enqueue(u->g32[op.out], u->g16[op.out], fan, fan_init, cs, cs_ld, B, pix,
+                                        op.cout, st))
+          return e;
+        if (op.bias >= 0) {
+          if (int e = rowsum_enqueue(cs, gp(op.bias), B, op.cout, cs_ld, 0, st)) return e;
+          ++nl;
+        }
+        if (op.bias2 >= 0) {
+          if (int e = rowsum_enqueue(cs, gp(op.bias2), B, op.cout, cs_ld, 0, st)) return e;
+          ++nl;
+        }
+        {
+          ConvLaunch L = op.dlaunch;
+          L.p.resid = written[op.in] ? u->g32[op.in] : nullptr;   // accumulate in place
+          written[op.in] = 1;
+          if (int e = conv_enqueue(L, st)) return e;
+        }
+        if (op.cin_extra) {
+          ConvLaunch L = op.dxlaunch;
+          L.p.resid = written[op.extra] ? u->g32[op.extra] : nullptr;
+          written[op.extra] = 1;
+          if (int e = conv_enqueue(L, st)) return e;
+          ++nl;
+        }
+        if (int e = wgrad_enqueue(op.wlaunch, st)) return e;
+        if (int e = unpack_wgrad_enqueue(op.mode, u->G + op.g_off, gp(op.w), op.wx >= 0 ? gp(op.wx) : nullptr,
+                                         op.cout, op.cin, op.cin_extra, 1, st))
+          return e;
+        nl += 4;
+      } break;
+      case OP_ATTN: {
+        CM_CHECK(written[op.ctx], "backward: gradient of '%s' output missing", op.tag.c_str());
+        const Tens& q = u->tens[op.qkv];
+        const int S = u->levels[q.level].pps();
+        if (int e = attn_core_backward_enqueue(q.p32, u->g32[op.ctx], u->g32[op.qkv], B, S, u->tens[op.ctx].C,
+                                               op.heads, st))
+          return e;
+        written[op.qkv] = 1;
+        ++nl;
+      } break;
+      case OP_FIRST: {
+        CM_CHECK(written[op.out], "backward: gradient of the first conv output missing");
+        if (int e = first_conv_wgrad_enqueue(u->live_future, u->live_past, u->g32[op.out], gp(u->p_first_w),
+                                             gp(u->p_first_b), B, l0.H, l0.W, c.past_len, c.future_len,
+                                             c.in_channels, c.base_channels, st))
+          return e;
+        ++nl;
+      } break;
+    }
+  }
+  // ---- time-embedding MLP (embeddings.py:22-34) and the per-block dense_1 (layers.py:35,62) ----
+  const size_t nE = (size_t)B * E;
+  if (int e = silu_forward_enqueue(u->tsave_h1, u->ts1, nE, st)) return e;
+  if (int e = silu_forward_enqueue(u->tsave_h2, u->ts2, nE, st)) return e;
+  nl += 2;
+  for (size_t k = 0; k < u->temb_couts.size(); ++k) {
+    const int co = u->temb_couts[k], off = u->temb_offs[k];
+    const float* dt = u->dtemb + off;
+    // (dense_1.bias gradient == the conv_1 bias gradient: both are the batch sum of dtemb)
+    if (int e = rowsum_enqueue(dt, gp(u->temb_dense_b[k]), B, co, u->temb_ld, 0, st)) return e;
+    if (int e = small_gemm_enqueue(co, E, B, dt, 1, u->temb_ld, u->ts2, E, 1, gp(u->temb_dense_w[k]), E, 0, st))
+      return e;
+    if (int e = small_gemm_enqueue(B, E, co, dt, u->temb_ld, 1, u->params[u->temb_dense_w[k]].ptr, E, 1,
+                                   u->tds2, E, k > 0, st))
+      return e;
+    nl += 3;
+  }
+  if (int e = silu_backward_enqueue(u->tsave_h2, u->tds2, u->tdh2, nE, st)) return e;
+  if (int e = rowsum_enqueue(u->tdh2, gp(u->p_b2), B, E, E, 0, st)) return e;
+  if (int e = small_gemm_enqueue(E, E, B, u->tdh2, 1, E, u->ts1, E, 1, gp(u->p_w2), E, 0, st)) return e;
+  if (int e = small_gemm_enqueue(B, E, E, u->tdh2, E, 1, u->params[u->p_w2].ptr, E, 1, u->tds1, E, 0, st)) return e;
+  if (int e = silu_backward_enqueue(u->tsave_h1, u->tds1, u->tdh1, nE, st)) return e;
+  if (int e = rowsum_enqueue(u->tdh1, gp(u->p_b1), B, E, E, 0, st)) return e;
+  if (int e = small_gemm_enqueue(E, c.base_channels, B, u->tdh1, 1, E, u->tsave_e, c.base_channels, 1,
+                                 gp(u->p_w1), c.base_channels, 0, st))
+    return e;
+  if (int e = scale_inplace_enqueue(grads, u->grad_total, u->loss_scale + 1, st)) return e;
+  nl += 8;
+  if (launches) *launches = nl;
+  return 0;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -540,6 +895,8 @@ int cm_unet_destroy(cm_unet* u) {
   cudaFree(u->d_step);
   cudaFree(u->d_tsteps);
   cudaFree(u->d_coef);
+  cudaFree(u->dpack);
+  cudaFree(u->tarena);
   delete u;
   return 0;
 }
@@ -568,6 +925,8 @@ int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_
   if (p.ptr != dev_ptr) {
     p.ptr = dev_ptr;
     u->packed = false;
+    u->dpacked = false;
+    u->train_prepared = 0;
     if (u->graph_exec) {   // baked pointers are stale
       cudaGraphExecDestroy(u->graph_exec);
       u->graph_exec = nullptr;
@@ -639,6 +998,7 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
     if (int e = temb_enqueue(t, st)) return e;
   }
   u->packed = true;
+  u->dpacked = false;   // dgrad caches are re-derived lazily by the next training forward
   return 0;
 }
 
@@ -693,6 +1053,78 @@ int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, const flo
   rc.fin.eps_out = eps_out;
   return run_ops(u, rc, st, nullptr);
 }
+
+
+/* ---- training ---- */
+int cm_unet_grad_layout(const cm_unet* u, int64_t* offsets, int cap, int64_t* total) {
+  CM_CHECK(u, "null handle");
+  if (offsets) {
+    CM_CHECK(cap >= (int)u->params.size(), "offsets array too small");
+    for (size_t i = 0; i < u->params.size(); ++i) offsets[i] = (int64_t)u->grad_off[i];
+  }
+  if (total) *total = (int64_t)u->grad_total;
+  return 0;
+}
+
+int cm_unet_dropout_layout(const cm_unet* u, int32_t* offsets, int32_t* channels, int cap, int32_t* ld) {
+  CM_CHECK(u, "null handle");
+  const int nb = (int)u->temb_couts.size();
+  if (offsets || channels) CM_CHECK(cap >= nb, "arrays too small (%d blocks)", nb);
+  for (int k = 0; k < nb; ++k) {
+    if (offsets) offsets[k] = u->temb_offs[k];
+    if (channels) channels[k] = u->temb_couts[k];
+  }
+  if (ld) *ld = u->temb_ld;
+  return nb;
+}
+
+int cm_unet_train_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
+                          float* eps_out, int batch, const float* drop_scale, void* stream) {
+  CM_CHECK(u && future && t && past && eps_out, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = ensure_ready(u, batch)) return e;
+  if (int e = backward_init()) return e;
+  if (int e = reserve_train(u, batch)) return e;
+  if (int e = pack_dgrad(u, st)) return e;
+  if (int e = prepare_train(u, batch)) return e;
+  TembParams tp;
+  fill_temb(u, tp, t, batch);
+  tp.save_e = u->tsave_e;
+  tp.save_h1 = u->tsave_h1;
+  tp.save_h2 = u->tsave_h2;
+  if (int e = temb_enqueue(tp, st)) return e;
+  RunCtx rc{};
+  rc.batch = batch;
+  rc.future = future;
+  rc.past = past;
+  rc.temb = u->temb_batch;
+  rc.t_dev = nullptr;
+  rc.temb_bstride = u->temb_ld;
+  rc.fin = FinalParams{};
+  rc.fin.eps_out = eps_out;
+  rc.train = true;
+  rc.drop_scale = drop_scale;
+  if (int e = run_ops(u, rc, st, nullptr)) return e;
+  u->live_train_batch = batch;
+  u->live_future = future;
+  u->live_past = past;
+  u->live_drop = drop_scale;
+  return 0;
+}
+
+int cm_unet_backward(cm_unet* u, const float* d_eps, float* grads, void* stream) {
+  CM_CHECK(u && d_eps && grads, "null argument");
+  CM_CHECK(u->live_train_batch > 0, "cm_unet_backward without a preceding cm_unet_train_forward");
+  CM_CHECK((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grads must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t nl = 0;
+  const int e = run_backward(u, d_eps, grads, st, &nl);
+  u->live_train_batch = 0;   // activations are consumed: one backward per forward
+  u->last_backward_launches = nl;
+  return e;
+}
+
+int64_t cm_last_backward_launches(const cm_unet* u) { return u ? u->last_backward_launches : -1; }
 
 int cm_unet_op_count(const cm_unet* u) { return u ? (int)u->ops.size() : -1; }
 

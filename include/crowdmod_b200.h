@@ -76,6 +76,30 @@ CM_API int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, co
 CM_API int cm_unet_launches_per_forward(const cm_unet* u);
 CM_API double cm_unet_flops_per_sample(const cm_unet* u);
 
+
+/* ---- training: replaces what autograd executes for DDPM_model._train_step / loss.backward()
+ *      (models/diffusion/ddpm.py:111-121,142-144) ---- */
+/* Flat parameter-gradient buffer: offsets[i] = element offset of state_dict entry i (the order
+ * of cm_unet_param_info; every entry 16-byte aligned), *total = elements to allocate. */
+CM_API int cm_unet_grad_layout(const cm_unet* u, int64_t* offsets, int cap, int64_t* total);
+/* Dropout3d scale table layout (layers.py:42,70): block k of the plan (encoder, bottleneck,
+ * decoder ResnetBlocks in order) reads channels[k] columns at offsets[k] of a [batch][*ld] fp32
+ * table holding mask/(1-p).  Returns the number of blocks. */
+CM_API int cm_unet_dropout_layout(const cm_unet* u, int32_t* offsets, int32_t* channels, int cap,
+                                  int32_t* ld);
+/* Training-mode UNet.forward: as cm_unet_forward, plus saves what the backward needs (GroupNorm
+ * statistics, time-MLP pre-activations; every activation stays resident in the workspace) and
+ * applies the optional Dropout3d scales (NULL = no dropout).  future / past / drop_scale must stay
+ * alive until cm_unet_backward returns. */
+CM_API int cm_unet_train_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
+                                 float* eps_out, int batch, const float* drop_scale, void* stream);
+/* Backward of the last cm_unet_train_forward: d_eps [B,C,H,W,F] (gradient of the loss w.r.t. the
+ * predicted noise) -> grads (flat fp32, cm_unet_grad_layout; overwritten).  dgrad / wgrad of every
+ * conv run on tcgen05; gradients are carried with a power-of-two loss scale chosen on the device
+ * and unscaled before returning.  One backward per forward. */
+CM_API int cm_unet_backward(cm_unet* u, const float* d_eps, float* grads, void* stream);
+CM_API int64_t cm_last_backward_launches(const cm_unet* u);
+
 /* Measurement support for bench.py: the plan's ops (tag, kind: 0 first conv, 1 GroupNorm+SiLU,
  * 2 tcgen05 conv, 3 attention core, 4 final conv; algorithmic FLOPs per sample in the
  * reference's dense formulation) and one forward with CUDA events around every launch
@@ -126,6 +150,17 @@ CM_API int cm_op_first_conv(const float* x, const float* past, const float* w, c
                      void* stream);
 CM_API int cm_op_final_conv(const void* act16, const float* w, const float* bias, float* eps_out, int B,
                      int H, int W, int L, int P, int cin, int cout, void* stream);
+
+/* Backward op-level entry points.  Geometry arguments describe the FORWARD conv (mode, input
+ * grid B,D,H,W, cin, cout); dout16 is the fp16 gradient on the forward output grid.
+ * dgrad: dx32 fp32 [B,D,H,W,cin] (overwritten).  wgrad: dw fp32 [cout,cin,taps] with taps in
+ * activation-dim order, dwx fp32 [cout,cin_extra] or NULL; impl 0 = tcgen05 kernel, 1 = scalar
+ * restatement (test only). */
+CM_API int cm_op_conv3d_dgrad(int mode, const void* dout16, int B, int D, int H, int W, int cin,
+                              const float* w, int cout, int terms, float* dx32, void* stream);
+CM_API int cm_op_conv3d_wgrad(int mode, const void* act16, int B, int D, int H, int W, int cin,
+                              const void* extra16, int cin_extra, const void* dout16, int cout,
+                              float* dw, float* dwx, int impl, void* stream);
 
 #ifdef __cplusplus
 }

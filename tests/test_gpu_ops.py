@@ -207,3 +207,100 @@ def test_final_conv(nat, B, H, W, P, Fu, cin, cout):
     torch.cuda.synchronize()
     ref = F.conv3d(act.float().permute(0, 4, 2, 3, 1), w, b, padding=1)[..., P:]
     assert rel_l2(eps, ref) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# backward: data gradient (conv_umma with re-packed weights) and weight gradient (wgrad_umma,
+# MN-major tcgen05) of every conv shape, against torch autograd on the same fp16-rounded operands
+# ---------------------------------------------------------------------------------------------
+def _out_grid(mode, D, H, W):
+    if mode == 1:
+        return (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if mode == 2:
+        return 2 * D, 2 * H, 2 * W
+    return D, H, W
+
+
+def torch_conv_grads(mode, act16, extra16, w, wx, dout16):
+    x = act16.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    w = w.clone().requires_grad_(True)
+    if mode == 0:
+        y = F.conv3d(x, w, None, stride=1, padding=1)
+    elif mode == 1:
+        y = F.conv3d(x, w, None, stride=2, padding=1)
+    elif mode == 2:
+        y = F.conv3d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, stride=1, padding=1)
+    else:
+        y = F.conv3d(x, w, None)
+    wxg = None
+    if extra16 is not None:
+        e = extra16.float().permute(0, 4, 1, 2, 3).contiguous()
+        wxg = wx.clone().requires_grad_(True)
+        y = y + F.conv3d(e, wxg[:, :, None, None, None], None)
+    y.backward(dout16.float().permute(0, 4, 1, 2, 3).contiguous())
+    dx = x.grad.permute(0, 2, 3, 4, 1).contiguous()
+    return dx, w.grad, (wxg.grad if wxg is not None else None)
+
+
+BWD_CASES = [
+    # (mode, B, D, H, W, cin, cout, cin_extra)
+    (0, 2, 12, 36, 8, 32, 32, 0),
+    (0, 2, 6, 18, 4, 64, 64, 32),
+    (0, 3, 3, 9, 2, 128, 128, 64),
+    (0, 2, 3, 9, 2, 256, 128, 0),
+    (0, 1, 12, 36, 8, 96, 32, 0),
+    (0, 1, 6, 18, 4, 192, 64, 0),
+    (1, 2, 12, 36, 8, 32, 32, 0),
+    (1, 3, 6, 18, 4, 64, 64, 0),
+    (2, 2, 3, 9, 2, 128, 128, 0),
+    (2, 1, 6, 18, 4, 64, 64, 0),
+    (3, 3, 3, 9, 2, 128, 384, 0),
+    (3, 3, 3, 9, 2, 128, 128, 0),
+]
+
+
+def _bwd_inputs(mode, B, D, H, W, cin, cout, cx, seed=3):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    act = torch.randn(B, D, H, W, cin, device="cuda", generator=g).half()
+    k = 1 if mode == 3 else 3
+    w = torch.randn(cout, cin, k, k, k, device="cuda", generator=g) / (cin * k ** 3) ** 0.5
+    od, oh, ow = _out_grid(mode, D, H, W)
+    extra = wx = None
+    if cx:
+        extra = torch.randn(B, od, oh, ow, cx, device="cuda", generator=g).half()
+        wx = torch.randn(cout, cx, device="cuda", generator=g) / cx ** 0.5
+    dout = torch.randn(B, od, oh, ow, cout, device="cuda", generator=g).half()
+    return act, w, extra, wx, dout
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d" % c)
+def test_conv_dgrad_vs_torch_autograd(nat, case):
+    mode, B, D, H, W, cin, cout, cx = case
+    act, w, extra, wx, dout = _bwd_inputs(*case)
+    dx = torch.full((B, D, H, W, cin), float("nan"), device="cuda")
+    nat.check(nat.lib().cm_op_conv3d_dgrad(mode, nat.ptr(dout), B, D, H, W, cin, nat.ptr(w), cout, 2,
+                                           nat.ptr(dx), nat.current_stream()))
+    torch.cuda.synchronize()
+    assert nat.lib().cm_device_error() == 0
+    ref, _, _ = torch_conv_grads(mode, act, None, w, None, dout)
+    e = rel_l2(dx, ref)
+    assert e <= 3e-5, f"dgrad rel-L2 {e:.3e}; " + describe_mismatch(dx, ref)
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d" % c)
+@pytest.mark.parametrize("impl", [1, 0], ids=["scalar", "umma"])
+def test_conv_wgrad_vs_torch_autograd(nat, case, impl):
+    mode, B, D, H, W, cin, cout, cx = case
+    act, w, extra, wx, dout = _bwd_inputs(*case)
+    dw = torch.full_like(w, float("nan"))
+    dwx = torch.full_like(wx, float("nan")) if cx else None
+    nat.check(nat.lib().cm_op_conv3d_wgrad(mode, nat.ptr(act), B, D, H, W, cin, nat.ptr(extra), cx,
+                                           nat.ptr(dout), cout, nat.ptr(dw), nat.ptr(dwx), impl,
+                                           nat.current_stream()))
+    torch.cuda.synchronize()
+    assert nat.lib().cm_device_error() == 0
+    _, rw, rwx = torch_conv_grads(mode, act, extra, w, wx, dout)
+    e = rel_l2(dw, rw)
+    assert e <= 3e-5, f"wgrad rel-L2 {e:.3e}; " + describe_mismatch(dw.reshape(cout, -1), rw.reshape(cout, -1))
+    if cx:
+        assert rel_l2(dwx, rwx) <= 3e-5
