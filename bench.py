@@ -247,6 +247,10 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    train = None
+    if not args.no_train:
+        train = train_bench(rank, world, dev, cpu_baseline=not args.no_cpu_baseline)
+
     if rank == 0:
         total = n * world * args.steps
         value = total / (ms / 1e3)
@@ -264,6 +268,8 @@ def run_native(args, rank, world, local_rank):
             "clocks": clk,
         }
         line["roofline"] = roofline(net, nat, past, n, dev, ms / args.steps / args.timesteps)
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             s_it = cpu_oracle_sample(n, args.ref_iters, threads)
@@ -274,6 +280,102 @@ def run_native(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ---- training leg (BASELINE config #4: HERMES-CR-120.yml, 28x24 grid, batch 64 per GPU) ----------
+H_ROWS, H_COLS = 28, 24
+
+
+def train_bench(rank, world, dev, steps=8, warmup=4, cpu_baseline=True):
+    """DDPM_model._train_step + loss.backward() + Adam step (reference ddpm.py:111-121,142-144)
+    through the reference-facing modules: native training forward/backward (tcgen05 fprop / dgrad
+    / wgrad), one flat-gradient all-reduce when world > 1, torch.optim.Adam as in the reference.
+    Returns a dict added to the bench line under "train"."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
+    from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM
+    n = 64
+    torch.manual_seed(42)
+    net = UNet(**ATC).to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=5e-5, betas=(0.5, 0.999), weight_decay=3e-3)
+    fs = DDPM(timesteps=T_STEPS, scale=SCALE).to(dev)
+    past = synthetic_macroprops(n, 3, H_ROWS, H_COLS, PAST, 1234 + rank, dev)
+    fut = synthetic_macroprops(n, 3, H_ROWS, H_COLS, FUT, 4321 + rank, dev)
+
+    def step():
+        t = torch.randint(0, T_STEPS, (n,), device=dev)
+        x_t, eps = fs(fut, t)
+        loss = F.mse_loss(net(x_t, t, past), eps)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    step_ms = ms.item()
+    # forward / backward split on rank 0 (events around the two native calls)
+    t = torch.randint(0, T_STEPS, (n,), device=dev)
+    x_t, eps = fs(fut, t)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    loss = F.mse_loss(net(x_t, t, past), eps)
+    e[1].record()
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    e[2].record()
+    torch.cuda.synchronize()
+    plan = net._plan(H_ROWS, H_COLS, PAST, FUT)
+    fl = net.native_stats(H_ROWS, H_COLS, PAST, FUT)[1]
+    out = {"workload": "config/HERMES-CR-120.yml: DDPM-UNet training step (t~U, q-sample, fwd, MSE, bwd, Adam), "
+                       "grid 28x24, past 5 + future 3, batch 64 per GPU, dropout 0.1",
+           "step_ms": step_ms, "samples_per_s": n * world / (step_ms * 1e-3),
+           "fwd_ms": e[0].elapsed_time(e[1]), "bwd_ms": e[1].elapsed_time(e[2]),
+           "loss": float(loss.item()), "grad_allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer"
+           if world > 1 else "none (1 GPU)",
+           "algorithmic_tflops": 3.0 * fl * n / (step_ms * 1e-3) / 1e12,
+           "bwd_launches": int(plan.n.lib().cm_last_backward_launches(plan.handle))}
+    if cpu_baseline and rank == 0 and world == 1:
+        out["cpu_baseline"] = train_cpu_baseline()
+    return out
+
+
+def train_cpu_baseline(n=8):
+    """One fwd+bwd of the reference path's CPU restatement on the host cores (bounded sample)."""
+    import torch.nn.functional as F
+    from oracle import ddpm_oracle as do
+    from oracle import unet_oracle as uo
+    from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "time_blocks.0" not in k)
+          for k, v in UNet(**ATC).state_dict().items()}
+    s = do.schedule(T_STEPS, SCALE)
+    past = do.synthetic_macroprops(n, 3, H_ROWS, H_COLS, PAST, 1234)
+    fut = do.synthetic_macroprops(n, 3, H_ROWS, H_COLS, FUT, 4321)
+    den = lambda x, tt, p: uo.unet_forward(sd, x, tt, p, num_res_blocks=1, num_levels=3)
+    t = torch.randint(0, T_STEPS, (n,))
+    eps = torch.randn_like(fut)
+    t0 = time.perf_counter()
+    do.train_loss(den, s, fut, past, t, eps).backward()
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"one fwd+bwd at batch {n} (of 64) on the host cores, oracle/ restatement"}
 
 
 def roofline(net, nat, past, n, dev, step_ms):
@@ -335,6 +437,7 @@ def main():
     ap.add_argument("--timesteps", type=int, default=T_STEPS)
     ap.add_argument("--ref-iters", type=int, default=8, help="CPU denoiser iterations per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (extra key 'train')")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

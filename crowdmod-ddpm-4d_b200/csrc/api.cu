@@ -125,7 +125,15 @@ int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, const fl
   g.gamma = gamma; g.beta = beta; g.B = B; g.pixels = pixels; g.eps = eps; g.silu = silu;
   g.out_norm = static_cast<__half*>(out_norm16);
   g.out_raw = static_cast<__half*>(out_raw16);
-  return gn_silu_enqueue(g, nullptr, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = nullptr;
+  CM_CUDA(cudaMalloc(&partial, (size_t)B * 32 * 8 * 3 * sizeof(float)));
+  const int rc = gn_silu_enqueue(g, partial, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(partial);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
 }
 
 int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream) {

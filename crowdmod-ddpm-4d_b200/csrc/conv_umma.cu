@@ -198,7 +198,16 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
   p.err_flag = device_error_flag();
 
   const int stage_bytes = CONV_BM * bk * 2 + terms * bn * bk * 2;
+  // Few CTAs (coarse levels: 27 M tiles) are TMA-latency bound: give each all the shared memory
+  // it can use.  Many CTAs per SM: keep stages modest so that several CTAs stay co-resident.
   int stages = 4;
+  {
+    const long ctas = (long)((p.M + CONV_BM - 1) / CONV_BM) * (cout / bn) * p.nphase;
+    const long per_sm = (ctas + 147) / 148;
+    const long budget = 200 * 1024 / (per_sm < 3 ? per_sm : 3);
+    const long fit = budget / stage_bytes;
+    if (fit > stages) stages = (int)(fit < CONV_MAX_STAGES ? fit : CONV_MAX_STAGES);
+  }
   if (const char* e = getenv("CM_DBG_STAGES")) stages = atoi(e);
   if (const char* e = getenv("CM_DBG_SKIP")) p.dbg = atoi(e);
   if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;

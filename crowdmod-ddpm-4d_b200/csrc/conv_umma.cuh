@@ -26,7 +26,7 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 
 constexpr int CONV_BM = 128;        // UMMA M (cta_group::1)
 constexpr int CONV_THREADS = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int CONV_MAX_STAGES = 6;
+constexpr int CONV_MAX_STAGES = 8;
 
 struct ConvParams {
   CUtensorMap amap[8];   // main source, one map per output phase (1 normally, 8 for upsample)
@@ -79,7 +79,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + CONV_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* colv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 128);   // [BN] per-column epilogue constants
+  float* colv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 192);   // [BN] per-column epilogue constants
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

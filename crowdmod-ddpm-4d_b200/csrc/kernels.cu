@@ -4,6 +4,7 @@
 #include "conv_umma.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 
 namespace cm {
@@ -292,14 +293,325 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
   cluster.sync();   // peers may still be reading slice_stat through DSMEM
 }
 
+
+// =============================================================================================
+// GroupNorm as two fully parallel streaming kernels (default path; the cluster kernel above is
+// kept behind CM_GN_CLUSTER=1 for A/B measurements):
+//   gn_stats2_kernel : CTA = (pixel slice, sample).  Every thread accumulates shifted sums of its
+//                      (fixed) channel quad, converts them to (n, mean, M2) and the CTA merges
+//                      the triples per group with Chan's formula in a fixed tree -> partial[b][slice][g].
+//   gn_apply2_kernel : CTA = (pixel slice, sample).  Merges the sample's slice statistics in slice
+//                      order, then one pass  fp32 -> normalise/affine/SiLU(/Dropout3d) -> fp16.
+// The slicing depends only on the pixel index inside the sample, so a sample's result is
+// bit-identical wherever it sits in the batch (and on whichever GPU its shard runs).
+// =============================================================================================
+constexpr int GN2_T = 256;
+constexpr int GN2_MAX_SLICES = 32;
+
+struct Chan3 {
+  float n, mean, m2;
+};
+__device__ __forceinline__ Chan3 chan_merge(const Chan3 a, const Chan3 b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  const float nn = a.n + b.n;
+  const float delta = b.mean - a.mean;
+  Chan3 r;
+  r.n = nn;
+  r.mean = a.mean + delta * (b.n / nn);
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / nn);
+  return r;
+}
+
+__global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int slices, float* __restrict__ partial) {
+  __shared__ float tri[GN2_T][3];
+  const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2, vpp = Q >> 3;
+  // blockDim.x == GN2_T; the first T = floor(GN2_T/Q)*Q threads sweep the data (fixed channel quad)
+  const int tid = threadIdx.x;
+  const int T = (GN2_T / Q) * Q;
+  const int b = blockIdx.y, slice = blockIdx.x;
+  const int px0 = (int)(((long long)p.pixels * slice) / slices);
+  const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
+  const int c = (tid % Q) * 4;
+  const int rows_per_iter = T / Q;
+  const bool from0 = c < p.c0;
+  const int src_ld = from0 ? p.c0 : p.c1;
+  const float* src = (from0 ? p.src0 + c : p.src1 + (c - p.c0)) + ((size_t)b * p.pixels) * src_ld;
+  float s1 = 0.f, s2 = 0.f, k = 0.f, cnt = 0.f;
+  int px = px0 + tid / Q;
+  if (tid < T && px < px1) {
+    // batches of 8 independent 16-byte loads; the shift k is this thread's first value
+    float4 v[8];
+    bool first = true;
+    for (; px < px1; px += 8 * rows_per_iter) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int pj = px + j * rows_per_iter;
+        if (pj < px1) v[j] = *reinterpret_cast<const float4*>(src + (size_t)pj * src_ld);
+      }
+      if (first) { k = v[0].x; first = false; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (px + j * rows_per_iter < px1) {
+          const float dx = v[j].x - k, dy = v[j].y - k, dz = v[j].z - k, dw = v[j].w - k;
+          s1 += (dx + dy) + (dz + dw);
+          s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          cnt += 4.f;
+        }
+      }
+    }
+  }
+  {
+    const float d = cnt > 0.f ? s1 / cnt : 0.f;
+    tri[tid][0] = cnt;
+    tri[tid][1] = k + d;
+    tri[tid][2] = fmaxf(s2 - s1 * d, 0.f);
+  }
+  __syncthreads();
+  // warp gi merges the threads of group gi: t = r*Q + gi*vpp + o  (r < T/Q, o < vpp)
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < 8) {
+    const int members = (T / Q) * vpp;            // = T/8 <= 32
+    Chan3 a{0.f, 0.f, 0.f};
+    if (lane < members) {
+      const int r = lane / vpp, o = lane - r * vpp;
+      const int t = r * Q + warp * vpp + o;
+      a = Chan3{tri[t][0], tri[t][1], tri[t][2]};
+    }
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1) {
+      Chan3 o;
+      o.n = __shfl_xor_sync(0xffffffffu, a.n, w);
+      o.mean = __shfl_xor_sync(0xffffffffu, a.mean, w);
+      o.m2 = __shfl_xor_sync(0xffffffffu, a.m2, w);
+      // merge (lower lane, upper lane) in that order on both sides: identical results
+      a = (lane & w) ? chan_merge(o, a) : chan_merge(a, o);
+    }
+    if (lane == 0) {
+      float* o = partial + (((size_t)b * GN2_MAX_SLICES + slice) * 8 + warp) * 3;
+      o[0] = a.n;
+      o[1] = a.mean;
+      o[2] = a.m2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int slices, int stat_slices,
+                                                          const float* __restrict__ partial) {
+  __shared__ float stat[2][8];
+  const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2;
+  const int tid = threadIdx.x;
+  const int T = (GN2_T / Q) * Q;
+  const int b = blockIdx.y, slice = blockIdx.x;
+  __shared__ float ptri[GN2_MAX_SLICES * 8 * 3];
+  for (int i = tid; i < stat_slices * 24; i += GN2_T)       // all slice statistics in one round trip
+    ptri[i] = partial[(size_t)b * GN2_MAX_SLICES * 24 + i];
+  __syncthreads();
+  if (tid < 8) {
+    Chan3 a{0.f, 0.f, 0.f};
+    for (int sidx = 0; sidx < stat_slices; ++sidx) {
+      const float* o = ptri + (sidx * 8 + tid) * 3;
+      a = chan_merge(a, Chan3{o[0], o[1], o[2]});
+    }
+    stat[0][tid] = a.mean;
+    stat[1][tid] = 1.0f / sqrtf(a.m2 / a.n + p.eps);
+    if (p.stats && slice == 0) {
+      p.stats[(b * 8 + tid) * 2 + 0] = a.mean;
+      p.stats[(b * 8 + tid) * 2 + 1] = stat[1][tid];
+    }
+  }
+  __syncthreads();
+  const int px0 = (int)(((long long)p.pixels * slice) / slices);
+  const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
+  const int c = (tid % Q) * 4;
+  const int g = c / cg_ch;
+  const float mean = stat[0][g], rstd = stat[1][g];
+  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
+  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  const int rows_per_iter = T / Q;
+  const bool from0 = c < p.c0;
+  const int src_ld = from0 ? p.c0 : p.c1;
+  const size_t pix_base = (size_t)b * p.pixels;
+  const float* src = (from0 ? p.src0 + c : p.src1 + (c - p.c0)) + pix_base * src_ld;
+  __half* on = p.out_norm + pix_base * C + c;
+  __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
+  if (tid >= T) return;
+  for (int px = px0 + tid / Q; px < px1; px += 4 * rows_per_iter) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pj = px + j * rows_per_iter;
+      if (pj < px1) v[j] = *reinterpret_cast<const float4*>(src + (size_t)pj * src_ld);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pj = px + j * rows_per_iter;
+      if (pj >= px1) break;
+      float y0 = fmaf(v[j].x, sc.x, sh.x), y1 = fmaf(v[j].y, sc.y, sh.y), y2 = fmaf(v[j].z, sc.z, sh.z),
+            y3 = fmaf(v[j].w, sc.w, sh.w);
+      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+      y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
+      const size_t o = (size_t)pj * C;
+      __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(on + o) = u;
+      if (orw) {
+        __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
+        u.x = *reinterpret_cast<uint32_t*>(&r0);
+        u.y = *reinterpret_cast<uint32_t*>(&r1);
+        *reinterpret_cast<uint2*>(orw + o) = u;
+      }
+    }
+  }
+}
+
+
+// Small tensors (coarse levels): ONE kernel, one CTA per sample, the sample lives in registers
+// between the statistics and the apply phase (<= GNS_CACHE float4 per thread).
+constexpr int GNS_CACHE = 8;
+
+__global__ void __launch_bounds__(1024) gn_small_kernel(const GnParams p) {
+  __shared__ float tri[1024][3];
+  __shared__ float stat[2][8];
+  const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2, vpp = Q >> 3;
+  const int tid = threadIdx.x;
+  const int T = (blockDim.x / Q) * Q;            // sweeping threads (fixed channel quad each)
+  const int b = blockIdx.x;
+  const int c = (tid % Q) * 4;
+  const int rows_per_iter = T / Q;
+  const bool from0 = c < p.c0;
+  const int src_ld = from0 ? p.c0 : p.c1;
+  const size_t pix_base = (size_t)b * p.pixels;
+  const float* src = (from0 ? p.src0 + c : p.src1 + (c - p.c0)) + pix_base * src_ld;
+  float4 v[GNS_CACHE];
+  float s1 = 0.f, s2 = 0.f, k = 0.f, cnt = 0.f;
+  const int px0 = tid / Q;
+  if (tid < T) {
+#pragma unroll
+    for (int j = 0; j < GNS_CACHE; ++j) {
+      const int pj = px0 + j * rows_per_iter;
+      if (pj < p.pixels) v[j] = *reinterpret_cast<const float4*>(src + (size_t)pj * src_ld);
+    }
+    if (px0 < p.pixels) k = v[0].x;
+#pragma unroll
+    for (int j = 0; j < GNS_CACHE; ++j) {
+      if (px0 + j * rows_per_iter < p.pixels) {
+        const float dx = v[j].x - k, dy = v[j].y - k, dz = v[j].z - k, dw = v[j].w - k;
+        s1 += (dx + dy) + (dz + dw);
+        s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        cnt += 4.f;
+      }
+    }
+  }
+  {
+    const float d = cnt > 0.f ? s1 / cnt : 0.f;
+    tri[tid][0] = cnt;
+    tri[tid][1] = k + d;
+    tri[tid][2] = fmaxf(s2 - s1 * d, 0.f);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < 8) {
+    const int members = (T / Q) * vpp;            // = T/8 <= 128
+    Chan3 a{0.f, 0.f, 0.f};
+    for (int m = lane; m < members; m += 32) {    // fixed order: lane-strided, then the butterfly
+      const int r = m / vpp, o = m - r * vpp;
+      const int t = r * Q + warp * vpp + o;
+      a = chan_merge(a, Chan3{tri[t][0], tri[t][1], tri[t][2]});
+    }
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1) {
+      Chan3 o;
+      o.n = __shfl_xor_sync(0xffffffffu, a.n, w);
+      o.mean = __shfl_xor_sync(0xffffffffu, a.mean, w);
+      o.m2 = __shfl_xor_sync(0xffffffffu, a.m2, w);
+      a = (lane & w) ? chan_merge(o, a) : chan_merge(a, o);
+    }
+    if (lane == 0) {
+      stat[0][warp] = a.mean;
+      stat[1][warp] = 1.0f / sqrtf(a.m2 / a.n + p.eps);
+      if (p.stats) {
+        p.stats[(b * 8 + warp) * 2 + 0] = a.mean;
+        p.stats[(b * 8 + warp) * 2 + 1] = stat[1][warp];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid >= T) return;
+  const int g = c / cg_ch;
+  const float mean = stat[0][g], rstd = stat[1][g];
+  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
+  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  __half* on = p.out_norm + pix_base * C + c;
+  __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
+#pragma unroll
+  for (int j = 0; j < GNS_CACHE; ++j) {
+    const int pj = px0 + j * rows_per_iter;
+    if (pj >= p.pixels) break;
+    float y0 = fmaf(v[j].x, sc.x, sh.x), y1 = fmaf(v[j].y, sc.y, sh.y), y2 = fmaf(v[j].z, sc.z, sh.z),
+          y3 = fmaf(v[j].w, sc.w, sh.w);
+    if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+    y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
+    const size_t o = (size_t)pj * C;
+    __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(on + o) = u;
+    if (orw) {
+      __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
+      u.x = *reinterpret_cast<uint32_t*>(&r0);
+      u.y = *reinterpret_cast<uint32_t*>(&r1);
+      *reinterpret_cast<uint2*>(orw + o) = u;
+    }
+  }
+}
+
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 int gn_chunks(int pixels, int C) { (void)pixels; (void)C; return GN_CLUSTER; }
 
 int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st) {
-  (void)partial;
   const int C = p.c0 + p.c1;
   CM_CHECK(C % 32 == 0 && p.c0 % 4 == 0, "GroupNorm channels must be a multiple of 32 (C=%d)", C);
+  static const bool use_cluster = getenv("CM_GN_CLUSTER") != nullptr;
+  if (partial && !use_cluster && C / 4 <= GN2_T) {
+    const int Q = C / 4;
+    const long nvec = (long)p.pixels * Q;                       // float4 per sample
+    if (nvec <= 1024L * GNS_CACHE) {
+      // one CTA per sample: threads = a multiple of 32 covering nvec/GNS_CACHE, >= Q
+      int T = (int)((nvec + GNS_CACHE - 1) / GNS_CACHE);
+      if (T < Q) T = Q;
+      T = (T + 31) / 32 * 32;
+      if (T < 256) T = 256;
+      while ((long)(T / Q) * Q * GNS_CACHE < nvec) T += 32;      // sweeping threads are floor(T/Q)*Q
+      if (T <= 1024) {
+        gn_small_kernel<<<p.B, T, 0, st>>>(p);
+        CM_CUDA(cudaGetLastError());
+        return 0;
+      }
+    }
+    // slices: one wave of <= 4 CTAs per SM over the batch, >= 4 vectors per thread
+    int slices = (148 * 4) / p.B;
+    const int max_slices = (int)((nvec + 4 * GN2_T - 1) / (4 * GN2_T));
+    if (slices > max_slices) slices = max_slices;
+    if (slices > GN2_MAX_SLICES) slices = GN2_MAX_SLICES;
+    if (slices < 1) slices = 1;
+    gn_stats2_kernel<<<dim3(slices, p.B), GN2_T, 0, st>>>(p, slices, partial);
+    gn_apply2_kernel<<<dim3(slices, p.B), GN2_T, 0, st>>>(p, slices, slices, partial);
+    CM_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int Q = C / 4;
   const int L = Q / gcd_i(Q, 32) * 32;                 // lcm(Q, 32)
   CM_CHECK(L <= 384, "GroupNorm: too many channels (C=%d)", C);
@@ -634,80 +946,208 @@ int temb_enqueue(const TembParams& p, cudaStream_t st) {
 }
 
 // =============================================================================================
-// attention core (S <= a few hundred tokens: whole K/V of one (sample, head) lives in smem)
+// attention core: softmax(Q K^T / sqrt(dh)) V per (sample, head) on mma.sync m16n8k16 (S is a few
+// dozen tokens: far too small for a tcgen05 tile, and the scalar version was shared-memory-bound).
+// One warp owns 16 query rows end to end (flash-attention register dataflow, no online rescaling
+// needed since all S keys fit one pass).  Q and K enter as fp16 hi+lo pairs (3 MMAs per product:
+// hi*hi + hi*lo + lo*hi), so the scores are fp32-accurate; P and V are single fp16 operands like
+// every other contraction operand of the path.
 // =============================================================================================
-constexpr int ATTN_WARPS = 8;
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t* hi, uint32_t* lo) {
+  const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
+  __half2 h = __halves2half2(hx, hy);
+  __half2 l = __floats2half2_rn(x - __half2float(hx), y - __half2float(hy));
+  *hi = *reinterpret_cast<uint32_t*>(&h);
+  *lo = *reinterpret_cast<uint32_t*>(&l);
+}
 
-__global__ void __launch_bounds__(ATTN_WARPS * 32)
-attn_core_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx, int S, int C, int heads) {
-  extern __shared__ float sm[];
+// DH = head dim padded to a multiple of 16 (16 | 32 | 64; dh = C/heads may be 8 -> zero padded),
+// NT = key tiles of 8 (S_pad = 8*NT, multiple of 16)
+template <int DH, int NT>
+__global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx,
+                                                          int S, int C, int heads) {
   const int dh = C / heads;
+  constexpr int SP = NT * 8;            // padded sequence length
+  constexpr int KLD = DH + 8;           // smem row stride (halfs) of K  [SP][KLD]
+  constexpr int VLD = SP + 8;           // smem row stride (halfs) of V^T [DH][VLD]
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __half* Kh = reinterpret_cast<__half*>(smraw);
+  __half* Kl = Kh + SP * KLD;
+  __half* Vt = Kl + SP * KLD;
   const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
-  float* Ks = sm;                          // [S][dh+1]
-  float* Vs = Ks + (size_t)S * (dh + 1);   // [S][dh]
-  float* Qs = Vs + (size_t)S * dh;         // [ATTN_WARPS][dh]
-  float* Pw = Qs + ATTN_WARPS * dh;        // [ATTN_WARPS][S]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* base = qkv + (size_t)b * S * 3 * C;
-  for (int idx = threadIdx.x; idx < S * dh; idx += blockDim.x) {
-    const int j = idx / dh, d = idx - j * dh;
-    Ks[j * (dh + 1) + d] = base[(size_t)j * 3 * C + C + hd * dh + d];
-    Vs[j * dh + d] = base[(size_t)j * 3 * C + 2 * C + hd * dh + d];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (size_t)b * S * 3 * C + hd * dh;
+  // ---- Q fragments straight from global (issued before the K/V staging barrier) ----
+  const int i0 = warp * 16 + g, i1 = i0 + 8;
+  const float scale = rsqrtf((float)dh);
+  uint32_t qh[DH / 16][4], ql[DH / 16][4];
+#pragma unroll
+  for (int kt = 0; kt < DH / 16; ++kt) {
+    float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+    const bool lo_ok = kt * 16 + 2 * t < dh, hi_ok = kt * 16 + 8 + 2 * t < dh;
+    if (i0 < S) {
+      if (lo_ok) v00 = *reinterpret_cast<const float2*>(base + (size_t)i0 * 3 * C + kt * 16 + 2 * t);
+      if (hi_ok) v01 = *reinterpret_cast<const float2*>(base + (size_t)i0 * 3 * C + kt * 16 + 8 + 2 * t);
+    }
+    if (i1 < S) {
+      if (lo_ok) v10 = *reinterpret_cast<const float2*>(base + (size_t)i1 * 3 * C + kt * 16 + 2 * t);
+      if (hi_ok) v11 = *reinterpret_cast<const float2*>(base + (size_t)i1 * 3 * C + kt * 16 + 8 + 2 * t);
+    }
+    split_h2(v00.x * scale, v00.y * scale, &qh[kt][0], &ql[kt][0]);
+    split_h2(v10.x * scale, v10.y * scale, &qh[kt][1], &ql[kt][1]);
+    split_h2(v01.x * scale, v01.y * scale, &qh[kt][2], &ql[kt][2]);
+    split_h2(v11.x * scale, v11.y * scale, &qh[kt][3], &ql[kt][3]);
+  }
+  // ---- stage K (hi, lo) and V^T as fp16 ----
+  for (int idx = tid; idx < SP * (DH / 2); idx += blockDim.x) {
+    const int j = idx / (DH / 2), d = (idx - j * (DH / 2)) * 2;
+    float2 kv = make_float2(0.f, 0.f), vv = kv;
+    if (j < S && d < dh) {
+      kv = *reinterpret_cast<const float2*>(base + (size_t)j * 3 * C + C + d);
+      vv = *reinterpret_cast<const float2*>(base + (size_t)j * 3 * C + 2 * C + d);
+    }
+    uint32_t hi, lo;
+    split_h2(kv.x, kv.y, &hi, &lo);
+    *reinterpret_cast<uint32_t*>(Kh + j * KLD + d) = hi;
+    *reinterpret_cast<uint32_t*>(Kl + j * KLD + d) = lo;
+    Vt[d * VLD + j] = __float2half_rn(vv.x);
+    Vt[(d + 1) * VLD + j] = __float2half_rn(vv.y);
   }
   __syncthreads();
-  const float scale = rsqrtf((float)dh);
-  float* q = Qs + warp * dh;
-  float* pw = Pw + warp * S;
-  for (int i = warp; i < S; i += ATTN_WARPS) {
-    for (int d = lane; d < dh; d += 32) q[d] = base[(size_t)i * 3 * C + hd * dh + d] * scale;
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) {
-      const float* kr = Ks + j * (dh + 1);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int d = 0; d < dh; d += 4) {
-        a0 = fmaf(q[d], kr[d], a0);
-        a1 = fmaf(q[d + 1], kr[d + 1], a1);
-        a2 = fmaf(q[d + 2], kr[d + 2], a2);
-        a3 = fmaf(q[d + 3], kr[d + 3], a3);
-      }
-      const float a = (a0 + a1) + (a2 + a3);
-      pw[j] = a;
-      mx = fmaxf(mx, a);
+  if (warp * 16 >= S) return;
+  // ---- scores: 16 x SP per warp ----
+  float sc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+    const int j = nt * 8 + g;
+#pragma unroll
+    for (int kt = 0; kt < DH / 16; ++kt) {
+      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(Kh + j * KLD + kt * 16 + 2 * t);
+      const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(Kh + j * KLD + kt * 16 + 8 + 2 * t);
+      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(Kl + j * KLD + kt * 16 + 2 * t);
+      const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(Kl + j * KLD + kt * 16 + 8 + 2 * t);
+      mma_16816(sc[nt], ql[kt], bh0, bh1);
+      mma_16816(sc[nt], qh[kt], bl0, bl1);
+      mma_16816(sc[nt], qh[kt], bh0, bh1);
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < S; j += 32) {
-      const float ev = expf(pw[j] - mx);
-      pw[j] = ev;
-      sum += ev;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    const float inv = 1.0f / sum;
-    for (int d = lane; d < dh; d += 32) {
-      float a0 = 0.f, a1 = 0.f;
-      int j = 0;
-      for (; j + 1 < S; j += 2) {
-        a0 = fmaf(pw[j], Vs[j * dh + d], a0);
-        a1 = fmaf(pw[j + 1], Vs[(j + 1) * dh + d], a1);
-      }
-      if (j < S) a0 = fmaf(pw[j], Vs[j * dh + d], a0);
-      ctx[((size_t)b * S + i) * C + hd * dh + d] = __float2half_rn((a0 + a1) * inv);
-    }
-    __syncwarp();
   }
+  // ---- softmax over keys (rows g and g+8 live in the 4 lanes of a quad) ----
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int j = nt * 8 + 2 * t;
+    if (j >= S) sc[nt][0] = sc[nt][2] = -INFINITY;
+    if (j + 1 >= S) sc[nt][1] = sc[nt][3] = -INFINITY;
+    m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+    m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    sc[nt][0] = expf(sc[nt][0] - m0);
+    sc[nt][1] = expf(sc[nt][1] - m0);
+    sc[nt][2] = expf(sc[nt][2] - m1);
+    sc[nt][3] = expf(sc[nt][3] - m1);
+    l0 += sc[nt][0] + sc[nt][1];
+    l1 += sc[nt][2] + sc[nt][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  // ---- context = P V  (P normalised before the fp16 rounding) ----
+  float oc[DH / 8][4];
+#pragma unroll
+  for (int dt = 0; dt < DH / 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NT / 2; ++kt) {
+    uint32_t pa[4];
+    pa[0] = pack_h2(sc[2 * kt][0] * inv0, sc[2 * kt][1] * inv0);
+    pa[1] = pack_h2(sc[2 * kt][2] * inv1, sc[2 * kt][3] * inv1);
+    pa[2] = pack_h2(sc[2 * kt + 1][0] * inv0, sc[2 * kt + 1][1] * inv0);
+    pa[3] = pack_h2(sc[2 * kt + 1][2] * inv1, sc[2 * kt + 1][3] * inv1);
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; ++dt) {
+      const int d = dt * 8 + g;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Vt + d * VLD + kt * 16 + 2 * t);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vt + d * VLD + kt * 16 + 8 + 2 * t);
+      mma_16816(oc[dt], pa, b0, b1);
+    }
+  }
+  __half* ob = ctx + (size_t)b * S * C + hd * dh;
+#pragma unroll
+  for (int dt = 0; dt < DH / 8; ++dt) {
+    const int d = dt * 8 + 2 * t;
+    if (d >= dh) continue;
+    if (i0 < S) *reinterpret_cast<uint32_t*>(ob + (size_t)i0 * C + d) = pack_h2(oc[dt][0], oc[dt][1]);
+    if (i1 < S) *reinterpret_cast<uint32_t*>(ob + (size_t)i1 * C + d) = pack_h2(oc[dt][2], oc[dt][3]);
+  }
+}
+
+template <int DH, int NT>
+static int attn_launch(const float* qkv, __half* ctx, int B, int S, int C, int heads, cudaStream_t st) {
+  constexpr int SP = NT * 8;
+  const size_t smem = ((size_t)2 * SP * (DH + 8) + (size_t)DH * (SP + 8)) * sizeof(__half);
+  attn_mma_kernel<DH, NT><<<B * heads, NT * 16, smem, st>>>(qkv, ctx, S, C, heads);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int DH>
+static int attn_dispatch(const float* qkv, __half* ctx, int B, int S, int C, int heads, cudaStream_t st) {
+  const int sp16 = (S + 15) / 16;       // query tiles = warps
+  switch (sp16) {
+    case 1: return attn_launch<DH, 2>(qkv, ctx, B, S, C, heads, st);
+    case 2: return attn_launch<DH, 4>(qkv, ctx, B, S, C, heads, st);
+    case 3: return attn_launch<DH, 6>(qkv, ctx, B, S, C, heads, st);
+    case 4: return attn_launch<DH, 8>(qkv, ctx, B, S, C, heads, st);
+    case 5: return attn_launch<DH, 10>(qkv, ctx, B, S, C, heads, st);
+    case 6: return attn_launch<DH, 12>(qkv, ctx, B, S, C, heads, st);
+    case 7: return attn_launch<DH, 14>(qkv, ctx, B, S, C, heads, st);
+    case 8: return attn_launch<DH, 16>(qkv, ctx, B, S, C, heads, st);
+    default:
+      CM_CHECK(false, "attention: sequence length %d > 128 tokens is not supported", S);
+  }
+  return 0;
 }
 
 int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int heads,
                       cudaStream_t st) {
-  CM_CHECK(C % heads == 0 && (C / heads) % 4 == 0, "embed dim %d / heads %d unsupported", C, heads);
+  CM_CHECK(C % heads == 0, "embed dim %d / heads %d unsupported", C, heads);
   const int dh = C / heads;
-  const size_t smem = ((size_t)S * (dh + 1) + (size_t)S * dh + ATTN_WARPS * dh + ATTN_WARPS * (size_t)S) *
-                      sizeof(float);
-  CM_CHECK(smem <= 200 * 1024, "attention tile too large for shared memory (S=%d dh=%d)", S, dh);
-  attn_core_kernel<<<B * heads, ATTN_WARPS * 32, smem, st>>>(qkv, ctx, S, C, heads);
-  CM_CUDA(cudaGetLastError());
+  CM_CHECK(dh % 2 == 0 && dh <= 64, "attention: head dim %d unsupported (even, <= 64)", dh);
+  if (dh <= 16) return attn_dispatch<16>(qkv, ctx, B, S, C, heads, st);
+  if (dh <= 32) return attn_dispatch<32>(qkv, ctx, B, S, C, heads, st);
+  return attn_dispatch<64>(qkv, ctx, B, S, C, heads, st);
+}
+
+// pre-set the shared-memory attribute of every attention instantiation outside stream capture
+template <int DH, int NT>
+static int attn_attr() {
+  CM_CUDA(cudaFuncSetAttribute(attn_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  return 0;
+}
+static int attn_init() {
+#define CM_AT(NT) if (int rc = attn_attr<16, NT>()) return rc; if (int rc = attn_attr<32, NT>()) return rc; if (int rc = attn_attr<64, NT>()) return rc;
+  CM_AT(2) CM_AT(4) CM_AT(6) CM_AT(8) CM_AT(10) CM_AT(12) CM_AT(14) CM_AT(16)
+#undef CM_AT
   return 0;
 }
 
@@ -723,7 +1163,7 @@ int kernels_init() {
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CM_CUDA(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (int rc = attn_init()) return rc;
   if (int rc = conv_init()) return rc;
   done = true;
   return 0;

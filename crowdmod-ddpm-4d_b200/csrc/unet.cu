@@ -430,7 +430,7 @@ int reserve(cm_unet* u, int batch) {
   const size_t temb_off = off;
   off = align_up(off + (size_t)batch * u->temb_ld * 4, 1024);
   const size_t gnp_off = off;
-  off = align_up(off + (size_t)batch * 64 * 16 * 4, 1024);
+  off = align_up(off + (size_t)batch * 32 * 8 * 3 * 4, 1024);   // [batch][GN2_MAX_SLICES][8][3]
   CM_CUDA(cudaMalloc(&u->arena, off));
   CM_CUDA(cudaMemset(u->arena, 0, off));
   u->arena_bytes = off;

@@ -101,6 +101,16 @@ def ddim_coefficients(sampler: ForwardSampler, taus, sigma_t, guidance="None", l
     return torch.tensor(order, dtype=torch.int32), coef
 
 
+def shard_samples(nsamples, rank, world):
+    """Contiguous slice [lo, hi) of the sample batch owned by `rank` (sampling
+    shards the independent sample batch across GPUs with no communication).  `lo` is also the
+    shard's `sample_offset`, so the in-kernel Philox noise depends on the GLOBAL sample index and
+    the union of the shards equals the single-GPU result."""
+    base, rem = divmod(int(nsamples), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class _RunningMean:
     def __init__(self):
         self.total, self.count = 0.0, 0

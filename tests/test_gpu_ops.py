@@ -164,7 +164,7 @@ def test_gn_silu(nat, B, pixels, c0, c1, silu):
     assert torch.equal(raw, x.half())
 
 
-@pytest.mark.parametrize("B,S,C_", [(3, 54, 128), (2, 108, 256), (2, 12, 128), (1, 84, 128)])
+@pytest.mark.parametrize("B,S,C_", [(3, 54, 128), (2, 108, 256), (2, 12, 128), (1, 84, 128), (3, 64, 32), (2, 8, 64), (1, 128, 96)])
 def test_attn_core(nat, B, S, C_):
     g = torch.Generator(device="cuda").manual_seed(2)
     heads = 4
@@ -176,7 +176,8 @@ def test_attn_core(nat, B, S, C_):
     q, k, v = [t.reshape(B, S, heads, dh).transpose(1, 2) for t in qkv.split(C_, dim=2)]
     p = torch.softmax((q @ k.transpose(-1, -2)) / dh ** 0.5, dim=-1)
     ref = (p @ v).transpose(1, 2).reshape(B, S, C_)
-    assert rel_l2(ctx.float(), ref) <= 4e-4
+    # P, V and the output are fp16 MMA operands (2^-11 relative each); Q K^T is fp32-accurate (hi+lo)
+    assert rel_l2(ctx.float(), ref) <= 7e-4
 
 
 @pytest.mark.parametrize("B,H,W,P,Fu,cin,cout", [(2, 12, 36, 5, 3, 3, 32), (1, 8, 12, 5, 3, 3, 64), (2, 4, 4, 2, 2, 4, 32)])
