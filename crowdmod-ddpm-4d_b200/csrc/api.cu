@@ -8,6 +8,7 @@
 
 #include "../../include/crowdmod_b200.h"
 #include "backward.cuh"
+#include "conv_plane.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 #include "wgrad_umma.cuh"
@@ -60,6 +61,47 @@ int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int ci
   if (mode == 2) rc = pack_upsample_weights(w, wp, cout, cin, terms, 0, st);
   else rc = pack_conv_weights(w, wx, wp, cout, cin, cin_extra, mode == 3 ? 1 : 27, terms, 0, st);
   ConvLaunch L;
+  if (!rc && impl == 2) {
+    // plane-tile kernel (conv_plane.cuh); mode 0 only.  Fails if the geometry is not covered.
+    PlaneLaunch PLn;
+    rc = (mode == 0) ? plane_prepare(&PLn, static_cast<const __half*>(act16), B, D, H, W, cin,
+                                     static_cast<const __half*>(extra16), cin_extra, wp, cout, terms)
+                     : 2;
+    if (!rc && !PLn.ok) {
+      set_error("plane-tile conv does not cover this geometry");
+      rc = 2;
+    }
+    if (!rc) {
+      PLn.p.bias = bias;
+      PLn.p.resid = resid;
+      PLn.p.out32 = out32;
+      PLn.p.out16 = static_cast<__half*>(out16);
+      rc = plane_enqueue(PLn, st);
+      if (const char* e = getenv("CM_DBG_REPS")) {
+        const int reps = atoi(e);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaStreamSynchronize(st);
+        cudaEventRecord(a, st);
+        for (int i = 0; i < reps && !rc; ++i) rc = plane_enqueue(PLn, st);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "CM_DBG plane B=%d D=%d H=%d W=%d cin=%d+%d cout=%d bn=%d bk=%d R=%d HB=%d tiles=%d units=%d stages=%d grid=%d: %.2f us/launch (%.1f TF/s)\n",
+                B, D, H, W, cin, cin_extra, cout, PLn.bn, PLn.bk, PLn.p.R, PLn.p.HB, PLn.p.ntiles, PLn.p.n_units,
+                PLn.p.stages, PLn.grid.x, ms * 1e3f / reps, PLn.flops / (ms * 1e-3 / reps) * 1e-12);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+      }
+    }
+    cudaError_t se2 = cudaStreamSynchronize(st);
+    cudaFree(wp);
+    if (rc) return rc;
+    CM_CUDA(se2);
+    return 0;
+  }
   if (!rc) rc = conv_prepare(&L, mode, static_cast<const __half*>(act16), B, D, H, W, cin,
                              static_cast<const __half*>(extra16), cin_extra, wp, cout, terms);
   if (!rc) {

@@ -2,6 +2,7 @@
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 #include "wgrad_umma.cuh"
+#include "conv_plane.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -99,6 +100,7 @@ int conv_init() {
   static bool done = false;
   if (done) return 0;
   if (int rc = load_driver_syms()) return rc;
+  if (int rc = plane_init()) return rc;
   if (int rc = set_attr_t<128, 64>()) return rc;
   if (int rc = set_attr_t<64, 64>()) return rc;
   if (int rc = set_attr_t<32, 64>()) return rc;
@@ -231,6 +233,151 @@ int conv_enqueue(const ConvLaunch& L, cudaStream_t st) {
   }
 }
 
+
+
+// ================================ plane-tile conv (conv_plane.cuh) ================================
+namespace {
+
+int make_plane_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int bk, int R,
+                   int HB) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)(W + 2), (cuuint32_t)HB, (cuuint32_t)R, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (plane) failed: %d (B=%d D=%d H=%d W=%d C=%d R=%d)", (int)r,
+           B, D, H, W, C, R);
+  return 0;
+}
+
+template <int BN, int BK>
+int plane_launch_t(const PlaneLaunch& L, cudaStream_t st) {
+  if (L.p.terms == 2) conv_plane_kernel<BN, BK, 2><<<L.grid, PL_THREADS, L.smem, st>>>(L.p);
+  else conv_plane_kernel<BN, BK, 1><<<L.grid, PL_THREADS, L.smem, st>>>(L.p);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int BN, int BK>
+int plane_attr_t() {
+  CM_CUDA(cudaFuncSetAttribute(conv_plane_kernel<BN, BK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(conv_plane_kernel<BN, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return 0;
+}
+
+}  // namespace
+
+int plane_init() {
+  static bool done = false;
+  if (done) return 0;
+  if (int rc = load_driver_syms()) return rc;
+  if (int rc = plane_attr_t<32, 32>()) return rc;
+  if (int rc = plane_attr_t<32, 64>()) return rc;
+  if (int rc = plane_attr_t<64, 32>()) return rc;
+  if (int rc = plane_attr_t<64, 64>()) return rc;
+  if (int rc = plane_attr_t<128, 32>()) return rc;
+  if (int rc = plane_attr_t<128, 64>()) return rc;
+  done = true;
+  return 0;
+}
+
+int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W, int cin,
+                  const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms) {
+  if (int rc = load_driver_syms()) return rc;
+  memset(L, 0, sizeof(*L));
+  L->ok = false;
+  if (cin % 32 || cin_extra % 32 || cout % 32) return 0;
+  const int Wp = W + 2;
+  if (Wp > 256 || H > 256) return 0;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    CM_CUDA(cudaGetDevice(&dev));
+    CM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int bk = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
+  int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
+  while (bn > 32 && bn * terms > 256) bn >>= 1;         // stacked hi|lo MMA: N <= 256
+  const int nst = bn * terms, rowb = bk * 2;
+  const int max_tiles = 256 / nst;                      // two accumulator buffers in 512 TMEM columns
+  if (max_tiles < 1) return 0;
+  const long smem_cap = 220 * 1024;
+  const long tail = 256 + 512 + 4L * 32 * (bn + 4) * 4 + 1024;
+  // work unit: R planes x HB rows.  Score = useful MMA rows x SM fill of the last wave; ties go to
+  // the larger unit (more reuse of every weight tile).
+  int bestR = 0, bestHB = 0;
+  double best = 0.0;
+  auto consider = [&](int R, int HB) {
+    const int P = R * HB * Wp;
+    const int ntiles = (P + 127) / 128;
+    if (ntiles > max_tiles || R > 256 || HB > 256) return;
+    const long a_stage = ((long)(ntiles * 128 + 8) * rowb + 1023) / 1024 * 1024;
+    const long stage = a_stage + 3L * nst * rowb;
+    if (2 * stage + tail > smem_cap) return;
+    const long units = (long)B * (D / R) * (H / HB) * (cout / bn);
+    const long waves = (units + n_sm - 1) / n_sm;
+    const double eff = (double)R * HB * W / (ntiles * 128.0);
+    if (eff < 0.6) return;                               // mostly padding: leave it to conv_umma
+    const double score = eff * ((double)units / (waves * n_sm));
+    if (score > best * 1.0001 || (score > best * 0.9999 && R * HB > bestR * bestHB)) {
+      best = score;
+      bestR = R;
+      bestHB = HB;
+    }
+  };
+  for (int hb = 1; hb <= H; ++hb)
+    if (H % hb == 0) consider(1, hb);
+  for (int r = 2; r <= D; ++r)
+    if (D % r == 0) consider(r, H);
+  if (bestR == 0) return 0;
+  const int R = bestR, HB = bestHB;
+  const int P = R * HB * Wp;
+  const int ntiles = (P + 127) / 128;
+  PlaneParams& p = L->p;
+  if (int rc = make_plane_map(&p.amap, act, B, D, H, W, cin, bk, R, HB)) return rc;
+  if (cin_extra) {
+    CM_CHECK(extra != nullptr, "extra source pointer missing");
+    if (int rc = make_plane_map(&p.xmap, extra, B, D, H, W, cin_extra, bk, R, HB)) return rc;
+  }
+  const size_t ktot = conv_packed_k(0, cin, cin_extra);
+  if (int rc = make_weight_map(&p.bmap, wpacked, (size_t)terms * cout, ktot, bk, bn)) return rc;
+  p.H = H; p.W = W; p.D = D; p.Wp = Wp; p.R = R; p.HB = HB; p.P = P; p.ntiles = ntiles;
+  p.units_per_sample = (D / R) * (H / HB);
+  p.n_ntiles = cout / bn;
+  p.n_units = B * p.units_per_sample * p.n_ntiles;
+  p.a_stage_bytes = (int)(((long)(ntiles * 128 + 8) * rowb + 1023) / 1024 * 1024);
+  p.cin_main = cin; p.cin_extra = cin_extra; p.cout = cout; p.terms = terms;
+  p.out_ld = cout;
+  p.err_flag = device_error_flag();
+  if (const char* e = getenv("CM_PLANE_DBG")) p.dbg = atoi(e);
+  const long stage = p.a_stage_bytes + 3L * nst * rowb;
+  int stages = (int)((smem_cap - tail) / stage);
+  if (stages > PL_MAX_STAGES) stages = PL_MAX_STAGES;
+  if (const char* e = getenv("CM_PLANE_STAGES")) stages = atoi(e);
+  if (stages < 2) return 0;
+  p.stages = stages;
+  L->bn = bn;
+  L->bk = bk;
+  L->smem = (size_t)stages * stage + tail;
+  L->grid = dim3(p.n_units < n_sm ? p.n_units : n_sm, 1, 1);
+  L->flops = 2.0 * B * D * H * W * cout * (27.0 * cin + cin_extra);
+  L->ok = true;
+  return 0;
+}
+
+int plane_enqueue(const PlaneLaunch& L, cudaStream_t st) {
+  if (L.bk == 64) {
+    if (L.bn == 128) return plane_launch_t<128, 64>(L, st);
+    if (L.bn == 64) return plane_launch_t<64, 64>(L, st);
+    return plane_launch_t<32, 64>(L, st);
+  }
+  if (L.bn == 128) return plane_launch_t<128, 32>(L, st);
+  if (L.bn == 64) return plane_launch_t<64, 32>(L, st);
+  return plane_launch_t<32, 32>(L, st);
+}
 
 // ================================ weight gradient (wgrad_umma.cuh) ================================
 namespace {

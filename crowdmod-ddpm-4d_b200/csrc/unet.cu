@@ -14,6 +14,7 @@
 
 #include "../../include/crowdmod_b200.h"
 #include "backward.cuh"
+#include "conv_plane.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 #include "wgrad_umma.cuh"
@@ -51,6 +52,7 @@ struct Op {
       resid = -1, out = -1, cin = 0, cin_extra = 0, cout = 0, in_level = 0;
   size_t wpack_off = 0;   // element offset into the packed-weight buffer
   ConvLaunch launch;
+  PlaneLaunch plaunch;      // plane-tile kernel (conv_plane.cuh) when it covers the geometry
   // ATTN
   int qkv = -1, ctx = -1, heads = 4;
   // training (backward) bookkeeping
@@ -456,6 +458,21 @@ int prepare_convs(cm_unet* u, int batch) {
     if (int rc = conv_prepare(&op.launch, op.mode, tin.p16, batch, li.D, li.H, li.W, op.cin, extra,
                               op.cin_extra, u->wpack + op.wpack_off, op.cout, u->cfg.weight_terms))
       return rc;
+    op.plaunch.ok = false;
+    static const bool no_plane = getenv("CM_NO_PLANE") != nullptr;
+    if (op.mode == 0 && !no_plane) {
+      if (int rc = plane_prepare(&op.plaunch, tin.p16, batch, li.D, li.H, li.W, op.cin, extra, op.cin_extra,
+                                 u->wpack + op.wpack_off, op.cout, u->cfg.weight_terms))
+        return rc;
+      if (op.plaunch.ok) {
+        PlaneParams& q = op.plaunch.p;
+        q.bias = op.bias >= 0 ? u->params[op.bias].ptr : nullptr;
+        q.bias2 = op.bias2 >= 0 ? u->params[op.bias2].ptr : nullptr;
+        q.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
+        q.out32 = u->tens[op.out].p32;
+        q.out16 = u->tens[op.out].p16;
+      }
+    }
     ConvParams& p = op.launch.p;
     p.bias = op.bias >= 0 ? u->params[op.bias].ptr : nullptr;
     p.bias2 = op.bias2 >= 0 ? u->params[op.bias2].ptr : nullptr;
@@ -528,6 +545,17 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         if (int e = gn_silu_enqueue(g, u->gn_partial, st)) return e;
       } break;
       case OP_CONV: {
+        if (op.plaunch.ok) {
+          PlaneLaunch L = op.plaunch;
+          if (op.temb_off >= 0) {
+            L.p.temb = rc.temb + op.temb_off;
+            L.p.t_dev = rc.t_dev;
+            L.p.temb_ld = u->temb_ld;
+            L.p.temb_bstride = rc.temb_bstride;
+          }
+          if (int e = plane_enqueue(L, st)) return e;
+          break;
+        }
         ConvLaunch L = op.launch;
         if (op.temb_off >= 0) {
           L.p.temb = rc.temb + op.temb_off;

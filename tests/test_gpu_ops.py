@@ -305,3 +305,31 @@ def test_conv_wgrad_vs_torch_autograd(nat, case, impl):
     assert e <= 3e-5, f"wgrad rel-L2 {e:.3e}; " + describe_mismatch(dw.reshape(cout, -1), rw.reshape(cout, -1))
     if cx:
         assert rel_l2(dwx, rwx) <= 3e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# plane-tile conv (conv_plane.cuh): W-shifted descriptor views of one haloed TMA box, stacked hi|lo
+# MMA, persistent CTAs with double-buffered TMEM.  impl=2 forces it (error if not covered).
+# ---------------------------------------------------------------------------------------------
+PLANE_CASES = [
+    (0, 2, 8, 12, 36, 32, 32, 0, True),     # encoder_blocks.0.conv_2 (HB=6 row blocks)
+    (0, 2, 8, 12, 36, 64, 32, 0, False),    # decoder_blocks.7.conv_1 (BK=64)
+    (0, 1, 8, 12, 36, 96, 32, 0, False),    # decoder_blocks.6.conv_1 (3 channel chunks)
+    (0, 2, 8, 12, 36, 32, 32, 96, False),   # decoder_blocks.6.conv_2 + match_input slab
+    (0, 3, 4, 6, 18, 64, 64, 32, False),    # encoder_blocks.2.conv_2 + slab, odd batch
+    (0, 1, 4, 6, 18, 192, 64, 0, False),    # decoder_blocks.3.conv_1 (R=2 planes per unit)
+    (0, 1, 8, 28, 24, 32, 32, 0, True),     # HERMES-CR-120 level 0
+    (0, 5, 8, 8, 12, 32, 32, 0, True),      # ETH-UCY level 0
+    (0, 150, 8, 12, 36, 32, 32, 0, True),   # more units than SMs: several units per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", PLANE_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d_r%d" % c)
+@pytest.mark.parametrize("terms", [2, 1])
+def test_conv_plane_vs_torch(nat, case, terms):
+    mode, B, D, H, W, cin, cout, cx, resid = case
+    out32, out16, ref, flag = run_conv(nat, mode, B, D, H, W, cin, cout, cx, terms, resid, impl=2)
+    assert flag == 0, f"device protocol error flag {flag}"
+    e = rel_l2(out32, ref)
+    assert e <= (2e-5 if terms == 2 else 1e-3), f"rel-L2 {e:.3e}; " + describe_mismatch(out32, ref)
+    assert rel_l2(out16.float(), ref) <= 1e-3
