@@ -226,6 +226,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// same, without the wait: issue several loads, then tmem_ld_wait() once
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major shared-memory matrix descriptor for a TMA-written tile whose rows are `row_bytes`
 // (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B) wide.  SBO = 8 rows; LBO unused (=1) for swizzled
 // K-major; version = 1 (Blackwell).  Layout-type encoding: 2 = SW128, 4 = SW64.

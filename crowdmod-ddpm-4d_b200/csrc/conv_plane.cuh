@@ -7,15 +7,19 @@
 // so narrow layers are shared-memory-bandwidth bound inside the tensor pipe as well.  This kernel
 //   * gives a work unit R whole planes (or a block of HB rows of one plane) of one sample: with W
 //     padded to W+2 the unit is a flat array of P = R*HB*(W+2) "positions" and ONE tiled TMA box
-//     {BK ch, W+2, HB, R} (zero-filled halo) per (td, th, channel chunk) serves all three tw taps:
-//     a tap shift is a +1/+2 row offset of the UMMA shared-memory descriptor (positions on the two
-//     pad columns compute garbage that the epilogue drops) -> 9 A loads per channel chunk, not 27.
-//     (The UMMA swizzle is a function of the absolute shared-memory address: an offset start
-//     address needs no descriptor base_offset -- verified on hardware, tools/plane_probe.py.)
+//     {BK ch, W+2, HB, R} (zero-filled halo) per (td, th, channel chunk) serves all three tw taps
+//     -> 9 A loads per channel chunk, not 27;
+//   * stacks the three tw taps along N: Y[row, (tw, co)] = X[row, :] . W[(tw, co), :] is ONE
+//     128 x (3*BN) MMA per k16 step (hi and lo weight terms are two MMAs into the same
+//     accumulator).  A 128-row SS-mode tcgen05.mma costs >= ~64 cycles whatever N is (measured:
+//     it re-reads its 4 KB A operand from shared memory), so 3x wider MMAs = 3x fewer of them.
+//     The epilogue forms out[h, w] = Y0[row] + Y1[row+1] + Y2[row+2] (row = h*(W+2) + w) with a
+//     row-shifted accumulation in shared memory; rows on the two pad columns are dropped.
+//     (An earlier variant expressed the tw shift as a +1/+2 row offset of the A descriptor --
+//     it is correct, the UMMA swizzle being a function of the absolute shared-memory address, so
+//     an offset start needs no base_offset -- but it needs 3x the MMA instructions.)
 //   * keeps ceil(P/128) accumulators in TMEM, so every weight tile is loaded once per unit and
 //     reused by all of its M tiles;
-//   * stacks the hi and lo weight terms along N: one 128 x (2*BN) MMA instead of two 128 x BN
-//     ones, halving the A-operand shared-memory reads; the epilogue adds the two halves;
 //   * is persistent: one CTA per SM walks the units; TMEM is double-buffered, so the epilogue of
 //     unit i (coalesced through a shared-memory transpose) overlaps the main loop of unit i+1.
 // Same operands, same packed weights, same epilogue semantics as conv_umma_kernel (mode 0 with
@@ -25,7 +29,8 @@
 
 namespace cm {
 
-constexpr int PL_THREADS = 192;      // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int PL_THREADS = 320;      // warp0 TMA, warp1 MMA, warps2-9 epilogue (two warps per TMEM lane quarter)
+constexpr int PL_EPI = 256;          // epilogue threads
 constexpr int PL_MAX_STAGES = 6;
 
 struct PlaneParams {
@@ -85,11 +90,13 @@ template <int BN, int BK, int TERMS>
 __global__ void __launch_bounds__(PL_THREADS, 1)
 conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   constexpr int ROWB = BK * 2;
-  constexpr int NST = BN * TERMS;                    // stacked N of one MMA (hi | lo)
-  constexpr int B_TAP = NST * ROWB;                  // weight bytes per tap per stage
-  constexpr int B_STAGE = 3 * B_TAP;
+  constexpr int NST = 3 * BN;                        // N of one MMA = accumulator columns per M tile: (tw, co)
+  constexpr int B_TAP = BN * ROWB;                   // weight bytes of one (term, tw) slab
+  constexpr int B_TERM = 3 * B_TAP;                  // one term: tw0 | tw1 | tw2 slabs, contiguous
+  constexpr int B_STAGE = TERMS * B_TERM;
   constexpr uint32_t IDESC = make_idesc_f16(128, NST);
-  constexpr int TLD = BN + 4;                        // transpose-buffer row (floats)
+  constexpr uint32_t IDESC_X = make_idesc_f16(128, BN);   // fused 1x1x1 source: centre (tw = 1) block only
+  constexpr int TLD = BN + 4;                        // accumulation-buffer row (floats)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -103,7 +110,8 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   uint64_t* tmem_empty = tmem_full + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* colv = reinterpret_cast<float*>(tail + 256);      // [BN]
-  float* tbuf_all = reinterpret_cast<float*>(tail + 256 + 512);   // [4 warps][32][TLD]
+  float* side = reinterpret_cast<float*>(tail + 256 + 512);       // [ntiles*4 + 1][3][BN] block-boundary rows
+  float* ybuf = side + (P.ntiles * 4 + 1) * 3 * BN;               // [ntiles*128][TLD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncm = P.cin_main / BK;
@@ -125,7 +133,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);                   // one arrival per epilogue warp
+      mbar_init(&tmem_empty[b], PL_EPI / 32);         // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -157,20 +165,20 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
             const int kcol = ((td * 3 + th) * 3) * P.cin_main + cc * BK;
             if (!(P.dbg & 2)) {
 #pragma unroll
-              for (int tw = 0; tw < 3; ++tw)
+              for (int t = 0; t < TERMS; ++t)
 #pragma unroll
-                for (int t = 0; t < TERMS; ++t)
-                  tma_load_2d(&P.bmap, &full_bar[s], sb + tw * B_TAP + t * (BN * ROWB), kcol + tw * P.cin_main,
+                for (int tw = 0; tw < 3; ++tw)
+                  tma_load_2d(&P.bmap, &full_bar[s], sb + t * B_TERM + tw * B_TAP, kcol + tw * P.cin_main,
                               U.n_tile * BN + t * P.cout);
             }
           } else {
             // fused 1x1x1 source: centre tap only (tw = 1 against a box that starts at w = -1)
             const int xc = ks - nks_main;
-            mbar_expect_tx(&full_bar[s], a_bytes + B_TAP);
+            mbar_expect_tx(&full_bar[s], a_bytes + TERMS * B_TAP);
             tma_load_tile_5d(&P.xmap, &full_bar[s], sa, xc * BK, -1, U.h0, U.d0, U.n);
 #pragma unroll
             for (int t = 0; t < TERMS; ++t)
-              tma_load_2d(&P.bmap, &full_bar[s], sb + 1 * B_TAP + t * (BN * ROWB), 27 * P.cin_main + xc * BK,
+              tma_load_2d(&P.bmap, &full_bar[s], sb + t * B_TERM + 1 * B_TAP, 27 * P.cin_main + xc * BK,
                           U.n_tile * BN + t * P.cout);
           }
         }
@@ -200,24 +208,43 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t a_lo0 = kmajor_desc_lo(a_addr);
           const uint32_t b_lo0 = kmajor_desc_lo(a_addr + P.a_stage_bytes);
-          const int tw0 = ks < nks_main ? 0 : 1, tw1 = ks < nks_main ? 3 : 2;
-          for (int rep = 0; rep < ((P.dbg & 128) ? 2 : 1); ++rep)
-          for (int tw = tw0; tw < ((P.dbg & 4) ? tw0 : tw1); ++tw) {
-            const uint32_t a_lo0 = kmajor_desc_lo(a_addr + ((P.dbg & 16) ? 0 : tw) * ROWB + ((P.dbg & 32) ? tw * 8 * ROWB : 0));      // tap shift = +tw rows
-            uint32_t first = (ks == 0 && tw == tw0) ? 0u : 1u;
+          if (!(P.dbg & 4)) {
+            if (ks < nks_main) {
+              uint32_t first = (ks == 0) ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t b_lo = b_lo0 + ((tw * B_TAP) >> 4) + 2 * k;
-              uint32_t a_lo = a_lo0 + 2 * k;
-              uint32_t d = d_base;
-#pragma unroll 4
-              for (int r = 0; r < P.ntiles; ++r) {
-                umma_f16_lohi(d, a_lo, b_lo, DESC_HI, IDESC, first);
-                a_lo += TILE_LO;
-                d += NST;
+              for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+                for (int t = 0; t < TERMS; ++t) {
+                  const uint32_t b_lo = b_lo0 + ((t * B_TERM) >> 4) + 2 * k;
+                  uint32_t a_lo = a_lo0 + 2 * k;
+                  uint32_t d = d_base;
+#pragma unroll 2
+                  for (int r = 0; r < P.ntiles; ++r) {
+                    umma_f16_lohi(d, a_lo, b_lo, DESC_HI, IDESC, first);
+                    a_lo += TILE_LO;
+                    d += NST;
+                  }
+                  first = 1u;
+                }
               }
-              first = 1u;
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+                for (int t = 0; t < TERMS; ++t) {
+                  const uint32_t b_lo = b_lo0 + ((t * B_TERM + B_TAP) >> 4) + 2 * k;
+                  uint32_t a_lo = a_lo0 + 2 * k;
+                  uint32_t d = d_base + BN;
+#pragma unroll 2
+                  for (int r = 0; r < P.ntiles; ++r) {
+                    umma_f16_lohi(d, a_lo, b_lo, DESC_HI, IDESC_X, 1u);
+                    a_lo += TILE_LO;
+                    d += NST;
+                  }
+                }
+              }
             }
           }
           umma_commit(&empty_bar[s]);
@@ -228,36 +255,66 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM lane quarter = warp % 4; the two warps of a quarter split the 16-column chunks.
     const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
     const bool temb_uniform = P.temb != nullptr && P.temb_bstride == 0;
     constexpr int LPR = BN / 4;                            // lanes per row in the store phase
-    constexpr int RPI = 32 / LPR;                          // rows per store instruction
-    constexpr int NIT = 32 / RPI;                          // store iterations per 32-row block
-    float* tbuf = tbuf_all + static_cast<size_t>(quarter) * 32 * TLD;
+    constexpr int RPP = PL_EPI / LPR;                      // rows per store pass of the epilogue threads
+    constexpr int NJ = 8;                                  // store rows per thread (host: ntiles*128 <= NJ*RPP)
     const int plane = P.HB * P.Wp;
-    const int sub_r = lane / LPR, sub_c = (lane % LPR) * 4;
+    const int sub_r = et / LPR, sub_c = (et % LPR) * 4;
     int it = 0;
     bool alive = true;
     for (int u = blockIdx.x; u < P.n_units && alive; u += gridDim.x, ++it) {
       const PlaneUnit U = plane_unit(P, u);
       const int buf = it & 1;
       const int nn0 = U.n_tile * BN;
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // previous unit's colv no longer read
+      // Everything that does not depend on the accumulators is fetched before waiting for them:
+      // per-column constants of this thread's 4 output channels, the output row of each of its
+      // NJ store rows and the residual values there.
+      float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
       {
-        const int trow = (P.temb && P.t_dev) ? *P.t_dev : 0;
-        for (int c = et; c < BN; c += 128) {
-          const int nn = nn0 + c;
-          float v = P.bias ? P.bias[nn] : 0.f;
-          if (P.bias2) v += P.bias2[nn];
-          if (temb_uniform) v += P.temb[static_cast<size_t>(trow) * P.temb_ld + nn];
-          if (P.temb && !temb_uniform) v += P.temb[static_cast<size_t>(U.n) * P.temb_bstride + nn];
-          colv[c] = v;
+        const int nn = nn0 + sub_c;
+        if (P.bias) cv = *reinterpret_cast<const float4*>(P.bias + nn);
+        if (P.bias2) {
+          const float4 t4 = *reinterpret_cast<const float4*>(P.bias2 + nn);
+          cv.x += t4.x; cv.y += t4.y; cv.z += t4.z; cv.w += t4.w;
+        }
+        if (P.temb) {
+          const size_t trow = temb_uniform ? static_cast<size_t>(P.t_dev ? *P.t_dev : 0) * P.temb_ld
+                                           : static_cast<size_t>(U.n) * P.temb_bstride;
+          const float4 t4 = *reinterpret_cast<const float4*>(P.temb + trow + nn);
+          cv.x += t4.x; cv.y += t4.y; cv.z += t4.z; cv.w += t4.w;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float4 cv = *reinterpret_cast<const float4*>(colv + sub_c);
+      int mi[NJ];
+      float4 rv[NJ];
+      {
+        int q = sub_r;
+        int dl = q / plane;
+        int rem = q - dl * plane;
+        int hl = rem / P.Wp;
+        int w = rem - hl * P.Wp;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          mi[j] = -1;
+          rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < P.P && w < P.W && !(P.dbg & 8)) {
+            mi[j] = ((U.n * P.D + U.d0 + dl) * P.H + U.h0 + hl) * P.W + w;
+            if (P.resid)
+              rv[j] = *reinterpret_cast<const float4*>(P.resid + static_cast<size_t>(mi[j]) * P.cout + nn0 + sub_c);
+          }
+          q += RPP;
+          w += RPP;
+          while (w >= P.Wp) {
+            w -= P.Wp;
+            if (++hl == P.HB) { hl = 0; ++dl; }
+          }
+        }
+      }
       if (!mbar_wait(&tmem_full[buf], (it >> 1) & 1, P.err_flag, 403)) { alive = false; break; }
       tc_fence_after();
       if (P.dbg & 64) {            // bring-up: no epilogue work at all
@@ -266,66 +323,77 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         continue;
       }
+      // out[row] = Y0[row] + Y1[row + 1] + Y2[row + 2].  Rows are TMEM lanes: the +1 / +2 shifts are
+      // warp shuffles; the two rows a 32-row block needs from the NEXT block travel through `side`
+      // (Y1 of its lane 0, Y2 of its lanes 0 and 1) and are added at read-out.  Fixed order -> the
+      // result is deterministic.
 #pragma unroll 1
       for (int r = 0; r < P.ntiles; ++r) {
-        // global coordinates of this thread's rows of the store phase + residual prefetch
-        const int q0 = r * 128 + quarter * 32;
-        size_t mrow[NIT];
-        float4 rv[NIT];
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {
-          const int q = q0 + sub_r + j * RPI;
-          mrow[j] = ~static_cast<size_t>(0);
-          rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < P.P) {
-            const int dl = q / plane;
-            const int rem = q - dl * plane;
-            const int hl = rem / P.Wp;
-            const int w = rem - hl * P.Wp;
-            if (w < P.W && !(P.dbg & 8)) {
-              mrow[j] = ((static_cast<size_t>(U.n) * P.D + U.d0 + dl) * P.H + U.h0 + hl) * P.W + w;
-              if (P.resid) rv[j] = *reinterpret_cast<const float4*>(P.resid + mrow[j] * P.cout + nn0 + sub_c);
-            }
-          }
-        }
+        const int blk = r * 4 + quarter;
+        const int row = blk * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * buf_cols + r * NST;
+        float* sd = side + static_cast<size_t>(blk) * 3 * BN;
 #pragma unroll
-        for (int c = 0; c < BN / 16; ++c) {
-          float v[16];
-          tmem_ld16(t_lane + c * 16, v);
-          if (TERMS == 2) {
-            float v2[16];
-            tmem_ld16(t_lane + BN + c * 16, v2);
+        for (int c0 = 0; c0 < BN / 16; c0 += 2) {
+          const int c = c0 + group;
+          float y0[16], y1[16], y2[16];
+          tmem_ld16_async(t_lane + c * 16, y0);
+          tmem_ld16_async(t_lane + BN + c * 16, y1);
+          tmem_ld16_async(t_lane + 2 * BN + c * 16, y2);
+          tmem_ld_wait();
+          if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += v2[i];
+            for (int i = 0; i < 16; ++i) { sd[c * 16 + i] = y1[i]; sd[BN + c * 16 + i] = y2[i]; }
+          } else if (lane == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sd[2 * BN + c * 16 + i] = y2[i];
           }
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(tbuf + lane * TLD + c * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        if (r == P.ntiles - 1) {
-          // every accumulator of this buffer has been read by this warp: hand it back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {
-          if (mrow[j] == ~static_cast<size_t>(0)) continue;
-          float4 v = *reinterpret_cast<const float4*>(tbuf + (sub_r + j * RPI) * TLD + sub_c);
-          v.x += cv.x + rv[j].x; v.y += cv.y + rv[j].y; v.z += cv.z + rv[j].z; v.w += cv.w + rv[j].w;
-          if (P.out32) *reinterpret_cast<float4*>(P.out32 + mrow[j] * P.out_ld + nn0 + sub_c) = v;
-          if (P.out16) {
-            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-            uint2 uu;
-            uu.x = *reinterpret_cast<uint32_t*>(&h0);
-            uu.y = *reinterpret_cast<uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(P.out16 + mrow[j] * P.out_ld + nn0 + sub_c) = uu;
+          for (int i = 0; i < 16; ++i) {
+            const float s1 = __shfl_down_sync(0xffffffffu, y1[i], 1);
+            const float s2 = __shfl_down_sync(0xffffffffu, y2[i], 2);
+            y0[i] += (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
           }
+          float4* dst = reinterpret_cast<float4*>(ybuf + static_cast<size_t>(row) * TLD + c * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(y0[4 * i], y0[4 * i + 1], y0[4 * i + 2], y0[4 * i + 3]);
         }
-        __syncwarp();
       }
+      // every accumulator of this buffer has been read by this warp: hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // coalesced read-out: RPP rows per pass, LPR lanes per row
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (mi[j] < 0) continue;
+        const int q = sub_r + j * RPP;
+        float4 v = *reinterpret_cast<const float4*>(ybuf + static_cast<size_t>(q) * TLD + sub_c);
+        const int ln = q & 31;
+        if (ln >= 30) {
+          const float* sn = side + static_cast<size_t>((q >> 5) + 1) * 3 * BN + sub_c;
+          if (ln == 31) {
+            const float4 a = *reinterpret_cast<const float4*>(sn);            // Y1 of the next block's lane 0
+            const float4 b2 = *reinterpret_cast<const float4*>(sn + 2 * BN);  // Y2 of its lane 1
+            v.x += a.x + b2.x; v.y += a.y + b2.y; v.z += a.z + b2.z; v.w += a.w + b2.w;
+          } else {
+            const float4 b1 = *reinterpret_cast<const float4*>(sn + BN);      // Y2 of its lane 0
+            v.x += b1.x; v.y += b1.y; v.z += b1.z; v.w += b1.w;
+          }
+        }
+        v.x += cv.x + rv[j].x; v.y += cv.y + rv[j].y; v.z += cv.z + rv[j].z; v.w += cv.w + rv[j].w;
+        const size_t m = static_cast<size_t>(mi[j]);
+        if (P.out32) *reinterpret_cast<float4*>(P.out32 + m * P.out_ld + nn0 + sub_c) = v;
+        if (P.out16) {
+          __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+          uint2 uu;
+          uu.x = *reinterpret_cast<uint32_t*>(&h0);
+          uu.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(P.out16 + m * P.out_ld + nn0 + sub_c) = uu;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // ybuf / side are rewritten by the next unit
     }
   }
   tc_fence_before();

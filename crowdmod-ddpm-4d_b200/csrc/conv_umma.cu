@@ -300,12 +300,13 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
   }
   const int bk = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
   int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
-  while (bn > 32 && bn * terms > 256) bn >>= 1;         // stacked hi|lo MMA: N <= 256
-  const int nst = bn * terms, rowb = bk * 2;
+  while (bn > 32 && 3 * bn > 256) bn >>= 1;             // tw-stacked MMA: N = 3*BN <= 256
+  const int nst = 3 * bn, rowb = bk * 2;
   const int max_tiles = 256 / nst;                      // two accumulator buffers in 512 TMEM columns
   if (max_tiles < 1) return 0;
   const long smem_cap = 220 * 1024;
-  const long tail = 256 + 512 + 4L * 32 * (bn + 4) * 4 + 1024;
+  const long tail_fixed = 256 + 512 + 1024;
+  auto ybuf_bytes = [&](int ntiles) { return (long)(ntiles * 128 + 2) * (bn + 4) * 4 + (long)(ntiles * 4 + 1) * 3 * bn * 4; };
   // work unit: R planes x HB rows.  Score = useful MMA rows x SM fill of the last wave; ties go to
   // the larger unit (more reuse of every weight tile).
   int bestR = 0, bestHB = 0;
@@ -314,9 +315,10 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
     const int P = R * HB * Wp;
     const int ntiles = (P + 127) / 128;
     if (ntiles > max_tiles || R > 256 || HB > 256) return;
+    if (ntiles * 128 > 8 * (PL_EPI / (bn / 4))) return;    // NJ = 8 store rows per epilogue thread
     const long a_stage = ((long)(ntiles * 128 + 8) * rowb + 1023) / 1024 * 1024;
-    const long stage = a_stage + 3L * nst * rowb;
-    if (2 * stage + tail > smem_cap) return;
+    const long stage = a_stage + (long)terms * nst * rowb;
+    if (2 * stage + tail_fixed + ybuf_bytes(ntiles) > smem_cap) return;
     const long units = (long)B * (D / R) * (H / HB) * (cout / bn);
     const long waves = (units + n_sm - 1) / n_sm;
     const double eff = (double)R * HB * W / (ntiles * 128.0);
@@ -353,7 +355,8 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
   p.out_ld = cout;
   p.err_flag = device_error_flag();
   if (const char* e = getenv("CM_PLANE_DBG")) p.dbg = atoi(e);
-  const long stage = p.a_stage_bytes + 3L * nst * rowb;
+  const long stage = p.a_stage_bytes + (long)terms * nst * rowb;
+  const long tail = tail_fixed + ybuf_bytes(ntiles);
   int stages = (int)((smem_cap - tail) / stage);
   if (stages > PL_MAX_STAGES) stages = PL_MAX_STAGES;
   if (const char* e = getenv("CM_PLANE_STAGES")) stages = atoi(e);

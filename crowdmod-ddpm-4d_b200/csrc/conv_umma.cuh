@@ -66,7 +66,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   constexpr int ROWB = BK * 2;                  // bytes per smem row (swizzle span)
   constexpr int A_BYTES = CONV_BM * ROWB;
   constexpr int B_BYTES = BN * ROWB;
-  constexpr uint32_t IDESC = make_idesc_f16(CONV_BM, BN);
+  // hi and lo weight terms are stacked along N (their smem tiles are adjacent): ONE 128 x (TERMS*BN)
+  // MMA per k16 step.  A 128-row SS-mode tcgen05.mma costs >= ~64 cycles whatever N is (it re-reads
+  // its 4 KB A operand from shared memory), so halving the instruction count halves the MMA time of
+  // the narrow layers; the epilogue adds the two halves.
+  constexpr int NST = BN * TERMS;
+  constexpr uint32_t IDESC = make_idesc_f16(CONV_BM, NST);
+  constexpr uint32_t TMEM_COLS = NST < 32 ? 32 : NST;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -104,7 +110,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     mbar_init(tmem_full, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, BN);
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -178,12 +184,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
           if (!(P.dbg & 4)) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-#pragma unroll
-              for (int t = 0; t < terms; ++t) {
-                umma_f16_lohi(tmem_base, a_lo + 2 * k, a_lo + ((A_BYTES + t * B_BYTES) >> 4) + 2 * k,
-                              DESC_HI, IDESC, acc);
-                acc = 1;
-              }
+              umma_f16_lohi(tmem_base, a_lo + 2 * k, a_lo + (A_BYTES >> 4) + 2 * k, DESC_HI, IDESC, acc);
+              acc = 1;
             }
           }
           if (P.dbg & 64) mbar_arrive(&empty_bar[s]);
@@ -269,6 +271,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       }
       float v[16];
       tmem_ld16(t_lane + c * 16, v);
+      if (TERMS == 2) {
+        float v2[16];
+        tmem_ld16(t_lane + BN + c * 16, v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+      }
       if (!valid || (P.dbg & 8)) continue;
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
@@ -317,7 +325,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   if (tr && warp == 2 && lane == 0) P.trace[2] = gtime_ns();
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, BN);
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
   if (tr && threadIdx.x == 0) P.trace[3] = gtime_ns();
 }
 

@@ -7,7 +7,7 @@ from tests.test_gpu_ops import run_conv
 os.environ["CM_DBG_REPS"] = "20"
 for stages in ("3",):
     pass
-    for dbg in (64+3, 64+3+128):
+    for dbg in (0, 7):
         os.environ["CM_PLANE_DBG"] = str(dbg)
         print(f"--- stages={stages} dbg={dbg}", file=sys.stderr, flush=True)
         run_conv(nat, 0, 64, 8, 12, 36, 32, 32, 0, 2, True, impl=2)
