@@ -79,6 +79,24 @@ int make_weight_map(CUtensorMap* map, const __half* base, size_t rows, size_t kt
 
 template <int BN, int BK>
 int launch_t(const ConvLaunch& L, cudaStream_t st) {
+  if (L.p.ksplit > 1) {
+    // the ksplit CTAs along z that share an output tile form one thread-block cluster
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = L.grid;
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = L.p.ksplit;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (L.p.terms == 2) CM_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, 2>, L.p));
+    else CM_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, 1>, L.p));
+    return 0;
+  }
   if (L.p.terms == 2) conv_umma_kernel<BN, BK, 2><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
   else conv_umma_kernel<BN, BK, 1><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
   CM_CUDA(cudaGetLastError());
@@ -154,9 +172,21 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
   // N tile: as wide as possible (A is re-read once per N tile) unless that leaves most SMs idle
   // (coarse levels have only a few dozen M tiles): then trade A re-reads for more CTAs.
   int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
+  int ksplit = 1;
   {
     const long m_tiles = ((long)B * od * oh * ow + CONV_BM - 1) / CONV_BM * p.nphase;
-    while (bn > 32 && m_tiles * (cout / bn) < 120) bn >>= 1;
+    // M-starved deep-K layers (coarsest level: a few dozen M tiles, K in the thousands): keep the
+    // widest N tile (A and the weights are fetched once per tile) and split K across a cluster.
+    const long nkb_all = (long)(k * k * k) * (cin / bk) + cin_extra / bk;
+    static const bool no_split = getenv("CM_NO_SPLITK") != nullptr;
+    if (!no_split && p.nphase == 1 && m_tiles * (cout / bn) < 100) {
+      long sk = 2 * 148 / (m_tiles * (cout / bn));   // two CTAs per SM (see the stage budget below)
+      if (sk > 8) sk = 8;
+      while (sk > 1 && nkb_all / sk < 4) --sk;
+      if (sk >= 2) ksplit = (int)sk;
+    }
+    if (ksplit == 1)
+      while (bn > 32 && m_tiles * (cout / bn) < 120) bn >>= 1;
   }
   L->bk = bk;
   L->bn = bn;
@@ -215,8 +245,25 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
   if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
   while (stages > 2 && (size_t)stages * stage_bytes + 2048 > 200 * 1024) --stages;
   p.stages = stages;
+  p.ksplit = 1;
+  if (ksplit > 1) {
+    const int nkb_all = k * k * k * (cin / bk) + cin_extra / bk;
+    p.kb_per_split = (nkb_all + ksplit - 1) / ksplit;
+    ksplit = (nkb_all + p.kb_per_split - 1) / p.kb_per_split;          // no empty CTA
+    // Two CTAs per SM (<= ~100 KB of stages each): a cluster must be co-scheduled inside one GPC, and
+    // with one 200 KB CTA per SM the 27 x S CTAs of a coarse-level conv did not fit one wave (measured:
+    // 2 waves of 9 us instead of 1).  The partial tile [128][bn + 4] fp32 is staged over the
+    // pipeline buffers, which bounds the stage count from below.
+    stages = (int)((100 * 1024) / stage_bytes);
+    if (stages < 2) stages = 2;
+    if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
+    while ((size_t)stages * stage_bytes < (size_t)CONV_BM * (bn + 4) * 4 && stages < CONV_MAX_STAGES) ++stages;
+    CM_CHECK((size_t)stages * stage_bytes >= (size_t)CONV_BM * (bn + 4) * 4, "split-K staging does not fit");
+    p.stages = stages;
+    p.ksplit = ksplit;
+  }
   L->smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*colv*/;
-  L->grid = dim3((p.M + CONV_BM - 1) / CONV_BM, cout / bn, p.nphase);
+  L->grid = dim3((p.M + CONV_BM - 1) / CONV_BM, cout / bn, p.ksplit > 1 ? p.ksplit : p.nphase);
   L->flops = 2.0 * p.M * cout * (double)(k * k * k * cin + cin_extra) * p.nphase;
   return 0;
 }

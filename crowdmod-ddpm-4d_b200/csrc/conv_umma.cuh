@@ -55,6 +55,10 @@ struct ConvParams {
   __half* out16;         // fp16 [rows][out_ld] or nullptr
   int out_ld;
   int scatter;           // 1: rows are low-res pixels, written to (2z+pz, 2p+pp, 2q+pq)
+  // split-K (M-starved deep-K layers): gridDim.z = ksplit CTAs of one thread-block cluster share
+  // an output tile, each accumulating kb_per_split k-blocks; the partial tiles are reduced in a
+  // fixed order through distributed shared memory (deterministic, no atomics).
+  int ksplit, kb_per_split;
   int* err_flag;
   unsigned long long* trace;   // bring-up: per-k-block timestamps of CTA (0,0,0) (CM_DBG_TRACE)
   int dbg;               // bring-up knobs (CM_DBG_SKIP): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
@@ -91,11 +95,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   const int lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int phase = blockIdx.z;
+  const int phase = P.ksplit > 1 ? 0 : blockIdx.z;
+  const int split = P.ksplit > 1 ? blockIdx.z : 0;
 
   const int ncm = P.cin_main / BK;
   const int nkb_main = P.kd * P.kh * P.kw * ncm;
   const int nkb = nkb_main + P.cin_extra / BK;
+  const int kb_lo = P.ksplit > 1 ? split * P.kb_per_split : 0;
+  const int kb_hi = P.ksplit > 1 ? (kb_lo + P.kb_per_split < nkb ? kb_lo + P.kb_per_split : nkb) : nkb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.amap[phase]);
@@ -134,9 +141,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       const int kbase = phase * P.kphase;
       const uint32_t tx = ((P.dbg & 1) ? 0 : A_BYTES) + ((P.dbg & 2) ? 0 : terms * B_BYTES);
       int s = 0, tw = 0, th = 0, td = 0, cc = 0;
+      if (kb_lo > 0 && kb_lo < nkb_main) {          // resume the (tap, channel chunk) counters at kb_lo
+        cc = kb_lo % ncm;
+        const int tap = kb_lo / ncm;
+        tw = tap % P.kw;
+        th = (tap / P.kw) % P.kh;
+        td = tap / (P.kw * P.kh);
+      }
       uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (!mbar_wait(&empty_bar[s], ph ^ 1, P.err_flag, 101)) break;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        if (kb - kb_lo >= S && !mbar_wait(&empty_bar[s], ph ^ 1, P.err_flag, 101)) break;   // first S slots: free
         uint8_t* sa = smem + s * stage_bytes;
         if (elect_one()) {
           if (tr && kb < 120) P.trace[8 + kb * 4 + 0] = gtime_ns();
@@ -175,7 +189,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       const uint32_t lo_stage = static_cast<uint32_t>(stage_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0, acc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         if (!mbar_wait(&full_bar[s], ph, P.err_flag, 102)) break;
         tc_fence_after();
         if (elect_one()) {
@@ -237,7 +251,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     const float* temb_row = nullptr;     // per-sample rows (training): added per element
     if (P.temb && !temb_uniform)
       temb_row = P.temb + static_cast<size_t>(b) * P.temb_bstride + n_tile * BN;
-    const float* rp = (P.resid && valid) ? P.resid + orow * P.cout + n_tile * BN : nullptr;   // orow == m unless scattering
+    const float* rp = (P.resid && valid && P.ksplit <= 1) ? P.resid + orow * P.cout + n_tile * BN : nullptr;   // orow == m unless scattering
     float4 rnext[4];
     if (rp) {
 #pragma unroll
@@ -257,6 +271,25 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     if (tr && warp == 2 && lane == 0) P.trace[1] = gtime_ns();
 
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    if (P.ksplit > 1) {
+      // split-K: raw partial accumulators -> this CTA's shared memory (the pipeline stages are idle:
+      // every TMA landed and every MMA retired); reduced across the cluster after the barrier below
+      float* ptile = reinterpret_cast<float*>(smem) + static_cast<size_t>(row) * (BN + 4);
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        float v[16];
+        tmem_ld16(t_lane + c * 16, v);
+        if (TERMS == 2) {
+          float v2[16];
+          tmem_ld16(t_lane + BN + c * 16, v2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += v2[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(ptile + c * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else
 #pragma unroll 1
     for (int c = 0; c < BN / 16; ++c) {
       float4 rcur[4];
@@ -322,6 +355,63 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     }
   }
 
+  if (P.ksplit > 1) {
+    // ---- deterministic split-K reduction through distributed shared memory ----
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2) {
+      uint32_t rank;
+      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+      const int S = P.ksplit;
+      const int r0 = (CONV_BM * static_cast<int>(rank)) / S, r1 = (CONV_BM * (static_cast<int>(rank) + 1)) / S;
+      constexpr int LPR = BN / 4;                 // lanes per row
+      constexpr int RPP = 128 / LPR;              // rows per pass of the 128 epilogue threads
+      const int et = threadIdx.x - 64;
+      const int sub_c = (et % LPR) * 4;
+      const uint32_t local = smem_u32(smem);
+      const float4 cv = *reinterpret_cast<const float4*>(colv + sub_c);
+      for (int rr = r0 + et / LPR; rr < r1; rr += RPP) {
+        const int m = m_tile * CONV_BM + rr;
+        if (m >= P.M) break;
+        float4 acc = cv;
+        const uint32_t off = local + static_cast<uint32_t>((rr * (BN + 4) + sub_c) * 4);
+        const int n = n_tile * BN + sub_c;
+        // all peer loads (and the residual) in flight together, then a fixed-order sum
+        float4 pv[8];
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.resid) r4 = *reinterpret_cast<const float4*>(P.resid + static_cast<size_t>(m) * P.cout + n);
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          pv[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sidx < S) {
+            uint32_t remote;
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(off), "r"(sidx));
+            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(pv[sidx].x), "=f"(pv[sidx].y), "=f"(pv[sidx].z), "=f"(pv[sidx].w)
+                         : "r"(remote));
+          }
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          acc.x += pv[sidx].x; acc.y += pv[sidx].y; acc.z += pv[sidx].z; acc.w += pv[sidx].w;
+        }
+        if (P.temb && P.temb_bstride != 0) {
+          const float4 t4 = *reinterpret_cast<const float4*>(P.temb + static_cast<size_t>(m / P.pps) * P.temb_bstride + n);
+          acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+        }
+        acc.x += r4.x; acc.y += r4.y; acc.z += r4.z; acc.w += r4.w;
+        if (P.out32) *reinterpret_cast<float4*>(P.out32 + static_cast<size_t>(m) * P.out_ld + n) = acc;
+        if (P.out16) {
+          __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(P.out16 + static_cast<size_t>(m) * P.out_ld + n) = u;
+        }
+      }
+    }
+    // peers may still be reading this CTA's partial tile
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (tr && warp == 2 && lane == 0) P.trace[2] = gtime_ns();
   tc_fence_before();
   __syncthreads();
