@@ -379,7 +379,7 @@ def train_cpu_baseline(n=8):
 
 
 def roofline(net, nat, past, n, dev, step_ms):
-    """Dominant kernel = the tcgen05 implicit-GEMM conv (tensor-bound).  achieved = algorithmic
+    """Dominant kernel class = the tcgen05 implicit-GEMM convs (conv_plane_kernel + conv_umma_kernel).  achieved = algorithmic
     FLOPs of all its launches in one denoiser step / their summed device time, timed live with
     CUDA events around every launch (cm_unet_profile_forward)."""
     pk = peaks()
@@ -415,7 +415,7 @@ def roofline(net, nat, past, n, dev, step_ms):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     total_ms = sum(best)
-    return {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv3d)",
+    return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv3d: conv_plane_kernel (levels 0/1) + conv_umma_kernel",
             "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
             "peak_source": pk["source"] + ", sustained bf16/fp16 dense",

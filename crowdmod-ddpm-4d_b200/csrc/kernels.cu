@@ -581,7 +581,8 @@ static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 int gn_chunks(int pixels, int C) { (void)pixels; (void)C; return GN_CLUSTER; }
 
-int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st) {
+int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* launches) {
+  if (launches) *launches = 1;
   const int C = p.c0 + p.c1;
   CM_CHECK(C % 32 == 0 && p.c0 % 4 == 0, "GroupNorm channels must be a multiple of 32 (C=%d)", C);
   static const bool use_cluster = getenv("CM_GN_CLUSTER") != nullptr;
@@ -609,6 +610,7 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st) {
     if (slices < 1) slices = 1;
     gn_stats2_kernel<<<dim3(slices, p.B), GN2_T, 0, st>>>(p, slices, partial);
     gn_apply2_kernel<<<dim3(slices, p.B), GN2_T, 0, st>>>(p, slices, slices, partial);
+    if (launches) *launches = 2;
     CM_CUDA(cudaGetLastError());
     return 0;
   }

@@ -35,7 +35,8 @@ struct GnParams {
 };
 // `partial`: scratch of B * gn_chunks(pixels, C) * 16 floats (slice statistics)
 int gn_chunks(int pixels, int C);
-int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st);
+// *launches (optional) receives the number of kernels enqueued (1 or 2)
+int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* launches = nullptr);
 
 // ---- first conv: 3(+)->base channels straight from the API layout (unet.py:32,138,144) ----
 // x: [B][cin][H][W][F] fp32, past: [B][cin][H][W][P] fp32 (virtual concat along time),

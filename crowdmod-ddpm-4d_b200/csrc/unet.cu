@@ -110,6 +110,7 @@ struct cm_unet {
   cudaGraphExec_t graph_exec = nullptr;
   cm_chain_args graph_key{};
   int64_t last_chain_launches = 0;
+  int64_t graph_launches_per_step = 0;
   int64_t last_backward_launches = 0;
   double flops_per_sample = 0.0;
   // ---- training state (cm_unet_train_forward / cm_unet_backward) ----
@@ -542,7 +543,9 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
             g.drop_ld = u->temb_ld;
           }
         }
-        if (int e = gn_silu_enqueue(g, u->gn_partial, st)) return e;
+        int nl = 1;
+        if (int e = gn_silu_enqueue(g, u->gn_partial, st, &nl)) return e;
+        if (launches) *launches += nl - 1;
       } break;
       case OP_CONV: {
         if (op.plaunch.ok) {
@@ -1293,8 +1296,9 @@ int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
     CM_CUDA(cudaGraphInstantiate(&u->graph_exec, g, 0));
     cudaGraphDestroy(g);
     u->graph_key = *a;
+    u->graph_launches_per_step = per_step;
   } else {
-    per_step = (int64_t)cm_unet_launches_per_forward(u);   // ops (GroupNorm = 2 kernels) + step advance
+    per_step = u->graph_launches_per_step;
   }
   for (int i = 0; i < a->nsteps; ++i) CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
   u->last_chain_launches = per_step * a->nsteps;
