@@ -19,6 +19,12 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
 
+bool pdl_enabled() {
+  // measured on B200 (ATC B=64, graph replay): 1.296 ms/step with PDL vs 1.269 without -> opt-in only
+  static const bool on = getenv("CM_PDL") != nullptr;
+  return on;
+}
+
 static int* g_flag = nullptr;
 int* device_error_flag() {
   static std::once_flag once;

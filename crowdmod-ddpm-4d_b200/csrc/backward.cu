@@ -782,65 +782,121 @@ int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const
 }
 
 // =============================================================================================
-// first conv weight / bias gradient (unet.py:32); 256 threads = cout x (256/cout) k-groups
+// first conv weight / bias gradient (unet.py:32): dW[co][k] = sum_pixels dOut[p][co] * col[p][k],
+// k = ci*27 + tap.  Persistent CTAs walk chunks of 256 pixels: every thread expands ITS pixel
+// into an im2col row (84 floats, from the fp32 API tensors) and copies its dOut row to shared
+// memory; then warp g accumulates k-group g (12 k's = three 128-bit broadcast loads per pixel)
+// with lane = output channel.  Partial sums stay in registers across chunks; one atomicAdd per
+// (CTA, output) at the end.
 // =============================================================================================
-__global__ void __launch_bounds__(256)
+constexpr int FW_PIX = 192;     // pixels per chunk
+constexpr int FW_THREADS = 288; // 9 warps x 12 k's
+constexpr int FW_KP = 108;      // padded K = 27 * 4 input channels
+
+__global__ void __launch_bounds__(FW_THREADS)
 first_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ past,
                         const float* __restrict__ dout, float* __restrict__ dw, float* __restrict__ db,
-                        int B, int H, int W, int P, int F, int cin, int cout, int pix_per_cta) {
-  constexpr int MAXK = 28;
+                        int B, int H, int W, int P, int F, int cin, int cout, int nchunks) {
+  extern __shared__ float sm[];
+  float* col = sm;                       // [FW_PIX][FW_KP]
+  float* dsm = sm + FW_PIX * FW_KP;      // [FW_PIX][cout + 1]
   const int L = P + F, K = 27 * cin;
-  const int ngroups = 256 / cout;
-  const int kper = (K + ngroups - 1) / ngroups;
-  const int co = threadIdx.x % cout, grp = threadIdx.x / cout;
-  const int k0 = grp * kper;
-  float acc[MAXK];
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k) acc[k] = 0.f;
-  float bacc = 0.f;
   const size_t total = (size_t)B * L * H * W;
-  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
-  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
-  for (size_t pix = p0; pix < p1; ++pix) {          // internal layout [B][L][H][W]
-    const int wc = (int)(pix % W);
-    size_t r = pix / W;
-    const int h = (int)(r % H);
-    r /= H;
-    const int l = (int)(r % L);
-    const int b = (int)(r / L);
-    const float d = (grp < ngroups) ? dout[pix * cout + co] : 0.f;
-    bacc += d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ldd = cout + 1;
+  // accumulators: this warp's 12 k's x (cout/32) channel groups of this lane (cout <= 64)
+  float acc[2][12];
+  float bacc[2] = {0.f, 0.f};
 #pragma unroll
-    for (int kk = 0; kk < MAXK; ++kk) {
-      const int k = k0 + kk;
-      if (kk >= kper || k >= K) break;
-      const int ci = k / 27, tap = k - ci * 27;
-      const int hh = h + tap / 9 - 1, ww = wc + (tap / 3) % 3 - 1, ll = l + tap % 3 - 1;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W || ll < 0 || ll >= L) continue;
-      const size_t pl = ((size_t)(b * cin + ci) * H + hh) * W + ww;
-      const float a = (ll < P) ? past[pl * P + ll] : x[pl * F + (ll - P)];
-      acc[kk] = fmaf(a, d, acc[kk]);
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[g][j] = 0.f;
+  const int ngrp = cout / 32;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const size_t pix = (size_t)chunk * FW_PIX + tid;
+    __syncthreads();                     // previous chunk fully consumed
+    float* cr = col + tid * FW_KP;
+    if (tid >= FW_PIX) {
+      // warps beyond the chunk's pixels only take part in the accumulation
+    } else if (pix < total) {
+      const int wc = (int)(pix % W);
+      size_t r = pix / W;
+      const int h = (int)(r % H);
+      r /= H;
+      const int l = (int)(r % L);
+      const int b = (int)(r / L);
+      for (int k = 0; k < K; ++k) {
+        const int ci = k / 27, tap = k - ci * 27;
+        const int hh = h + tap / 9 - 1, ww = wc + (tap / 3) % 3 - 1, ll = l + tap % 3 - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W && ll >= 0 && ll < L) {
+          const size_t pl = ((size_t)(b * cin + ci) * H + hh) * W + ww;
+          v = (ll < P) ? past[pl * P + ll] : x[pl * F + (ll - P)];
+        }
+        cr[k] = v;
+      }
+      for (int k = K; k < FW_KP; ++k) cr[k] = 0.f;
+      for (int c = 0; c < cout; ++c) dsm[tid * ldd + c] = 0.f;
+    } else {
+      for (int k = 0; k < FW_KP; ++k) cr[k] = 0.f;
+      for (int c = 0; c < cout; ++c) dsm[tid * ldd + c] = 0.f;
+    }
+    __syncthreads();
+    // coalesced copy of the chunk's dOut rows: [FW_PIX][cout] contiguous in global memory
+    {
+      const size_t base = (size_t)chunk * FW_PIX;
+      const size_t nvalid = total - base < (size_t)FW_PIX ? total - base : (size_t)FW_PIX;
+      for (size_t i = tid; i < nvalid * cout; i += FW_THREADS) {
+        const int pp = (int)(i / cout), c = (int)(i - (size_t)pp * cout);
+        dsm[pp * ldd + c] = dout[base * cout + i];
+      }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int pp = 0; pp < FW_PIX; ++pp) {
+      const float4* c4 = reinterpret_cast<const float4*>(col + pp * FW_KP + warp * 12);
+      const float4 a0 = c4[0], a1 = c4[1], a2 = c4[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g >= ngrp) break;
+        const float d = dsm[pp * ldd + g * 32 + lane];
+        acc[g][0] = fmaf(a0.x, d, acc[g][0]); acc[g][1] = fmaf(a0.y, d, acc[g][1]);
+        acc[g][2] = fmaf(a0.z, d, acc[g][2]); acc[g][3] = fmaf(a0.w, d, acc[g][3]);
+        acc[g][4] = fmaf(a1.x, d, acc[g][4]); acc[g][5] = fmaf(a1.y, d, acc[g][5]);
+        acc[g][6] = fmaf(a1.z, d, acc[g][6]); acc[g][7] = fmaf(a1.w, d, acc[g][7]);
+        acc[g][8] = fmaf(a2.x, d, acc[g][8]); acc[g][9] = fmaf(a2.y, d, acc[g][9]);
+        acc[g][10] = fmaf(a2.z, d, acc[g][10]); acc[g][11] = fmaf(a2.w, d, acc[g][11]);
+        if (warp == 8) bacc[g] += d;
+      }
     }
   }
-  if (grp >= ngroups) return;
 #pragma unroll
-  for (int kk = 0; kk < MAXK; ++kk) {
-    const int k = k0 + kk;
-    if (kk >= kper || k >= K) break;
-    atomicAdd(dw + (size_t)co * K + k, acc[kk]);
+  for (int g = 0; g < 2; ++g) {
+    if (g >= ngrp) break;
+    const int co = g * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int k = warp * 12 + j;
+      if (k < K) atomicAdd(dw + (size_t)co * K + k, acc[g][j]);
+    }
+    if (warp == 8) atomicAdd(db + co, bacc[g]);
   }
-  if (grp == 0) atomicAdd(db + co, bacc);
 }
 
 int first_conv_wgrad_enqueue(const float* x, const float* past, const float* dout, float* dw, float* db,
                              int B, int H, int W, int P, int F, int cin, int cout, cudaStream_t st) {
-  CM_CHECK(cout <= 256 && cout % 32 == 0, "first conv wgrad: cout must be a multiple of 32, <= 256");
-  const int ngroups = 256 / cout;
-  CM_CHECK((27 * cin + ngroups - 1) / ngroups <= 28, "first conv wgrad: 27*cin/(256/cout) must be <= 28");
+  CM_CHECK(cout == 32 || cout == 64, "first conv wgrad: cout must be 32 or 64 (got %d)", cout);
+  CM_CHECK(27 * cin <= FW_KP, "first conv wgrad: at most 4 input channels (got %d)", cin);
   const size_t total = (size_t)B * (P + F) * H * W;
-  const int ppc = (int)((total + 1183) / 1184);
-  const int blocks = (int)((total + ppc - 1) / ppc);
-  first_conv_wgrad_kernel<<<blocks, 256, 0, st>>>(x, past, dout, dw, db, B, H, W, P, F, cin, cout, ppc);
+  const int nchunks = (int)((total + FW_PIX - 1) / FW_PIX);
+  const int blocks = nchunks < 296 ? nchunks : 296;
+  const size_t smem = ((size_t)FW_PIX * FW_KP + (size_t)FW_PIX * (cout + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    CM_CUDA(cudaFuncSetAttribute(first_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    attr = true;
+  }
+  first_conv_wgrad_kernel<<<blocks, FW_THREADS, smem, st>>>(x, past, dout, dw, db, B, H, W, P, F, cin, cout, nchunks);
   CM_CUDA(cudaGetLastError());
   return 0;
 }

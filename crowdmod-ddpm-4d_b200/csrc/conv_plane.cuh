@@ -138,10 +138,12 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is CTA-local set-up; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================

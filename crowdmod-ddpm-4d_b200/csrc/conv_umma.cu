@@ -86,21 +86,21 @@ int launch_t(const ConvLaunch& L, cudaStream_t st) {
     cfg.blockDim = dim3(CONV_THREADS);
     cfg.dynamicSmemBytes = L.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = L.p.ksplit;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (L.p.terms == 2) CM_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, 2>, L.p));
     else CM_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, 1>, L.p));
     return 0;
   }
-  if (L.p.terms == 2) conv_umma_kernel<BN, BK, 2><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
-  else conv_umma_kernel<BN, BK, 1><<<L.grid, CONV_THREADS, L.smem, st>>>(L.p);
-  CM_CUDA(cudaGetLastError());
-  return 0;
+  if (L.p.terms == 2) return launch_pdl(conv_umma_kernel<BN, BK, 2>, L.grid, dim3(CONV_THREADS), L.smem, st, L.p);
+  return launch_pdl(conv_umma_kernel<BN, BK, 1>, L.grid, dim3(CONV_THREADS), L.smem, st, L.p);
 }
 
 template <int BN, int BK>
@@ -303,10 +303,8 @@ int make_plane_map(CUtensorMap* map, const __half* base, int B, int D, int H, in
 
 template <int BN, int BK>
 int plane_launch_t(const PlaneLaunch& L, cudaStream_t st) {
-  if (L.p.terms == 2) conv_plane_kernel<BN, BK, 2><<<L.grid, PL_THREADS, L.smem, st>>>(L.p);
-  else conv_plane_kernel<BN, BK, 1><<<L.grid, PL_THREADS, L.smem, st>>>(L.p);
-  CM_CUDA(cudaGetLastError());
-  return 0;
+  if (L.p.terms == 2) return launch_pdl(conv_plane_kernel<BN, BK, 2>, L.grid, dim3(PL_THREADS), L.smem, st, L.p);
+  return launch_pdl(conv_plane_kernel<BN, BK, 1>, L.grid, dim3(PL_THREADS), L.smem, st, L.p);
 }
 template <int BN, int BK>
 int plane_attr_t() {

@@ -118,10 +118,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is CTA-local set-up; global memory is touched only from here on
 
   const bool tr = P.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
   if (tr && threadIdx.x == 0) P.trace[0] = gtime_ns();

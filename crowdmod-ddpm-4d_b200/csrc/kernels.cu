@@ -324,6 +324,8 @@ __device__ __forceinline__ Chan3 chan_merge(const Chan3 a, const Chan3 b) {
 }
 
 __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int slices, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tri[GN2_T][3];
   const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2, vpp = Q >> 3;
   // blockDim.x == GN2_T; the first T = floor(GN2_T/Q)*Q threads sweep the data (fixed channel quad)
@@ -398,6 +400,8 @@ __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int 
 
 __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int slices, int stat_slices,
                                                           const float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float stat[2][8];
   const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2;
   const int tid = threadIdx.x;
@@ -477,6 +481,8 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
 constexpr int GNS_CACHE = 8;
 
 __global__ void __launch_bounds__(1024) gn_small_kernel(const GnParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tri[1024][3];
   __shared__ float stat[2][8];
   const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2, vpp = Q >> 3;
@@ -597,8 +603,7 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* lau
       if (T < 256) T = 256;
       while ((long)(T / Q) * Q * GNS_CACHE < nvec) T += 32;      // sweeping threads are floor(T/Q)*Q
       if (T <= 1024) {
-        gn_small_kernel<<<p.B, T, 0, st>>>(p);
-        CM_CUDA(cudaGetLastError());
+        if (int e = launch_pdl(gn_small_kernel, dim3(p.B), dim3(T), 0, st, p)) return e;
         return 0;
       }
     }
@@ -608,8 +613,10 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* lau
     if (slices > max_slices) slices = max_slices;
     if (slices > GN2_MAX_SLICES) slices = GN2_MAX_SLICES;
     if (slices < 1) slices = 1;
-    gn_stats2_kernel<<<dim3(slices, p.B), GN2_T, 0, st>>>(p, slices, partial);
-    gn_apply2_kernel<<<dim3(slices, p.B), GN2_T, 0, st>>>(p, slices, slices, partial);
+    if (int e = launch_pdl(gn_stats2_kernel, dim3(slices, p.B), dim3(GN2_T), 0, st, p, slices, partial)) return e;
+    if (int e = launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), 0, st, p, slices, slices,
+                           static_cast<const float*>(partial)))
+      return e;
     if (launches) *launches = 2;
     CM_CUDA(cudaGetLastError());
     return 0;
@@ -653,6 +660,8 @@ __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ x, const float* __restrict__ past,
                   const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ out, int B, int H, int W, int P, int F, int cout) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   constexpr int K = 27 * CIN;
   const int L = P + F;
@@ -742,7 +751,7 @@ int first_conv_enqueue(const float* x, const float* past, const float* w, const 
   const size_t smem = ((size_t)27 * cin * cout + (size_t)cin * (FC_TS + 2) * (FC_TS + 2) * (L + 2)) * sizeof(float);
 #define CM_FIRST(CI)                                                                           \
   case CI:                                                                                     \
-    first_conv_kernel<CI><<<blocks, threads, smem, st>>>(x, past, w, bias, out, B, H, W, P, F, cout); \
+    if (int e = launch_pdl(first_conv_kernel<CI>, dim3(blocks), dim3(threads), smem, st, x, past, w, bias, out, B, H, W, P, F, cout)) return e; \
     break;
   switch (cin) {
     CM_FIRST(1) CM_FIRST(2) CM_FIRST(3) CM_FIRST(4)
@@ -758,6 +767,8 @@ int first_conv_enqueue(const float* x, const float* past, const float* w, const 
 // =============================================================================================
 template <int COUT>
 __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float ws[];   // [27][cin][COUT]
   const int cin = p.cin;
   for (int idx = threadIdx.x; idx < 27 * cin * COUT; idx += blockDim.x) {
@@ -885,7 +896,7 @@ int final_conv_enqueue(const FinalParams& p, cudaStream_t st) {
   const size_t smem = (size_t)27 * p.cin * p.cout * sizeof(float);
 #define CM_FINAL(CO)                                                                           \
   case CO: {                                                                                   \
-    final_conv_kernel<CO><<<blocks, 256, smem, st>>>(p);                                       \
+    if (int e = launch_pdl(final_conv_kernel<CO>, dim3(blocks), dim3(256), smem, st, p)) return e; \
   } break;
   switch (p.cout) {
     CM_FINAL(1) CM_FINAL(2) CM_FINAL(3) CM_FINAL(4)
@@ -978,6 +989,8 @@ __device__ __forceinline__ void split_h2(float x, float y, uint32_t* hi, uint32_
 template <int DH, int NT>
 __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx,
                                                           int S, int C, int heads) {
+  pdl_trigger();
+  pdl_wait();
   const int dh = C / heads;
   constexpr int SP = NT * 8;            // padded sequence length
   constexpr int KLD = DH + 8;           // smem row stride (halfs) of K  [SP][KLD]
@@ -1107,8 +1120,7 @@ template <int DH, int NT>
 static int attn_launch(const float* qkv, __half* ctx, int B, int S, int C, int heads, cudaStream_t st) {
   constexpr int SP = NT * 8;
   const size_t smem = ((size_t)2 * SP * (DH + 8) + (size_t)DH * (SP + 8)) * sizeof(__half);
-  attn_mma_kernel<DH, NT><<<B * heads, NT * 16, smem, st>>>(qkv, ctx, S, C, heads);
-  CM_CUDA(cudaGetLastError());
+  if (int e = launch_pdl(attn_mma_kernel<DH, NT>, dim3(B * heads), dim3(NT * 16), smem, st, qkv, ctx, S, C, heads)) return e;
   return 0;
 }
 
@@ -1175,13 +1187,14 @@ int kernels_init() {
 // chain bookkeeping
 // =============================================================================================
 __global__ void advance_step_kernel(int* step_dev, int* t_dev, const int* tsteps, int nsteps) {
+  pdl_trigger();
+  pdl_wait();
   const int s = *step_dev + 1;
   *step_dev = s;
   *t_dev = tsteps[s < nsteps ? s : nsteps - 1];
 }
 int advance_step_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaStream_t st) {
-  advance_step_kernel<<<1, 1, 0, st>>>(step_dev, t_dev, tsteps, nsteps);
-  CM_CUDA(cudaGetLastError());
+  if (int e = launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, st, step_dev, t_dev, tsteps, nsteps)) return e;
   return 0;
 }
 

@@ -62,6 +62,7 @@ struct Op {
   size_t g_off = 0;         // CONV: offset of the packed-K weight-gradient scratch
   size_t colsum_off = 0;    // CONV: per-sample channel sums of dOut ([B][cout])
   ConvLaunch dlaunch, dxlaunch;
+  PlaneLaunch dplaunch;     // dgrad of a k3 s1 conv is a k3 s1 conv: plane-tile kernel when it fits
   WgradLaunch wlaunch;
 };
 
@@ -706,6 +707,13 @@ int prepare_train(cm_unet* u, int batch) {
                               op.cout, nullptr, 0, u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
       return rc;
     op.dlaunch.p.out32 = u->g32[op.in];
+    op.dplaunch.ok = false;
+    if (op.mode == 0 && getenv("CM_NO_PLANE") == nullptr) {
+      if (int rc = plane_prepare(&op.dplaunch, u->g16[op.out], batch, lo.D, lo.H, lo.W, op.cout, nullptr, 0,
+                                 u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
+        return rc;
+      if (op.dplaunch.ok) op.dplaunch.p.out32 = u->g32[op.in];
+    }
     if (op.cin_extra) {
       if (int rc = conv_prepare(&op.dxlaunch, 3, u->g16[op.out], batch, lo.D, lo.H, lo.W, op.cout, nullptr, 0,
                                 u->dpack + op.dxpack_off, op.cin_extra, u->cfg.weight_terms))
@@ -756,6 +764,17 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
   if (int e = auto_scale_enqueue(d_eps, n_eps, 64.f, u->loss_scale, u->max_word, st)) return e;
   nl += 2;
   std::vector<char> written(u->tens.size(), 0);
+  // bring-up: CM_BWD_TRACE=1 brackets every backward stage with CUDA events and prints a table
+  static const bool trace = getenv("CM_BWD_TRACE") != nullptr;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  auto mark = [&](const std::string& what) {
+    if (!trace) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    marks.emplace_back(what, ev);
+  };
+  mark("begin");
   for (int oi = (int)u->ops.size() - 1; oi >= 0; --oi) {
     Op& op = u->ops[oi];
     switch (op.type) {
@@ -767,6 +786,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           return e;
         written[op.in] = 1;
         nl += 2;
+        mark("final_bwd " + op.tag);
       } break;
       case OP_GN: {
         GnBwdParams g{};
@@ -800,6 +820,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
         g.dbeta = gp(op.beta);
         if (int e = gn_backward_enqueue(g, u->gn_bwd_partial, st)) return e;
         nl += 3;
+        mark("gn_bwd " + op.tag);
       } break;
       case OP_CONV: {
         CM_CHECK(written[op.out], "backward: gradient of '%s' output missing", op.tag.c_str());
@@ -824,7 +845,13 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           if (int e = rowsum_enqueue(cs, gp(op.bias2), B, op.cout, cs_ld, 0, st)) return e;
           ++nl;
         }
-        {
+        mark("cast_colsum " + op.tag);
+        if (op.dplaunch.ok) {
+          PlaneLaunch L = op.dplaunch;
+          L.p.resid = written[op.in] ? u->g32[op.in] : nullptr;   // accumulate in place
+          written[op.in] = 1;
+          if (int e = plane_enqueue(L, st)) return e;
+        } else {
           ConvLaunch L = op.dlaunch;
           L.p.resid = written[op.in] ? u->g32[op.in] : nullptr;   // accumulate in place
           written[op.in] = 1;
@@ -837,11 +864,14 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           if (int e = conv_enqueue(L, st)) return e;
           ++nl;
         }
+        mark("dgrad " + op.tag);
         if (int e = wgrad_enqueue(op.wlaunch, st)) return e;
+        mark("wgrad " + op.tag);
         if (int e = unpack_wgrad_enqueue(op.mode, u->G + op.g_off, gp(op.w), op.wx >= 0 ? gp(op.wx) : nullptr,
                                          op.cout, op.cin, op.cin_extra, 1, st))
           return e;
         nl += 4;
+        mark("unpack " + op.tag);
       } break;
       case OP_ATTN: {
         CM_CHECK(written[op.ctx], "backward: gradient of '%s' output missing", op.tag.c_str());
@@ -852,6 +882,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           return e;
         written[op.qkv] = 1;
         ++nl;
+        mark("attn_bwd " + op.tag);
       } break;
       case OP_FIRST: {
         CM_CHECK(written[op.out], "backward: gradient of the first conv output missing");
@@ -860,6 +891,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
                                              c.in_channels, c.base_channels, st))
           return e;
         ++nl;
+        mark("first_wgrad " + op.tag);
       } break;
     }
   }
@@ -891,6 +923,22 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
     return e;
   if (int e = scale_inplace_enqueue(grads, u->grad_total, u->loss_scale + 1, st)) return e;
   nl += 8;
+  mark("temb_mlp + unscale");
+  if (trace) {
+    cudaStreamSynchronize(st);
+    std::map<std::string, float> agg;
+    float total = 0.f;
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      fprintf(stderr, "CM_BWD %-60s %8.1f us\n", marks[i].first.c_str(), ms * 1e3f);
+      agg[marks[i].first.substr(0, marks[i].first.find(' '))] += ms;
+      total += ms;
+    }
+    for (auto& kv : agg) fprintf(stderr, "CM_BWD_SUM %-14s %8.3f ms\n", kv.first.c_str(), kv.second);
+    fprintf(stderr, "CM_BWD_SUM %-14s %8.3f ms\n", "total", total);
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
   if (launches) *launches = nl;
   return 0;
 }
