@@ -14,7 +14,7 @@ namespace cm {
 // =============================================================================================
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const float* __restrict__ wx,
                                          __half* __restrict__ dst, int cout, int cin, int cinx,
-                                         int taps, int terms, int perm) {
+                                         int taps, int terms, int perm, int cin_src) {
   const size_t ktot = (size_t)taps * cin + cinx;
   const size_t total = (size_t)cout * ktot;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
@@ -30,7 +30,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const floa
       // [B, time, rows, cols, C]  ->  source tap = (h*3 + w)*3 + d
       int st = tap;
       if (perm && taps == 27) st = (((tap / 3) % 3) * 3 + (tap % 3)) * 3 + tap / 9;
-      v = w[((size_t)n * cin + ci) * taps + st];
+      v = ci < cin_src ? w[((size_t)n * cin_src + ci) * taps + st] : 0.f;   // zero-padded channels
     } else {
       v = wx[(size_t)n * cinx + (k - (size_t)taps * cin)];
     }
@@ -44,7 +44,52 @@ int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, in
                       int taps, int terms, int perm, cudaStream_t st) {
   const size_t total = (size_t)cout * ((size_t)taps * cin + cinx);
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, wx, dst, cout, cin, cinx, taps, terms, perm);
+  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, wx, dst, cout, cin, cinx, taps, terms, perm, cin);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pack_conv_weights_padded(const float* w, __half* dst, int cout, int cin_src, int cin_packed, int terms,
+                             int perm, cudaStream_t st) {
+  const size_t total = (size_t)cout * 27 * cin_packed;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, nullptr, dst, cout, cin_packed, 0, 27, terms, perm, cin_src);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// API tensors (future [B,C,H,W,F] | past [B,C,H,W,P], time fastest) -> channels 0..C-1 of the fp16
+// channels-last, time-major operand [B, P+F, H, W, 32] of the first conv (the other channels stay
+// zero from the arena's initialisation).  One thread per pixel, one 8-byte store.
+__global__ void pack_first_input_kernel(const float* __restrict__ x, const float* __restrict__ past,
+                                        __half* __restrict__ out, int B, int H, int W, int P, int F, int cin) {
+  const int L = P + F;
+  const size_t total = (size_t)B * L * H * W;
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    const int wc = (int)(pix % W);
+    size_t r = pix / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int l = (int)(r % L);
+    const int b = (int)(r / L);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < cin; ++ci) {
+      const size_t pl = ((size_t)(b * cin + ci) * H + h) * W + wc;
+      v[ci] = (l < P) ? past[pl * P + l] : x[pl * F + (l - P)];
+    }
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + pix * 32) = u;
+  }
+}
+int pack_first_input_enqueue(const float* x, const float* past, __half* out16, int B, int H, int W, int P, int F,
+                             int cin, cudaStream_t st) {
+  CM_CHECK(cin >= 1 && cin <= 4, "first conv supports 1..4 input channels (got %d)", cin);
+  const size_t total = (size_t)B * (P + F) * H * W;
+  const int blocks = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  pack_first_input_kernel<<<blocks, 256, 0, st>>>(x, past, out16, B, H, W, P, F, cin);
   CM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,6 +14,12 @@ int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, in
                       int taps, int terms, int perm, cudaStream_t st);
 // nearest-x2 + k3 conv folded into 8 phase convs with 2x2x2 combined taps
 // (layers.py:92-94).  dst: [terms*cout][64*cin], column = phase*8*cin + tap8*cin + ci.
+// k3 conv weights whose cin_src (< 32) input channels are zero-padded to cin_packed packed channels
+int pack_conv_weights_padded(const float* w, __half* dst, int cout, int cin_src, int cin_packed, int terms,
+                             int perm, cudaStream_t st);
+// first-conv operand: API tensors -> channels 0..cin-1 of fp16 [B, P+F, H, W, 32] (other channels untouched)
+int pack_first_input_enqueue(const float* x, const float* past, __half* out16, int B, int H, int W, int P, int F,
+                             int cin, cudaStream_t st);
 int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms, int perm,
                           cudaStream_t st);
 

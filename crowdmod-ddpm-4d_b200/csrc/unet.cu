@@ -88,6 +88,11 @@ struct cm_unet {
   int temb_ld = 0;
   int p_table = -1, p_w1 = -1, p_b1 = -1, p_w2 = -1, p_b2 = -1;
   int p_first_w = -1, p_first_b = -1, p_final_w = -1, p_final_b = -1;
+  // first conv on the tensor cores: the 3(+)-channel input is packed into a zero-padded 32-channel fp16
+  // operand and run through the plane-tile kernel (falls back to first_conv_kernel when not covered)
+  int first_in = -1;
+  size_t first_wpack_off = 0;
+  PlaneLaunch first_plane;
   // device state
   __half* wpack = nullptr;
   size_t wpack_elems = 0;
@@ -316,6 +321,10 @@ int build_plan(cm_unet* u) {
   u->p_first_w = u->add_param("first.weight", {base, c.in_channels, 3, 3, 3});
   u->p_first_b = u->add_param("first.bias", {base});
 
+  u->first_in = u->add_tensor(0, 32);
+  u->tens[u->first_in].need16 = true;
+  u->first_wpack_off = u->wpack_elems;
+  u->wpack_elems += (size_t)c.weight_terms * base * 27 * 32;
   Op first;
   first.type = OP_FIRST;
   first.tag = "first";
@@ -452,6 +461,20 @@ int reserve(cm_unet* u, int batch) {
 
 // conv launches depend on the live batch (grid, tensor-map extents): (re)built per call batch
 int prepare_convs(cm_unet* u, int batch) {
+  {
+    const Level& l0 = u->levels[0];
+    u->first_plane.ok = false;
+    static const bool no_tc_first = getenv("CM_NO_PLANE") != nullptr || getenv("CM_FIRST_SIMT") != nullptr;
+    if (!no_tc_first) {
+      if (int rc = plane_prepare(&u->first_plane, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32, nullptr, 0,
+                                 u->wpack + u->first_wpack_off, u->cfg.base_channels, u->cfg.weight_terms))
+        return rc;
+      if (u->first_plane.ok) {
+        u->first_plane.p.bias = u->params[u->p_first_b].ptr;
+        u->first_plane.p.out32 = nullptr;   // set per run (tensor of the OP_FIRST op)
+      }
+    }
+  }
   for (Op& op : u->ops) {
     if (op.type != OP_CONV) continue;
     const Level& li = u->levels[op.in_level];
@@ -517,6 +540,16 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
     switch (op.type) {
       case OP_FIRST: {
         const Level& l0 = u->levels[0];
+        if (u->first_plane.ok) {
+          if (int e = pack_first_input_enqueue(rc.future, rc.past, u->tens[u->first_in].p16, rc.batch, l0.H, l0.W,
+                                               c.past_len, c.future_len, c.in_channels, st))
+            return e;
+          PlaneLaunch L = u->first_plane;
+          L.p.out32 = u->tens[op.out].p32;
+          if (int e = plane_enqueue(L, st)) return e;
+          if (launches) ++*launches;
+          break;
+        }
         if (int e = first_conv_enqueue(rc.future, rc.past, u->params[u->p_first_w].ptr,
                                        u->params[u->p_first_b].ptr, u->tens[op.out].p32, rc.batch,
                                        l0.H, l0.W, c.past_len, c.future_len, c.in_channels,
@@ -1035,6 +1068,9 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
         return e;
     }
   }
+  if (int e = pack_conv_weights_padded(u->params[u->p_first_w].ptr, u->wpack + u->first_wpack_off,
+                                       u->cfg.base_channels, u->cfg.in_channels, 32, terms, 1, st))
+    return e;
   const int nb = (int)u->temb_couts.size();
   if (!u->d_wd) {
     CM_CUDA(cudaMalloc(&u->d_wd, nb * sizeof(float*)));
