@@ -56,6 +56,11 @@ struct PlaneParams {
   float* out32;
   __half* out16;
   int out_ld;
+  // GroupNorm statistics records of the values this launch writes (nullptr = none): per (sample, unit
+  // of the sample, output channel) a float4 {shift, sum(v - shift), sum((v - shift)^2), 0} over the
+  // unit's R*HB*W valid rows; units belong to ONE sample, so the consumer (gn_apply2_kernel) merges
+  // them in a fixed order -> bit-reproducible wherever the sample sits in the batch.
+  float* stats_rec;
   int* err_flag;
 };
 
@@ -112,6 +117,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   float* colv = reinterpret_cast<float*>(tail + 256);      // [BN]
   float* side = reinterpret_cast<float*>(tail + 256 + 512);       // [ntiles*4 + 1][3][BN] block-boundary rows
   float* ybuf = side + (P.ntiles * 4 + 1) * 3 * BN;               // [ntiles*128][TLD]
+  float* sred = ybuf + (P.ntiles * 128 + 2) * TLD;                // [8 warps][BN][2] + [BN] shifts
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncm = P.cin_main / BK;
@@ -367,6 +373,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // coalesced read-out: RPP rows per pass, LPR lanes per row
+      float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = st1;   // GroupNorm partial sums of (v - cv)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (mi[j] < 0) continue;
@@ -384,7 +391,11 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
             v.x += b1.x; v.y += b1.y; v.z += b1.z; v.w += b1.w;
           }
         }
-        v.x += cv.x + rv[j].x; v.y += cv.y + rv[j].y; v.z += cv.z + rv[j].z; v.w += cv.w + rv[j].w;
+        v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w;
+        st1.x += v.x; st1.y += v.y; st1.z += v.z; st1.w += v.w;
+        st2.x = fmaf(v.x, v.x, st2.x); st2.y = fmaf(v.y, v.y, st2.y);
+        st2.z = fmaf(v.z, v.z, st2.z); st2.w = fmaf(v.w, v.w, st2.w);
+        v.x += cv.x; v.y += cv.y; v.z += cv.z; v.w += cv.w;
         const size_t m = static_cast<size_t>(mi[j]);
         if (P.out32) *reinterpret_cast<float4*>(P.out32 + m * P.out_ld + nn0 + sub_c) = v;
         if (P.out16) {
@@ -395,7 +406,36 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
           *reinterpret_cast<uint2*>(P.out16 + m * P.out_ld + nn0 + sub_c) = uu;
         }
       }
+      if (P.stats_rec) {
+        // lanes that share a channel quad (same lane % LPR) hold different rows: butterfly over them
+#pragma unroll
+        for (int w = LPR; w < 32; w <<= 1) {
+          st1.x += __shfl_xor_sync(0xffffffffu, st1.x, w); st1.y += __shfl_xor_sync(0xffffffffu, st1.y, w);
+          st1.z += __shfl_xor_sync(0xffffffffu, st1.z, w); st1.w += __shfl_xor_sync(0xffffffffu, st1.w, w);
+          st2.x += __shfl_xor_sync(0xffffffffu, st2.x, w); st2.y += __shfl_xor_sync(0xffffffffu, st2.y, w);
+          st2.z += __shfl_xor_sync(0xffffffffu, st2.z, w); st2.w += __shfl_xor_sync(0xffffffffu, st2.w, w);
+        }
+        if (lane < LPR) {
+          float* d = sred + ((et >> 5) * BN + sub_c) * 2;
+          d[0] = st1.x; d[1] = st2.x; d[2] = st1.y; d[3] = st2.y;
+          d[4] = st1.z; d[5] = st2.z; d[6] = st1.w; d[7] = st2.w;
+        }
+        if (et < LPR) *reinterpret_cast<float4*>(sred + 8 * BN * 2 + sub_c) = cv;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");       // ybuf / side are rewritten by the next unit
+      if (P.stats_rec && et < BN) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < PL_EPI / 32; ++wv) {             // fixed order over the 8 epilogue warps
+          a1 += sred[(wv * BN + et) * 2];
+          a2 += sred[(wv * BN + et) * 2 + 1];
+        }
+        const int hblocks = P.H / P.HB;
+        const int uis = (U.d0 / P.R) * hblocks + U.h0 / P.HB;
+        float4* rec = reinterpret_cast<float4*>(P.stats_rec) +
+                      (static_cast<size_t>(U.n) * P.units_per_sample + uis) * P.cout + nn0 + et;
+        *rec = make_float4(sred[8 * BN * 2 + et], a1, a2, 0.f);
+      }
     }
   }
   tc_fence_before();

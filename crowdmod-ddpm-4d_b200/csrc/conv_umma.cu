@@ -351,7 +351,9 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
   if (max_tiles < 1) return 0;
   const long smem_cap = 220 * 1024;
   const long tail_fixed = 256 + 512 + 1024;
-  auto ybuf_bytes = [&](int ntiles) { return (long)(ntiles * 128 + 2) * (bn + 4) * 4 + (long)(ntiles * 4 + 1) * 3 * bn * 4; };
+  auto ybuf_bytes = [&](int ntiles) {
+    return (long)(ntiles * 128 + 2) * (bn + 4) * 4 + (long)(ntiles * 4 + 1) * 3 * bn * 4 + (long)(8 * bn * 2 + bn) * 4;
+  };
   // work unit: R planes x HB rows.  Score = useful MMA rows x SM fill of the last wave; ties go to
   // the larger unit (more reuse of every weight tile).
   int bestR = 0, bestHB = 0;

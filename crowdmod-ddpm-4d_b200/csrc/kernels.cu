@@ -453,11 +453,39 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   const int T = (GN2_T / Q) * Q;
   const int b = blockIdx.y, slice = blockIdx.x;
   __shared__ float ptri[GN2_MAX_SLICES * 8 * 3];
-  for (int i = tid; i < stat_slices * 24; i += GN2_T)       // all slice statistics in one round trip
-    ptri[i] = partial[(size_t)b * GN2_MAX_SLICES * 24 + i];
+  __shared__ float chst[512][2];                            // per-channel (mean, M2) from records
+  const bool from_rec = p.rec0.rec != nullptr;
+  if (from_rec) {
+    // statistics from the producing convs' records: channel c merges its units in unit order, then
+    // the 8 group threads merge their channels in channel order (fixed tree -> deterministic)
+    for (int c2 = tid; c2 < C; c2 += GN2_T) {
+      const bool s0 = c2 < p.c0;
+      const GnRec& r = s0 ? p.rec0 : p.rec1;
+      const int cs = s0 ? p.c0 : p.c1, cl = s0 ? c2 : c2 - p.c0;
+      const float4* rp = reinterpret_cast<const float4*>(r.rec) + ((size_t)b * r.units) * cs + cl;
+      Chan3 a{0.f, 0.f, 0.f};
+      const float nk = (float)r.nvalid;
+#pragma unroll 4
+      for (int uidx = 0; uidx < r.units; ++uidx) {
+        const float4 v = rp[(size_t)uidx * cs];
+        const float d = v.y / nk;
+        a = chan_merge(a, Chan3{nk, v.x + d, fmaxf(v.z - v.y * d, 0.f)});
+      }
+      chst[c2][0] = a.mean;
+      chst[c2][1] = a.m2;
+    }
+  } else {
+    for (int i = tid; i < stat_slices * 24; i += GN2_T)     // all slice statistics in one round trip
+      ptri[i] = partial[(size_t)b * GN2_MAX_SLICES * 24 + i];
+  }
   __syncthreads();
   if (tid < 8) {
     Chan3 a{0.f, 0.f, 0.f};
+    if (from_rec) {
+      const float nc = (float)p.pixels;
+      for (int k2 = 0; k2 < cg_ch; ++k2)
+        a = chan_merge(a, Chan3{nc, chst[tid * cg_ch + k2][0], chst[tid * cg_ch + k2][1]});
+    } else
     for (int sidx = 0; sidx < stat_slices; ++sidx) {
       const float* o = ptri + (sidx * 8 + tid) * 3;
       a = chan_merge(a, Chan3{o[0], o[1], o[2]});
@@ -637,6 +665,18 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* lau
   const int C = p.c0 + p.c1;
   CM_CHECK(C % 32 == 0 && p.c0 % 4 == 0, "GroupNorm channels must be a multiple of 32 (C=%d)", C);
   static const bool use_cluster = getenv("CM_GN_CLUSTER") != nullptr;
+  if (partial && !use_cluster && C / 4 <= GN2_T && C <= 512 && p.rec0.rec && (p.c1 == 0 || p.rec1.rec)) {
+    // statistics come from the producing convs: one streaming apply kernel, no statistics pass
+    const int Q = C / 4;
+    const long nvec = (long)p.pixels * Q;
+    int slices = (148 * 4) / p.B;
+    const int max_slices = (int)((nvec + 4 * GN2_T - 1) / (4 * GN2_T));
+    if (slices > max_slices) slices = max_slices;
+    if (slices > GN2_MAX_SLICES) slices = GN2_MAX_SLICES;
+    if (slices < 1) slices = 1;
+    return launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), 0, st, p, slices, 0,
+                      static_cast<const float*>(partial));
+  }
   if (partial && !use_cluster && C / 4 <= GN2_T) {
     const int Q = C / 4;
     const long nvec = (long)p.pixels * Q;                       // float4 per sample

@@ -24,6 +24,12 @@ int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int te
                           cudaStream_t st);
 
 // ---- GroupNorm(8) [+SiLU] [+Dropout3d scale] -> fp16 operand (layers.py:30,41,57,70; :9,14) ----
+// GroupNorm statistics records written by a producing plane-tile conv (PlaneParams::stats_rec)
+struct GnRec {
+  const float* rec;   // [B][units][C_src] float4 {shift, sum, sumsq, 0}; nullptr = none
+  int units;          // units per sample
+  int nvalid;         // rows per unit
+};
 struct GnParams {
   const float* src0;   // fp32 channels-last [B][pixels][c0]
   const float* src1;   // optional second source (skip concat, unet.py:160), channels c0..c0+c1
@@ -38,6 +44,7 @@ struct GnParams {
   __half* out_norm;         // [B][pixels][C]
   __half* out_raw;          // optional raw fp16 copy of the (concatenated) input
   float* stats;             // optional [B][8][2] (mean, rstd) for backward
+  GnRec rec0, rec1;         // both sources have records -> no statistics pass over the data
 };
 // `partial`: scratch of B * gn_chunks(pixels, C) * 16 floats (slice statistics)
 int gn_chunks(int pixels, int C);

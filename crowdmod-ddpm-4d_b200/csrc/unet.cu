@@ -38,6 +38,10 @@ struct Tens {
   bool need32 = false, need16 = false;
   float* p32 = nullptr;
   __half* p16 = nullptr;
+  // GroupNorm statistics records emitted by the plane-tile conv that produces this tensor
+  bool gn_src = false;      // consumed by a GroupNorm
+  float* rec = nullptr;     // [batch][D*H][C] float4 (sized for the finest unit split)
+  int rec_units = 0, rec_nvalid = 0;   // set when the producing launch emits records, else 0
 };
 
 enum OpType { OP_FIRST, OP_GN, OP_CONV, OP_ATTN, OP_FINAL };
@@ -184,6 +188,8 @@ int add_gn(cm_unet* u, const std::string& prefix, int src0, int src1, int silu, 
   op.gamma = u->add_param(prefix + ".weight", {C});
   op.beta = u->add_param(prefix + ".bias", {C});
   op.silu = silu;
+  u->tens[src0].gn_src = true;
+  if (src1 >= 0) u->tens[src1].gn_src = true;
   op.gn_index = u->n_gn++;
   op.drop_off = drop_off;
   if (C > u->max_gn_channels) u->max_gn_channels = C;
@@ -433,12 +439,17 @@ int reserve(cm_unet* u, int batch) {
   u->train_prepared = 0;   // backward launches bake forward-arena pointers
   u->live_train_batch = 0;
   size_t off = 0;
-  std::vector<size_t> o32(u->tens.size(), 0), o16(u->tens.size(), 0);
+  std::vector<size_t> o32(u->tens.size(), 0), o16(u->tens.size(), 0), orec(u->tens.size(), 0);
   for (size_t i = 0; i < u->tens.size(); ++i) {
     Tens& t = u->tens[i];
     const size_t n = (size_t)batch * u->levels[t.level].pps() * t.C;
     if (t.need32) { o32[i] = off; off = align_up(off + n * 4, 1024); }
     if (t.need16) { o16[i] = off; off = align_up(off + n * 2, 1024); }
+    if (t.gn_src) {
+      const Level& lv = u->levels[t.level];
+      orec[i] = off;
+      off = align_up(off + (size_t)batch * lv.D * lv.H * t.C * 16, 1024);
+    }
   }
   const size_t temb_off = off;
   off = align_up(off + (size_t)batch * u->temb_ld * 4, 1024);
@@ -451,6 +462,8 @@ int reserve(cm_unet* u, int batch) {
     Tens& t = u->tens[i];
     t.p32 = t.need32 ? reinterpret_cast<float*>(u->arena + o32[i]) : nullptr;
     t.p16 = t.need16 ? reinterpret_cast<__half*>(u->arena + o16[i]) : nullptr;
+    t.rec = t.gn_src ? reinterpret_cast<float*>(u->arena + orec[i]) : nullptr;
+    t.rec_units = 0;
   }
   u->temb_batch = reinterpret_cast<float*>(u->arena + temb_off);
   u->gn_partial = reinterpret_cast<float*>(u->arena + gnp_off);
@@ -472,6 +485,18 @@ int prepare_convs(cm_unet* u, int batch) {
       if (u->first_plane.ok) {
         u->first_plane.p.bias = u->params[u->p_first_b].ptr;
         u->first_plane.p.out32 = nullptr;   // set per run (tensor of the OP_FIRST op)
+      }
+      for (Op& fo : u->ops) {
+        if (fo.type != OP_FIRST) continue;
+        Tens& t = u->tens[fo.out];
+        t.rec_units = 0;
+        static const bool no_rec = getenv("CM_NO_GNREC") != nullptr;
+        if (u->first_plane.ok && t.rec && !no_rec) {
+          PlaneParams& q = u->first_plane.p;
+          q.stats_rec = t.rec;
+          t.rec_units = q.units_per_sample;
+          t.rec_nvalid = q.R * q.HB * q.W;
+        }
       }
     }
   }
@@ -496,6 +521,17 @@ int prepare_convs(cm_unet* u, int batch) {
         q.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
         q.out32 = u->tens[op.out].p32;
         q.out16 = u->tens[op.out].p16;
+      }
+    }
+    {
+      Tens& t = u->tens[op.out];
+      t.rec_units = 0;
+      static const bool no_rec = getenv("CM_NO_GNREC") != nullptr;
+      if (op.plaunch.ok && t.rec && !no_rec) {
+        PlaneParams& q = op.plaunch.p;
+        q.stats_rec = t.rec;
+        t.rec_units = q.units_per_sample;
+        t.rec_nvalid = q.R * q.HB * q.W;
       }
     }
     ConvParams& p = op.launch.p;
@@ -570,6 +606,18 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         g.silu = op.silu;
         g.out_norm = u->tens[op.out_norm].p16;
         g.out_raw = op.out_raw >= 0 ? u->tens[op.out_raw].p16 : nullptr;
+        {
+          const Tens& t0 = u->tens[op.src0];
+          const bool ok0 = t0.rec_units > 0;
+          const bool ok1 = op.src1 < 0 || u->tens[op.src1].rec_units > 0;
+          if (ok0 && ok1) {
+            g.rec0 = GnRec{t0.rec, t0.rec_units, t0.rec_nvalid};
+            if (op.src1 >= 0) {
+              const Tens& t1 = u->tens[op.src1];
+              g.rec1 = GnRec{t1.rec, t1.rec_units, t1.rec_nvalid};
+            }
+          }
+        }
         if (rc.train) {
           g.stats = u->gn_stats + (size_t)op.gn_index * rc.batch * 16;
           if (rc.drop_scale && op.drop_off >= 0) {
