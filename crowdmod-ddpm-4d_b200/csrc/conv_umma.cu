@@ -263,7 +263,15 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
     p.ksplit = ksplit;
   }
   L->smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*colv*/;
-  L->grid = dim3((p.M + CONV_BM - 1) / CONV_BM, cout / bn, p.ksplit > 1 ? p.ksplit : p.nphase);
+  // scatter convs: 4 phases per CTA when that still leaves >= 2 CTAs per SM, else 2, else 1
+  p.ppc = 1;
+  if (p.nphase == 8 && getenv("CM_NO_PPC") == nullptr) {
+    const long tiles = (long)((p.M + CONV_BM - 1) / CONV_BM) * (cout / bn);
+    if (tiles * 2 >= 296) p.ppc = 4;
+    else if (tiles * 4 >= 296) p.ppc = 2;
+    if (const char* e = getenv("CM_PPC")) p.ppc = atoi(e);
+  }
+  L->grid = dim3((p.M + CONV_BM - 1) / CONV_BM, cout / bn, p.ksplit > 1 ? p.ksplit : p.nphase / p.ppc);
   L->flops = 2.0 * p.M * cout * (double)(k * k * k * cin + cin_extra) * p.nphase;
   return 0;
 }

@@ -59,6 +59,9 @@ struct ConvParams {
   // an output tile, each accumulating kb_per_split k-blocks; the partial tiles are reduced in a
   // fixed order through distributed shared memory (deterministic, no atomics).
   int ksplit, kb_per_split;
+  // scatter (UpSample) convs: one CTA walks ppc consecutive phases of its M tile (barriers / TMEM are
+  // set up once; measured: the per-CTA set-up was more than half of the 8-tap phase convs' time)
+  int ppc;
   int* err_flag;
   unsigned long long* trace;   // bring-up: per-k-block timestamps of CTA (0,0,0) (CM_DBG_TRACE)
   int dbg;               // bring-up knobs (CM_DBG_SKIP): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
@@ -88,14 +91,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
   uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + CONV_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
   float* colv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 192);   // [BN] per-column epilogue constants
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int phase = P.ksplit > 1 ? 0 : blockIdx.z;
+  const int ppc = P.ppc > 1 ? P.ppc : 1;
+  const int phase0 = P.ksplit > 1 ? 0 : blockIdx.z * ppc;
   const int split = P.ksplit > 1 ? blockIdx.z : 0;
 
   const int ncm = P.cin_main / BK;
@@ -105,7 +110,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   const int kb_hi = P.ksplit > 1 ? (kb_lo + P.kb_per_split < nkb ? kb_lo + P.kb_per_split : nkb) : nkb;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&P.amap[phase]);
+    for (int pi = 0; pi < ppc; ++pi) tma_prefetch_desc(&P.amap[phase0 + pi]);
     tma_prefetch_desc(&P.bmap);
     if (P.cin_extra) tma_prefetch_desc(&P.xmap);
   }
@@ -115,6 +120,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);        // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -137,12 +143,17 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       r -= z0 * P.oh * P.ow;
       const int p0 = r / P.ow;
       const int q0 = r - p0 * P.ow;
+      const uint32_t tx = ((P.dbg & 1) ? 0 : A_BYTES) + ((P.dbg & 2) ? 0 : terms * B_BYTES);
+      int s = 0, git = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int pi = 0; pi < ppc && alive; ++pi) {
+      const int phase = phase0 + pi;
       const int w0 = q0 * P.conv_stride + P.lower[phase][0];
       const int h0 = p0 * P.conv_stride + P.lower[phase][1];
       const int d0 = z0 * P.conv_stride + P.lower[phase][2];
       const int kbase = phase * P.kphase;
-      const uint32_t tx = ((P.dbg & 1) ? 0 : A_BYTES) + ((P.dbg & 2) ? 0 : terms * B_BYTES);
-      int s = 0, tw = 0, th = 0, td = 0, cc = 0;
+      int tw = 0, th = 0, td = 0, cc = 0;
       if (kb_lo > 0 && kb_lo < nkb_main) {          // resume the (tap, channel chunk) counters at kb_lo
         cc = kb_lo % ncm;
         const int tap = kb_lo / ncm;
@@ -150,9 +161,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         th = (tap / P.kw) % P.kh;
         td = tap / (P.kw * P.kh);
       }
-      uint32_t ph = 0;
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        if (kb - kb_lo >= S && !mbar_wait(&empty_bar[s], ph ^ 1, P.err_flag, 101)) break;   // first S slots: free
+      for (int kb = kb_lo; kb < kb_hi; ++kb, ++git) {
+        if (git >= S && !mbar_wait(&empty_bar[s], ph ^ 1, P.err_flag, 101)) { alive = false; break; }   // first S slots: free
         uint8_t* sa = smem + s * stage_bytes;
         if (elect_one()) {
           if (tr && kb < 120) P.trace[8 + kb * 4 + 0] = gtime_ns();
@@ -182,6 +192,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====
@@ -191,8 +202,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
       const uint32_t lo_stage = static_cast<uint32_t>(stage_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0, acc = 0;
+      bool alive = true;
+      for (int pi = 0; pi < ppc && alive; ++pi) {
+      if (pi > 0) {                                   // the epilogue must have drained the accumulator
+        if (!mbar_wait(tmem_empty, (pi - 1) & 1, P.err_flag, 104)) break;
+        tc_fence_after();
+        acc = 0;
+      }
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        if (!mbar_wait(&full_bar[s], ph, P.err_flag, 102)) break;
+        if (!mbar_wait(&full_bar[s], ph, P.err_flag, 102)) { alive = false; break; }
         tc_fence_after();
         if (elect_one()) {
           if (tr && kb < 120) P.trace[8 + kb * 4 + 2] = gtime_ns();
@@ -210,7 +228,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) umma_commit(tmem_full);       // accumulator complete
+      if (elect_one()) umma_commit(tmem_full);       // accumulator of this phase complete
+      __syncwarp();
+      }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -233,19 +253,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         colv[c] = v;
       }
     }
-    int b = 0;
+    int b = 0, sz = 0, sp = 0, sq = 0;
     size_t orow = 0;
     if (valid) {
       b = m / P.pps;
       if (P.scatter) {
         int r = m - b * P.pps;
-        const int z = r / (P.oh * P.ow);
-        r -= z * P.oh * P.ow;
-        const int p = r / P.ow;
-        const int q = r - p * P.ow;
-        const int pq = phase & 1, pp = (phase >> 1) & 1, pz = (phase >> 2) & 1;
-        orow = ((static_cast<size_t>(b) * (2 * P.od) + (2 * z + pz)) * (2 * P.oh) + (2 * p + pp)) *
-                   (2 * P.ow) + (2 * q + pq);
+        sz = r / (P.oh * P.ow);
+        r -= sz * P.oh * P.ow;
+        sp = r / P.ow;
+        sq = r - sp * P.ow;
       } else {
         orow = static_cast<size_t>(m);
       }
@@ -253,26 +270,26 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     const float* temb_row = nullptr;     // per-sample rows (training): added per element
     if (P.temb && !temb_uniform)
       temb_row = P.temb + static_cast<size_t>(b) * P.temb_bstride + n_tile * BN;
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // colv visible to the 4 epilogue warps
+
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int pi = 0; pi < ppc; ++pi) {
+    if (P.scatter && valid) {
+      const int phase = phase0 + pi;
+      const int pq = phase & 1, pp = (phase >> 1) & 1, pz = (phase >> 2) & 1;
+      orow = ((static_cast<size_t>(b) * (2 * P.od) + (2 * sz + pz)) * (2 * P.oh) + (2 * sp + pp)) *
+                 (2 * P.ow) + (2 * sq + pq);
+    }
     const float* rp = (P.resid && valid && P.ksplit <= 1) ? P.resid + orow * P.cout + n_tile * BN : nullptr;   // orow == m unless scattering
     float4 rnext[4];
-    if (rp) {
+    if (rp) {                      // first residual chunk in flight while the main loop finishes
 #pragma unroll
       for (int i = 0; i < 4; ++i) rnext[i] = *reinterpret_cast<const float4*>(rp + 4 * i);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // colv visible to the 4 epilogue warps
-
-    if (P.dbg & 16) {
-      if (lane == 0) {
-        while (!mbar_try_wait(tmem_full, 0)) __nanosleep(500);
-      }
-      __syncwarp();
-    } else {
-      mbar_wait(tmem_full, 0, P.err_flag, 103);
-    }
+    if (!mbar_wait(tmem_full, pi & 1, P.err_flag, 103)) break;
     tc_fence_after();
     if (tr && warp == 2 && lane == 0) P.trace[1] = gtime_ns();
 
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     if (P.ksplit > 1) {
       // split-K: raw partial accumulators -> this CTA's shared memory (the pipeline stages are idle:
       // every TMA landed and every MMA retired); reduced across the cluster after the barrier below
@@ -354,6 +371,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
           *reinterpret_cast<uint4*>(op + i) = u;
         }
       }
+    }
+    if (pi + 1 < ppc) {          // hand the accumulator back to the MMA warp for the next phase
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
     }
   }
 
