@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
 // =============================================================================================
 constexpr int GN2_T = 256;
 constexpr int GN2_MAX_SLICES = 32;
+constexpr int GN2_REC_SMEM = 32 * 1024;   // dynamic shared memory of the record-fed apply kernel
 
 struct Chan3 {
   float n, mean, m2;
@@ -457,22 +458,33 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   const bool from_rec = p.rec0.rec != nullptr;
   if (from_rec) {
     // statistics from the producing convs' records: channel c merges its units in unit order, then
-    // the 8 group threads merge their channels in channel order (fixed tree -> deterministic)
-    for (int c2 = tid; c2 < C; c2 += GN2_T) {
-      const bool s0 = c2 < p.c0;
-      const GnRec& r = s0 ? p.rec0 : p.rec1;
-      const int cs = s0 ? p.c0 : p.c1, cl = s0 ? c2 : c2 - p.c0;
-      const float4* rp = reinterpret_cast<const float4*>(r.rec) + ((size_t)b * r.units) * cs + cl;
-      Chan3 a{0.f, 0.f, 0.f};
+    // the 8 group threads merge their channels in channel order (fixed tree -> deterministic).
+    // The records of a source are staged through shared memory in one coalesced round trip per
+    // chunk (a per-thread serial walk over the units exposed one L2 latency per unit).
+    extern __shared__ float4 rstage[];                      // [units in chunk][channels of the source]
+    for (int src = 0; src < (p.c1 ? 2 : 1); ++src) {
+      const GnRec& r = src ? p.rec1 : p.rec0;
+      const int cs = src ? p.c1 : p.c0, cbase = src ? p.c0 : 0;
+      const float4* rp = reinterpret_cast<const float4*>(r.rec) + ((size_t)b * r.units) * cs;
       const float nk = (float)r.nvalid;
-#pragma unroll 4
-      for (int uidx = 0; uidx < r.units; ++uidx) {
-        const float4 v = rp[(size_t)uidx * cs];
-        const float d = v.y / nk;
-        a = chan_merge(a, Chan3{nk, v.x + d, fmaxf(v.z - v.y * d, 0.f)});
+      const int uchunk = GN2_REC_SMEM / (16 * cs);
+      for (int u0 = 0; u0 < r.units; u0 += uchunk) {
+        const int un = (r.units - u0) < uchunk ? (r.units - u0) : uchunk;
+        __syncthreads();
+        for (int i = tid; i < un * cs; i += GN2_T) rstage[i] = rp[(size_t)u0 * cs + i];
+        __syncthreads();
+        for (int cl = tid; cl < cs; cl += GN2_T) {
+          Chan3 a{0.f, 0.f, 0.f};
+          if (u0 > 0) a = Chan3{(float)u0 * nk, chst[cbase + cl][0], chst[cbase + cl][1]};
+          for (int uidx = 0; uidx < un; ++uidx) {
+            const float4 v = rstage[uidx * cs + cl];
+            const float d = v.y / nk;
+            a = chan_merge(a, Chan3{nk, v.x + d, fmaxf(v.z - v.y * d, 0.f)});
+          }
+          chst[cbase + cl][0] = a.mean;
+          chst[cbase + cl][1] = a.m2;
+        }
       }
-      chst[c2][0] = a.mean;
-      chst[c2][1] = a.m2;
     }
   } else {
     for (int i = tid; i < stat_slices * 24; i += GN2_T)     // all slice statistics in one round trip
@@ -674,7 +686,7 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* lau
     if (slices > max_slices) slices = max_slices;
     if (slices > GN2_MAX_SLICES) slices = GN2_MAX_SLICES;
     if (slices < 1) slices = 1;
-    return launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), 0, st, p, slices, 0,
+    return launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), GN2_REC_SMEM, st, p, slices, 0,
                       static_cast<const float*>(partial));
   }
   if (partial && !use_cluster && C / 4 <= GN2_T) {
