@@ -55,6 +55,7 @@ struct Op {
   int mode = 0, in = -1, extra = -1, w = -1, wx = -1, bias = -1, bias2 = -1, temb_off = -1,
       resid = -1, out = -1, cin = 0, cin_extra = 0, cout = 0, in_level = 0;
   size_t wpack_off = 0;   // element offset into the packed-weight buffer
+  int terms = 0;            // weight terms of THIS conv's forward (0 = cfg.weight_terms)
   ConvLaunch launch;
   PlaneLaunch plaunch;      // plane-tile kernel (conv_plane.cuh) when it covers the geometry
   // ATTN
@@ -95,6 +96,7 @@ struct cm_unet {
   // first conv on the tensor cores: the 3(+)-channel input is packed into a zero-padded 32-channel fp16
   // operand and run through the plane-tile kernel (falls back to first_conv_kernel when not covered)
   int first_in = -1;
+  int fullres_terms = 0;    // CROWDMOD_FULLRES_TERMS (0 = same as cfg.weight_terms)
   size_t first_wpack_off = 0;
   PlaneLaunch first_plane;
   // device state
@@ -240,6 +242,7 @@ int add_conv(cm_unet* u, const std::string& tag, int mode, int in, int extra, in
   u->g_elems += wgrad_g_elems(mode, op.cin, op.cin_extra, cout);
   op.colsum_off = u->colsum_per_sample;
   u->colsum_per_sample += cout;
+  if (mode == 0 && op.in_level == 0 && u->fullres_terms > 0) op.terms = u->fullres_terms;
   u->ops.push_back(op);
   return op.out;
 }
@@ -418,6 +421,13 @@ int build_plan(cm_unet* u) {
   return 0;
 }
 
+// Forward weight precision per conv.  Policy knob CROWDMOD_FULLRES_TERMS (default: cfg.weight_terms):
+// the full-resolution k3 s1 convs -- where the tensor pipe is bound by the number of MMA
+// instructions -- may run with single fp16 weights while every other layer keeps the hi+lo split.
+int fwd_terms(const cm_unet* u, const Op& op) {
+  return op.terms > 0 ? op.terms : u->cfg.weight_terms;
+}
+
 int check_params_bound(cm_unet* u) {
   for (auto& p : u->params)
     CM_CHECK(p.ptr != nullptr, "parameter '%s' not bound (cm_unet_set_param)", p.name.c_str());
@@ -480,7 +490,8 @@ int prepare_convs(cm_unet* u, int batch) {
     static const bool no_tc_first = getenv("CM_NO_PLANE") != nullptr || getenv("CM_FIRST_SIMT") != nullptr;
     if (!no_tc_first) {
       if (int rc = plane_prepare(&u->first_plane, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32, nullptr, 0,
-                                 u->wpack + u->first_wpack_off, u->cfg.base_channels, u->cfg.weight_terms))
+                                 u->wpack + u->first_wpack_off, u->cfg.base_channels,
+                                 u->fullres_terms > 0 ? u->fullres_terms : u->cfg.weight_terms))
         return rc;
       if (u->first_plane.ok) {
         u->first_plane.p.bias = u->params[u->p_first_b].ptr;
@@ -506,13 +517,13 @@ int prepare_convs(cm_unet* u, int batch) {
     const Tens& tin = u->tens[op.in];
     const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
     if (int rc = conv_prepare(&op.launch, op.mode, tin.p16, batch, li.D, li.H, li.W, op.cin, extra,
-                              op.cin_extra, u->wpack + op.wpack_off, op.cout, u->cfg.weight_terms))
+                              op.cin_extra, u->wpack + op.wpack_off, op.cout, fwd_terms(u, op)))
       return rc;
     op.plaunch.ok = false;
     static const bool no_plane = getenv("CM_NO_PLANE") != nullptr;
     if (op.mode == 0 && !no_plane) {
       if (int rc = plane_prepare(&op.plaunch, tin.p16, batch, li.D, li.H, li.W, op.cin, extra, op.cin_extra,
-                                 u->wpack + op.wpack_off, op.cout, u->cfg.weight_terms))
+                                 u->wpack + op.wpack_off, op.cout, fwd_terms(u, op)))
         return rc;
       if (op.plaunch.ok) {
         PlaneParams& q = op.plaunch.p;
@@ -1037,6 +1048,10 @@ int cm_unet_create(const cm_unet_config* cfg, cm_unet** out) {
   u->cfg = *cfg;
   if (u->cfg.table_steps <= 0) u->cfg.table_steps = 1000;
   if (u->cfg.weight_terms <= 0) u->cfg.weight_terms = 2;
+  if (const char* e = getenv("CROWDMOD_FULLRES_TERMS")) {
+    const int ft = atoi(e);
+    if (ft == 1 || ft == 2) u->fullres_terms = ft < u->cfg.weight_terms ? ft : 0;
+  }
   if (int e = build_plan(u.get())) return e;
   *out = u.release();
   return 0;
@@ -1112,12 +1127,13 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
     } else {
       const float* wx = op.wx >= 0 ? u->params[op.wx].ptr : nullptr;
       if (int e = pack_conv_weights(w, wx, dst, op.cout, op.cin, op.cin_extra, op.mode == 3 ? 1 : 27,
-                                    terms, 1, st))
+                                    fwd_terms(u, op), 1, st))
         return e;
     }
   }
   if (int e = pack_conv_weights_padded(u->params[u->p_first_w].ptr, u->wpack + u->first_wpack_off,
-                                       u->cfg.base_channels, u->cfg.in_channels, 32, terms, 1, st))
+                                       u->cfg.base_channels, u->cfg.in_channels, 32,
+                                       u->fullres_terms > 0 ? u->fullres_terms : terms, 1, st))
     return e;
   const int nb = (int)u->temb_couts.size();
   if (!u->d_wd) {
