@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
 // =============================================================================================
 constexpr int GN2_T = 256;
 constexpr int GN2_MAX_SLICES = 32;
-constexpr int GN2_REC_SMEM = 32 * 1024;   // dynamic shared memory of the record-fed apply kernel
+constexpr int GN3_V = 4;                  // float4 per sweeping thread per ring stage (stage = T*64 B <= 16 KB)
+constexpr int GN3_NS = 4;                 // ring depth: up to 64 KB of bulk copies in flight per CTA
+constexpr int GN3_SMEM = GN3_NS * GN2_T * GN3_V * 16;
+constexpr int GN3_CTAS_PER_SM = 3;
 
 struct Chan3 {
   float n, mean, m2;
@@ -369,11 +372,35 @@ __device__ __forceinline__ Chan3 chan_merge(const Chan3 a, const Chan3 b) {
   return r;
 }
 
+// Streaming skeleton shared by the statistics and the apply kernel: the CTA's pixel slice of one
+// sample is a contiguous byte range of each source, so one thread feeds a ring of shared-memory
+// stages with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) and the CTA consumes them.
+// Memory-level parallelism is then set by the ring (64 KB per CTA, 192 KB per SM) and not by how
+// many loads a thread can keep in registers (the register-batched version reached 20-40 % of HBM).
+struct GnRing {
+  float* ring;
+  uint64_t* bar;
+  const float* g0;     // first row of this CTA's slice in source 0 / 1
+  const float* g1;
+  int c0, c1, RS, stage_floats, rows, total;
+  __device__ __forceinline__ void issue(int s) const {          // one thread
+    const int slot = s % GN3_NS;
+    const int row0 = s * RS;
+    const int nr = (rows - row0) < RS ? (rows - row0) : RS;
+    float* dst = ring + (size_t)slot * stage_floats;
+    const uint32_t b0 = (uint32_t)nr * c0 * 4u, b1 = (uint32_t)nr * c1 * 4u;
+    mbar_expect_tx(&bar[slot], b0 + b1);
+    bulk_g2s(dst, g0 + (size_t)row0 * c0, b0, &bar[slot]);
+    if (c1) bulk_g2s(dst + (size_t)RS * c0, g1 + (size_t)row0 * c1, b1, &bar[slot]);
+  }
+};
+
 __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int slices, float* __restrict__ partial) {
   pdl_trigger();
-  pdl_wait();
+  extern __shared__ __align__(128) unsigned char gn_dyn[];
+  __shared__ uint64_t full_bar[GN3_NS];
   __shared__ float tri[GN2_T][3];
-  const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2, vpp = Q >> 3;
+  const int C = p.c0 + p.c1, Q = C >> 2, vpp = Q >> 3;
   // blockDim.x == GN2_T; the first T = floor(GN2_T/Q)*Q threads sweep the data (fixed channel quad)
   const int tid = threadIdx.x;
   const int T = (GN2_T / Q) * Q;
@@ -381,32 +408,53 @@ __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int 
   const int px0 = (int)(((long long)p.pixels * slice) / slices);
   const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
   const int c = (tid % Q) * 4;
-  const int rows_per_iter = T / Q;
+  const int rpi = T / Q;
+  GnRing rg;
+  rg.ring = reinterpret_cast<float*>(gn_dyn);
+  rg.bar = full_bar;
+  rg.c0 = p.c0; rg.c1 = p.c1;
+  rg.RS = rpi * GN3_V;
+  rg.stage_floats = T * GN3_V * 4;
+  rg.rows = px1 - px0;
+  rg.total = (rg.rows + rg.RS - 1) / rg.RS;
+  rg.g0 = p.src0 + ((size_t)b * p.pixels + px0) * p.c0;
+  rg.g1 = p.c1 ? p.src1 + ((size_t)b * p.pixels + px0) * p.c1 : nullptr;
+  if (tid == 0) {
+    for (int i = 0; i < GN3_NS; ++i) mbar_init(&full_bar[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0)
+    for (int s = 0; s < GN3_NS && s < rg.total; ++s) rg.issue(s);
   const bool from0 = c < p.c0;
-  const int src_ld = from0 ? p.c0 : p.c1;
-  const float* src = (from0 ? p.src0 + c : p.src1 + (c - p.c0)) + ((size_t)b * p.pixels) * src_ld;
+  const int ld = from0 ? p.c0 : p.c1;
+  const int soff = from0 ? c : rg.RS * p.c0 + (c - p.c0);
+  const int r = tid / Q;
   float s1 = 0.f, s2 = 0.f, k = 0.f, cnt = 0.f;
-  int px = px0 + tid / Q;
-  if (tid < T && px < px1) {
-    // batches of 8 independent 16-byte loads; the shift k is this thread's first value
-    float4 v[8];
-    bool first = true;
-    for (; px < px1; px += 8 * rows_per_iter) {
+  bool first = true;
+  for (int s = 0; s < rg.total; ++s) {
+    const int slot = s % GN3_NS;
+    mbar_wait(&full_bar[slot], (uint32_t)((s / GN3_NS) & 1), nullptr, 0);
+    const int nr = (rg.rows - s * rg.RS) < rg.RS ? (rg.rows - s * rg.RS) : rg.RS;
+    if (tid < T) {
+      const float* sb = rg.ring + (size_t)slot * rg.stage_floats + soff;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int pj = px + j * rows_per_iter;
-        if (pj < px1) v[j] = *reinterpret_cast<const float4*>(src + (size_t)pj * src_ld);
-      }
-      if (first) { k = v[0].x; first = false; }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (px + j * rows_per_iter < px1) {
-          const float dx = v[j].x - k, dy = v[j].y - k, dz = v[j].z - k, dw = v[j].w - k;
+      for (int j = 0; j < GN3_V; ++j) {
+        const int row = r + j * rpi;
+        if (row < nr) {
+          const float4 v = *reinterpret_cast<const float4*>(sb + row * ld);
+          if (first) { k = v.x; first = false; }
+          const float dx = v.x - k, dy = v.y - k, dz = v.z - k, dw = v.w - k;
           s1 += (dx + dy) + (dz + dw);
           s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
           cnt += 4.f;
         }
       }
+    }
+    if (s + GN3_NS < rg.total) {
+      __syncthreads();                                   // every thread is done with this slot
+      if (tid == 0) rg.issue(s + GN3_NS);
     }
   }
   {
@@ -422,8 +470,8 @@ __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int 
     const int members = (T / Q) * vpp;            // = T/8 <= 32
     Chan3 a{0.f, 0.f, 0.f};
     if (lane < members) {
-      const int r = lane / vpp, o = lane - r * vpp;
-      const int t = r * Q + warp * vpp + o;
+      const int rr = lane / vpp, o = lane - rr * vpp;
+      const int t = rr * Q + warp * vpp + o;
       a = Chan3{tri[t][0], tri[t][1], tri[t][2]};
     }
 #pragma unroll
@@ -447,27 +495,52 @@ __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int 
 __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int slices, int stat_slices,
                                                           const float* __restrict__ partial) {
   pdl_trigger();
-  pdl_wait();
+  extern __shared__ __align__(128) unsigned char gn_dyn[];
+  __shared__ uint64_t full_bar[GN3_NS];
   __shared__ float stat[2][8];
+  __shared__ float ptri[GN2_MAX_SLICES * 8 * 3];
+  __shared__ float chst[512][2];                            // per-channel (mean, M2) from records
   const int C = p.c0 + p.c1, cg_ch = C >> 3, Q = C >> 2;
   const int tid = threadIdx.x;
   const int T = (GN2_T / Q) * Q;
   const int b = blockIdx.y, slice = blockIdx.x;
-  __shared__ float ptri[GN2_MAX_SLICES * 8 * 3];
-  __shared__ float chst[512][2];                            // per-channel (mean, M2) from records
+  const int px0 = (int)(((long long)p.pixels * slice) / slices);
+  const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
+  const int rpi = T / Q;
+  GnRing rg;
+  rg.ring = reinterpret_cast<float*>(gn_dyn);
+  rg.bar = full_bar;
+  rg.c0 = p.c0; rg.c1 = p.c1;
+  rg.RS = rpi * GN3_V;
+  rg.stage_floats = T * GN3_V * 4;
+  rg.rows = px1 - px0;
+  rg.total = (rg.rows + rg.RS - 1) / rg.RS;
+  rg.g0 = p.src0 + ((size_t)b * p.pixels + px0) * p.c0;
+  rg.g1 = p.c1 ? p.src1 + ((size_t)b * p.pixels + px0) * p.c1 : nullptr;
+  if (tid == 0) {
+    for (int i = 0; i < GN3_NS; ++i) mbar_init(&full_bar[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  // the data stream starts before the statistics prologue; the last ring slot doubles as the
+  // staging buffer of the producers' records and joins the ring after the prologue
+  if (tid == 0)
+    for (int s = 0; s < GN3_NS - 1 && s < rg.total; ++s) rg.issue(s);
   const bool from_rec = p.rec0.rec != nullptr;
   if (from_rec) {
     // statistics from the producing convs' records: channel c merges its units in unit order, then
     // the 8 group threads merge their channels in channel order (fixed tree -> deterministic).
     // The records of a source are staged through shared memory in one coalesced round trip per
     // chunk (a per-thread serial walk over the units exposed one L2 latency per unit).
-    extern __shared__ float4 rstage[];                      // [units in chunk][channels of the source]
+    float4* rstage = reinterpret_cast<float4*>(rg.ring + (size_t)(GN3_NS - 1) * rg.stage_floats);
+    const int rcap = rg.stage_floats / 4;                   // float4 capacity of the slot
     for (int src = 0; src < (p.c1 ? 2 : 1); ++src) {
       const GnRec& r = src ? p.rec1 : p.rec0;
       const int cs = src ? p.c1 : p.c0, cbase = src ? p.c0 : 0;
       const float4* rp = reinterpret_cast<const float4*>(r.rec) + ((size_t)b * r.units) * cs;
       const float nk = (float)r.nvalid;
-      const int uchunk = GN2_REC_SMEM / (16 * cs);
+      const int uchunk = rcap / cs;
       for (int u0 = 0; u0 < r.units; u0 += uchunk) {
         const int un = (r.units - u0) < uchunk ? (r.units - u0) : uchunk;
         __syncthreads();
@@ -491,6 +564,10 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
       ptri[i] = partial[(size_t)b * GN2_MAX_SLICES * 24 + i];
   }
   __syncthreads();
+  if (tid == 0 && GN3_NS - 1 < rg.total) {
+    fence_proxy_async();                                    // generic writes to the slot -> bulk copy
+    rg.issue(GN3_NS - 1);
+  }
   if (tid < 8) {
     Chan3 a{0.f, 0.f, 0.f};
     if (from_rec) {
@@ -510,8 +587,6 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
     }
   }
   __syncthreads();
-  const int px0 = (int)(((long long)p.pixels * slice) / slices);
-  const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
   const int c = (tid % Q) * 4;
   const int g = c / cg_ch;
   const float mean = stat[0][g], rstd = stat[1][g];
@@ -521,41 +596,51 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
   const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
-  const int rows_per_iter = T / Q;
   const bool from0 = c < p.c0;
-  const int src_ld = from0 ? p.c0 : p.c1;
-  const size_t pix_base = (size_t)b * p.pixels;
-  const float* src = (from0 ? p.src0 + c : p.src1 + (c - p.c0)) + pix_base * src_ld;
-  __half* on = p.out_norm + pix_base * C + c;
-  __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
-  if (tid >= T) return;
-  for (int px = px0 + tid / Q; px < px1; px += 4 * rows_per_iter) {
-    float4 v[4];
+  const int ld = from0 ? p.c0 : p.c1;
+  const int soff = from0 ? c : rg.RS * p.c0 + (c - p.c0);
+  const int r = tid / Q;
+  const size_t out_base = ((size_t)b * p.pixels + px0) * C + c;
+  __half* on = p.out_norm + out_base;
+  __half* orw = p.out_raw ? p.out_raw + out_base : nullptr;
+  for (int s = 0; s < rg.total; ++s) {
+    const int slot = s % GN3_NS;
+    mbar_wait(&full_bar[slot], (uint32_t)((s / GN3_NS) & 1), nullptr, 0);
+    const int nr = (rg.rows - s * rg.RS) < rg.RS ? (rg.rows - s * rg.RS) : rg.RS;
+    if (tid < T) {
+      const float* sb = rg.ring + (size_t)slot * rg.stage_floats + soff;
+      float4 v[GN3_V];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pj = px + j * rows_per_iter;
-      if (pj < px1) v[j] = *reinterpret_cast<const float4*>(src + (size_t)pj * src_ld);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pj = px + j * rows_per_iter;
-      if (pj >= px1) break;
-      float y0 = fmaf(v[j].x, sc.x, sh.x), y1 = fmaf(v[j].y, sc.y, sh.y), y2 = fmaf(v[j].z, sc.z, sh.z),
-            y3 = fmaf(v[j].w, sc.w, sh.w);
-      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-      y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
-      const size_t o = (size_t)pj * C;
-      __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(on + o) = u;
-      if (orw) {
-        __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
-        u.x = *reinterpret_cast<uint32_t*>(&r0);
-        u.y = *reinterpret_cast<uint32_t*>(&r1);
-        *reinterpret_cast<uint2*>(orw + o) = u;
+      for (int j = 0; j < GN3_V; ++j) {
+        const int row = r + j * rpi;
+        if (row < nr) v[j] = *reinterpret_cast<const float4*>(sb + row * ld);
       }
+#pragma unroll
+      for (int j = 0; j < GN3_V; ++j) {
+        const int row = r + j * rpi;
+        if (row < nr) {
+          float y0 = fmaf(v[j].x, sc.x, sh.x), y1 = fmaf(v[j].y, sc.y, sh.y), y2 = fmaf(v[j].z, sc.z, sh.z),
+                y3 = fmaf(v[j].w, sc.w, sh.w);
+          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+          y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
+          const size_t o = (size_t)(s * rg.RS + row) * C;
+          __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(on + o) = u;
+          if (orw) {
+            __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
+            u.x = *reinterpret_cast<uint32_t*>(&r0);
+            u.y = *reinterpret_cast<uint32_t*>(&r1);
+            *reinterpret_cast<uint2*>(orw + o) = u;
+          }
+        }
+      }
+    }
+    if (s + GN3_NS < rg.total) {
+      __syncthreads();                                   // every thread is done with this slot
+      if (tid == 0) rg.issue(s + GN3_NS);
     }
   }
 }
@@ -681,12 +766,12 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* lau
     // statistics come from the producing convs: one streaming apply kernel, no statistics pass
     const int Q = C / 4;
     const long nvec = (long)p.pixels * Q;
-    int slices = (148 * 4) / p.B;
+    int slices = (148 * GN3_CTAS_PER_SM) / p.B;
     const int max_slices = (int)((nvec + 4 * GN2_T - 1) / (4 * GN2_T));
     if (slices > max_slices) slices = max_slices;
     if (slices > GN2_MAX_SLICES) slices = GN2_MAX_SLICES;
     if (slices < 1) slices = 1;
-    return launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), GN2_REC_SMEM, st, p, slices, 0,
+    return launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), GN3_SMEM, st, p, slices, 0,
                       static_cast<const float*>(partial));
   }
   if (partial && !use_cluster && C / 4 <= GN2_T) {
@@ -705,13 +790,13 @@ int gn_silu_enqueue(const GnParams& p, float* partial, cudaStream_t st, int* lau
       }
     }
     // slices: one wave of <= 4 CTAs per SM over the batch, >= 4 vectors per thread
-    int slices = (148 * 4) / p.B;
+    int slices = (148 * GN3_CTAS_PER_SM) / p.B;
     const int max_slices = (int)((nvec + 4 * GN2_T - 1) / (4 * GN2_T));
     if (slices > max_slices) slices = max_slices;
     if (slices > GN2_MAX_SLICES) slices = GN2_MAX_SLICES;
     if (slices < 1) slices = 1;
-    if (int e = launch_pdl(gn_stats2_kernel, dim3(slices, p.B), dim3(GN2_T), 0, st, p, slices, partial)) return e;
-    if (int e = launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), 0, st, p, slices, slices,
+    if (int e = launch_pdl(gn_stats2_kernel, dim3(slices, p.B), dim3(GN2_T), GN3_SMEM, st, p, slices, partial)) return e;
+    if (int e = launch_pdl(gn_apply2_kernel, dim3(slices, p.B), dim3(GN2_T), GN3_SMEM, st, p, slices, slices,
                            static_cast<const float*>(partial)))
       return e;
     if (launches) *launches = 2;
@@ -877,7 +962,10 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
   __syncthreads();
   const int F = p.L - p.P;
   const size_t total = (size_t)p.B * p.H * p.W * F;
-  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  // grid-stride over groups of 256 lanes (= 64 pixels): the weights are staged once per CTA and the
+  // grid is sized to ONE resident wave (1296 CTAs on 1184 slots ran as two waves)
+  for (size_t gbase = blockIdx.x * (size_t)blockDim.x; gbase < total * 4; gbase += (size_t)gridDim.x * blockDim.x) {
+  const size_t gid = gbase + threadIdx.x;
   const size_t pix = gid >> 2;
   const int sub = (int)(gid & 3);
   const bool active = pix < total;
@@ -929,7 +1017,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
     acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
     acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
   }
-  if (!active || sub != 0) return;
+  if (!active || sub != 0) continue;
 
   const size_t plane = (size_t)p.H * p.W * F;                       // elements per (b, c)
   const size_t e0 = ((size_t)b * COUT) * plane + ((size_t)h * p.W + wc) * F + f;
@@ -940,7 +1028,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
 #pragma unroll
     for (int co = 0; co < COUT; ++co) p.eps_out[e0 + co * plane] = eps[co];
   }
-  if (!p.x) return;
+  if (!p.x) continue;
 
   const int step = *p.step_dev;
   const float* cf = p.coef + (size_t)step * 8;
@@ -983,13 +1071,15 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
     p.x[e] = xn;
     if (p.history) p.history[(size_t)(step + 1) * nelem + e] = xn;
   }
+  }
 }
 
 int final_conv_enqueue(const FinalParams& p, cudaStream_t st) {
   CM_CHECK(p.cout >= 1 && p.cout <= 4, "final conv supports 1..4 output channels (got %d)", p.cout);
   CM_CHECK(p.cin % 32 == 0, "final conv cin must be a multiple of 32");
   const size_t total = (size_t)p.B * p.H * p.W * (p.L - p.P) * 4;
-  const int blocks = (int)((total + 255) / 256);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;          // one resident wave; the kernel grid-strides
   const size_t smem = (size_t)27 * p.cin * p.cout * sizeof(float);
 #define CM_FINAL(CO)                                                                           \
   case CO: {                                                                                   \
@@ -1274,6 +1364,8 @@ int kernels_init() {
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CM_CUDA(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN3_SMEM));
+  CM_CUDA(cudaFuncSetAttribute(gn_apply2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN3_SMEM));
   if (int rc = attn_init()) return rc;
   if (int rc = conv_init()) return rc;
   done = true;
