@@ -161,7 +161,6 @@ int cast_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t st) {
 // group, gamma, beta) and consecutive threads touch consecutive 16 bytes.
 // =============================================================================================
 constexpr int GN_CACHE = 8;          // float4 cached per thread
-constexpr int GN_MAX_CHUNKS = 64;
 
 struct GnGeom {
   int Q, vpp, cg, C, T, chunks;
@@ -353,9 +352,22 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
 constexpr int GN2_T = 256;
 constexpr int GN2_MAX_SLICES = 32;
 constexpr int GN3_V = 4;                  // float4 per sweeping thread per ring stage (stage = T*64 B <= 16 KB)
-constexpr int GN3_NS = 4;                 // ring depth: up to 64 KB of bulk copies in flight per CTA
+constexpr int GN3_NS = 3;                 // ring depth: up to 48 KB of bulk copies in flight per CTA
 constexpr int GN3_SMEM = GN3_NS * GN2_T * GN3_V * 16;
-constexpr int GN3_CTAS_PER_SM = 3;
+constexpr int GN3_CTAS_PER_SM = 4;
+
+// slice boundaries of a sample's pixel range (32-bit: pixels * slices < 2^31 for every supported grid)
+__device__ __forceinline__ int gn2_px(int pixels, int slice, int slices) {
+  return (int)(((unsigned)pixels * (unsigned)slice) / (unsigned)slices);
+}
+// SiLU from the pre-scaled exponent argument z = -y*log2(e): y / (1 + 2^z); two MUFU ops, no range fix-ups
+// (2^z overflow -> rcp(inf) = 0 -> y*0 = -0, underflow -> y)
+__device__ __forceinline__ float silu_ex2(float y, float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return y * r;
+}
 
 struct Chan3 {
   float n, mean, m2;
@@ -405,9 +417,9 @@ __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int 
   const int tid = threadIdx.x;
   const int T = (GN2_T / Q) * Q;
   const int b = blockIdx.y, slice = blockIdx.x;
-  const int px0 = (int)(((long long)p.pixels * slice) / slices);
-  const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
-  const int c = (tid % Q) * 4;
+  const int px0 = gn2_px(p.pixels, slice, slices), px1 = gn2_px(p.pixels, slice + 1, slices);
+  const int r = (int)((unsigned)tid / (unsigned)Q);
+  const int c = (tid - r * Q) * 4;
   const int rpi = T / Q;
   GnRing rg;
   rg.ring = reinterpret_cast<float*>(gn_dyn);
@@ -430,7 +442,6 @@ __global__ void __launch_bounds__(GN2_T) gn_stats2_kernel(const GnParams p, int 
   const bool from0 = c < p.c0;
   const int ld = from0 ? p.c0 : p.c1;
   const int soff = from0 ? c : rg.RS * p.c0 + (c - p.c0);
-  const int r = tid / Q;
   float s1 = 0.f, s2 = 0.f, k = 0.f, cnt = 0.f;
   bool first = true;
   for (int s = 0; s < rg.total; ++s) {
@@ -504,8 +515,7 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   const int tid = threadIdx.x;
   const int T = (GN2_T / Q) * Q;
   const int b = blockIdx.y, slice = blockIdx.x;
-  const int px0 = (int)(((long long)p.pixels * slice) / slices);
-  const int px1 = (int)(((long long)p.pixels * (slice + 1)) / slices);
+  const int px0 = gn2_px(p.pixels, slice, slices), px1 = gn2_px(p.pixels, slice + 1, slices);
   const int rpi = T / Q;
   GnRing rg;
   rg.ring = reinterpret_cast<float*>(gn_dyn);
@@ -527,6 +537,12 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   // staging buffer of the producers' records and joins the ring after the prologue
   if (tid == 0)
     for (int s = 0; s < GN3_NS - 1 && s < rg.total; ++s) rg.issue(s);
+  float4 gb[2];
+  {
+    const int cq = (tid - (int)((unsigned)tid / (unsigned)Q) * Q) * 4;
+    gb[0] = *reinterpret_cast<const float4*>(p.gamma + cq);
+    gb[1] = *reinterpret_cast<const float4*>(p.beta + cq);
+  }
   const bool from_rec = p.rec0.rec != nullptr;
   if (from_rec) {
     // statistics from the producing convs' records: channel c merges its units in unit order, then
@@ -587,53 +603,63 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
     }
   }
   __syncthreads();
-  const int c = (tid % Q) * 4;
-  const int g = c / cg_ch;
+  const int r = (int)((unsigned)tid / (unsigned)Q);
+  const int c = (tid - r * Q) * 4;
+  const int g = (int)((unsigned)c / (unsigned)cg_ch);
   const float mean = stat[0][g], rstd = stat[1][g];
-  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
-  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  const float4 ga = gb[0], be = gb[1];                      // fetched before the prologue
+  const bool drop = p.drop_scale != nullptr;
   float4 ds = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
+  if (drop) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
   const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  // exponent argument of the SiLU as its own affine map of the input (off the y dependency chain)
+  constexpr float NL2E = -1.4426950408889634f;
+  const float4 zc = make_float4(sc.x * NL2E, sc.y * NL2E, sc.z * NL2E, sc.w * NL2E);
+  const float4 zh = make_float4(sh.x * NL2E, sh.y * NL2E, sh.z * NL2E, sh.w * NL2E);
   const bool from0 = c < p.c0;
   const int ld = from0 ? p.c0 : p.c1;
   const int soff = from0 ? c : rg.RS * p.c0 + (c - p.c0);
-  const int r = tid / Q;
   const size_t out_base = ((size_t)b * p.pixels + px0) * C + c;
   __half* on = p.out_norm + out_base;
   __half* orw = p.out_raw ? p.out_raw + out_base : nullptr;
+  const bool silu = p.silu != 0;
+  const int ostep = rpi * C;                                // output elements between a thread's rows
   for (int s = 0; s < rg.total; ++s) {
     const int slot = s % GN3_NS;
     mbar_wait(&full_bar[slot], (uint32_t)((s / GN3_NS) & 1), nullptr, 0);
     const int nr = (rg.rows - s * rg.RS) < rg.RS ? (rg.rows - s * rg.RS) : rg.RS;
     if (tid < T) {
-      const float* sb = rg.ring + (size_t)slot * rg.stage_floats + soff;
+      const float* sb = rg.ring + (size_t)slot * rg.stage_floats + soff + r * ld;
+      const int sstep = rpi * ld;
       float4 v[GN3_V];
 #pragma unroll
-      for (int j = 0; j < GN3_V; ++j) {
-        const int row = r + j * rpi;
-        if (row < nr) v[j] = *reinterpret_cast<const float4*>(sb + row * ld);
-      }
+      for (int j = 0; j < GN3_V; ++j)
+        if (r + j * rpi < nr) v[j] = *reinterpret_cast<const float4*>(sb + j * sstep);
+      __half* o = on + (size_t)(s * rg.RS + r) * C;
+      __half* orr = orw ? orw + (size_t)(s * rg.RS + r) * C : nullptr;
 #pragma unroll
       for (int j = 0; j < GN3_V; ++j) {
-        const int row = r + j * rpi;
-        if (row < nr) {
+        if (r + j * rpi < nr) {
           float y0 = fmaf(v[j].x, sc.x, sh.x), y1 = fmaf(v[j].y, sc.y, sh.y), y2 = fmaf(v[j].z, sc.z, sh.z),
                 y3 = fmaf(v[j].w, sc.w, sh.w);
-          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-          y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
-          const size_t o = (size_t)(s * rg.RS + row) * C;
+          if (silu) {
+            y0 = silu_ex2(y0, fmaf(v[j].x, zc.x, zh.x));
+            y1 = silu_ex2(y1, fmaf(v[j].y, zc.y, zh.y));
+            y2 = silu_ex2(y2, fmaf(v[j].z, zc.z, zh.z));
+            y3 = silu_ex2(y3, fmaf(v[j].w, zc.w, zh.w));
+          }
+          if (drop) { y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w; }
           __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
           uint2 u;
           u.x = *reinterpret_cast<uint32_t*>(&h0);
           u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(on + o) = u;
-          if (orw) {
+          *reinterpret_cast<uint2*>(o + j * ostep) = u;
+          if (orr) {
             __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
             u.x = *reinterpret_cast<uint32_t*>(&r0);
             u.y = *reinterpret_cast<uint32_t*>(&r1);
-            *reinterpret_cast<uint2*>(orw + o) = u;
+            *reinterpret_cast<uint2*>(orr + j * ostep) = u;
           }
         }
       }
@@ -728,6 +754,10 @@ __global__ void __launch_bounds__(1024) gn_small_kernel(const GnParams p) {
   if (p.drop_scale) ds = *reinterpret_cast<const float4*>(p.drop_scale + (size_t)b * p.drop_ld + c);
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
   const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  constexpr float NL2E = -1.4426950408889634f;
+  const float4 zc = make_float4(sc.x * NL2E, sc.y * NL2E, sc.z * NL2E, sc.w * NL2E);
+  const float4 zh = make_float4(sh.x * NL2E, sh.y * NL2E, sh.z * NL2E, sh.w * NL2E);
+  const bool silu = p.silu != 0, drop = p.drop_scale != nullptr;
   __half* on = p.out_norm + pix_base * C + c;
   __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
 #pragma unroll
@@ -736,8 +766,13 @@ __global__ void __launch_bounds__(1024) gn_small_kernel(const GnParams p) {
     if (pj >= p.pixels) break;
     float y0 = fmaf(v[j].x, sc.x, sh.x), y1 = fmaf(v[j].y, sc.y, sh.y), y2 = fmaf(v[j].z, sc.z, sh.z),
           y3 = fmaf(v[j].w, sc.w, sh.w);
-    if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-    y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
+    if (silu) {
+      y0 = silu_ex2(y0, fmaf(v[j].x, zc.x, zh.x));
+      y1 = silu_ex2(y1, fmaf(v[j].y, zc.y, zh.y));
+      y2 = silu_ex2(y2, fmaf(v[j].z, zc.z, zh.z));
+      y3 = silu_ex2(y3, fmaf(v[j].w, zc.w, zh.w));
+    }
+    if (drop) { y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w; }
     const size_t o = (size_t)pj * C;
     __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
     uint2 u;
