@@ -1374,6 +1374,355 @@ int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int he
   return attn_dispatch<64>(qkv, ctx, B, S, C, heads, st);
 }
 
+// =============================================================================================
+// Fused AttentionBlock for the sampling path (layers.py:5-18): GroupNorm(8) -> in_proj -> softmax(QK^T/sqrt(dh))V
+// -> out_proj -> + x, ONE launch, one CTA per sample (the block is 0.55 GFLOP for 64 samples: four
+// dependent launches were pure latency).  C = 128, 4 heads, dh = 32, S <= 128 tokens.
+//   phase 0  x [S][C] fp32 -> exact two-pass group statistics -> h = GN(x) as fp16 in shared memory
+//   phase 1  qkv = h W_in^T + b_in   (mma.sync m16n8k16, A from smem, hi+lo fp16 weights straight from L2)
+//            -> Q/sqrt(dh) and K as hi+lo fp16 pairs, V^T as fp16, all in shared memory
+//   phase 2  per (head, 16-query tile) warp: fp32-accurate scores (3 MMAs), softmax, P V -> ctx fp16 (smem)
+//   phase 3  out = ctx W_o^T + b_o + x -> fp32 (and fp16) global
+// Same operand precisions as the unfused path (fp16 activations, hi+lo weights, hi+lo Q/K).
+// =============================================================================================
+constexpr int AB_C = 128, AB_HEADS = 4, AB_DH = 32, AB_THREADS = 512, AB_WARPS = 16;
+constexpr int AB_LD = AB_C + 8;           // smem row stride (halfs) of h / ctx / Q / K
+
+struct AttnBlockParams {
+  const float* x;          // [B][S][C] fp32 (block input = residual)
+  const float* gamma;
+  const float* beta;
+  const __half* w_in;      // packed [2*3C][C]: rows 0..3C-1 hi, 3C..6C-1 lo
+  const float* b_in;       // [3C]
+  const __half* w_out;     // packed [2*C][C]
+  const float* b_out;      // [C]
+  float* out32;            // optional [B][S][C]
+  __half* out16;           // optional
+  int S;
+  float eps;
+};
+
+// acc[MT][NTW] (+)= A[smem, rows mt*16.., K = AB_C] . W[n][k]^T with hi and lo weight rows
+template <int MT, int NTW>
+__device__ __forceinline__ void ab_gemm(const __half* __restrict__ A, int m_base, const __half* __restrict__ Whi,
+                                        const __half* __restrict__ Wlo, int n0, float (&acc)[MT][NTW][4], int g,
+                                        int t) {
+  uint32_t bh[2][NTW][2], bl[2][NTW][2];
+  auto load_b = [&](int kt, int buf) {
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      const size_t o = (size_t)(n0 + nt * 8 + g) * AB_C + kt * 16 + 2 * t;
+      bh[buf][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(Whi + o));
+      bh[buf][nt][1] = __ldg(reinterpret_cast<const uint32_t*>(Whi + o + 8));
+      bl[buf][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(Wlo + o));
+      bl[buf][nt][1] = __ldg(reinterpret_cast<const uint32_t*>(Wlo + o + 8));
+    }
+  };
+  load_b(0, 0);
+#pragma unroll
+  for (int kt = 0; kt < AB_C / 16; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < AB_C / 16) load_b(kt + 1, buf ^ 1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const __half* ar = A + (size_t)(m_base + mt * 16 + g) * AB_LD + kt * 16 + 2 * t;
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(ar);
+      a[1] = *reinterpret_cast<const uint32_t*>(ar + 8 * AB_LD);
+      a[2] = *reinterpret_cast<const uint32_t*>(ar + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(ar + 8 * AB_LD + 8);
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        mma_16816(acc[mt][nt], a, bl[buf][nt][0], bl[buf][nt][1]);
+        mma_16816(acc[mt][nt], a, bh[buf][nt][0], bh[buf][nt][1]);
+      }
+    }
+  }
+}
+
+template <int NT>   // NT = padded tokens / 8 (even): SP = 16, 32, ... 128
+__global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const AttnBlockParams p) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int SP = NT * 8, MTILES = SP / 16;
+  constexpr int VLD = SP + 8;
+  extern __shared__ __align__(16) uint8_t ab_raw[];
+  __half* Hs = reinterpret_cast<__half*>(ab_raw);       // [SP][AB_LD]  h, later ctx
+  __half* Qh = Hs + SP * AB_LD;
+  __half* Ql = Qh + SP * AB_LD;
+  __half* Kh = Ql + SP * AB_LD;
+  __half* Kl = Kh + SP * AB_LD;
+  __half* Vt = Kl + SP * AB_LD;                          // [AB_C][VLD]
+  __shared__ float red[AB_WARPS][8];
+  __shared__ float gstat[2][8];
+  const int S = p.S;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float* xb = p.x + (size_t)b * S * AB_C;
+
+  // ---- phase 0: GroupNorm.  warp = row (mod 16), lane = float4 column; group = lane / 4 (16 channels) ----
+  constexpr int RPT = (SP + AB_WARPS - 1) / AB_WARPS;    // rows per warp
+  float4 xv[RPT];
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int row = warp + j * AB_WARPS;
+    xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < S) xv[j] = *reinterpret_cast<const float4*>(xb + (size_t)row * AB_C + lane * 4);
+    s1 += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
+  }
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  if ((lane & 3) == 0) red[warp][lane >> 2] = s1;
+  __syncthreads();
+  const float cnt = (float)S * 16.f;
+  if (tid < 8) {
+    float a = 0.f;
+    for (int w = 0; w < AB_WARPS; ++w) a += red[w][tid];
+    gstat[0][tid] = a / cnt;
+  }
+  __syncthreads();
+  const float mean = gstat[0][lane >> 2];
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    if (warp + j * AB_WARPS < S) {
+      const float dx = xv[j].x - mean, dy = xv[j].y - mean, dz = xv[j].z - mean, dw = xv[j].w - mean;
+      s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  if ((lane & 3) == 0) red[warp][lane >> 2] = s2;     // (red was fully consumed before the second barrier)
+  __syncthreads();
+  if (tid < 8) {
+    float a = 0.f;
+    for (int w = 0; w < AB_WARPS; ++w) a += red[w][tid];
+    gstat[1][tid] = 1.0f / sqrtf(a / cnt + p.eps);
+  }
+  __syncthreads();
+  {
+    const float rstd = gstat[1][lane >> 2];
+    const float4 ga = *reinterpret_cast<const float4*>(p.gamma + lane * 4);
+    const float4 be = *reinterpret_cast<const float4*>(p.beta + lane * 4);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int row = warp + j * AB_WARPS;
+      if (row >= SP) continue;
+      uint2 u = make_uint2(0u, 0u);                     // padded rows are zero (finite q/k/v = bias)
+      if (row < S) {
+        u.x = pack_h2((xv[j].x - mean) * rstd * ga.x + be.x, (xv[j].y - mean) * rstd * ga.y + be.y);
+        u.y = pack_h2((xv[j].z - mean) * rstd * ga.z + be.z, (xv[j].w - mean) * rstd * ga.w + be.w);
+      }
+      *reinterpret_cast<uint2*>(Hs + (size_t)row * AB_LD + lane * 4) = u;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: qkv = h W_in^T + b_in.  Warp w owns output columns [24w, 24w+24) (3 n8 tiles) ----
+  {
+    constexpr int MC = MTILES < 4 ? MTILES : 4;          // M tiles per pass (accumulator registers)
+    const float qscale = rsqrtf((float)AB_DH);
+    const int n0 = warp * 24;
+    for (int m0 = 0; m0 < MTILES; m0 += MC) {
+      float acc[MC][3][4];
+#pragma unroll
+      for (int mt = 0; mt < MC; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      ab_gemm<MC, 3>(Hs, m0 * 16, p.w_in, p.w_in + (size_t)3 * AB_C * AB_C, n0, acc, g, t);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const int n = n0 + nt * 8 + 2 * t;               // this thread's two columns (n, n + 1)
+        const float2 bi = *reinterpret_cast<const float2*>(p.b_in + n);
+        const int which = n / AB_C, c = n - which * AB_C;   // 0 q, 1 k, 2 v (uniform per n8 tile)
+#pragma unroll
+        for (int mt = 0; mt < MC; ++mt) {
+          if (m0 + mt >= MTILES) continue;
+          const int r0 = (m0 + mt) * 16 + g, r1 = r0 + 8;
+          const float v00 = acc[mt][nt][0] + bi.x, v01 = acc[mt][nt][1] + bi.y;
+          const float v10 = acc[mt][nt][2] + bi.x, v11 = acc[mt][nt][3] + bi.y;
+          if (which == 2) {
+            Vt[(size_t)c * VLD + r0] = __float2half_rn(v00);
+            Vt[(size_t)(c + 1) * VLD + r0] = __float2half_rn(v01);
+            Vt[(size_t)c * VLD + r1] = __float2half_rn(v10);
+            Vt[(size_t)(c + 1) * VLD + r1] = __float2half_rn(v11);
+          } else {
+            const float sc = which == 0 ? qscale : 1.0f;
+            __half* hi = which == 0 ? Qh : Kh;
+            __half* lo = which == 0 ? Ql : Kl;
+            uint32_t h, l;
+            split_h2(v00 * sc, v01 * sc, &h, &l);
+            *reinterpret_cast<uint32_t*>(hi + (size_t)r0 * AB_LD + c) = h;
+            *reinterpret_cast<uint32_t*>(lo + (size_t)r0 * AB_LD + c) = l;
+            split_h2(v10 * sc, v11 * sc, &h, &l);
+            *reinterpret_cast<uint32_t*>(hi + (size_t)r1 * AB_LD + c) = h;
+            *reinterpret_cast<uint32_t*>(lo + (size_t)r1 * AB_LD + c) = l;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();     // q/k/v complete; h is dead -> Hs becomes ctx
+
+  // ---- phase 2: attention core, one (head, query tile) per warp pass ----
+  for (int pr = warp; pr < AB_HEADS * MTILES; pr += AB_WARPS) {
+    const int hd = pr % AB_HEADS, mt = pr / AB_HEADS;
+    const int i0 = mt * 16 + g, i1 = i0 + 8;
+    const int cb = hd * AB_DH;
+    uint32_t qh[AB_DH / 16][4], ql[AB_DH / 16][4];
+#pragma unroll
+    for (int kt = 0; kt < AB_DH / 16; ++kt) {
+      const int o0 = i0 * AB_LD + cb + kt * 16 + 2 * t, o1 = i1 * AB_LD + cb + kt * 16 + 2 * t;
+      qh[kt][0] = *reinterpret_cast<const uint32_t*>(Qh + o0);
+      qh[kt][1] = *reinterpret_cast<const uint32_t*>(Qh + o1);
+      qh[kt][2] = *reinterpret_cast<const uint32_t*>(Qh + o0 + 8);
+      qh[kt][3] = *reinterpret_cast<const uint32_t*>(Qh + o1 + 8);
+      ql[kt][0] = *reinterpret_cast<const uint32_t*>(Ql + o0);
+      ql[kt][1] = *reinterpret_cast<const uint32_t*>(Ql + o1);
+      ql[kt][2] = *reinterpret_cast<const uint32_t*>(Ql + o0 + 8);
+      ql[kt][3] = *reinterpret_cast<const uint32_t*>(Ql + o1 + 8);
+    }
+    float sc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      const int j = nt * 8 + g;
+#pragma unroll
+      for (int kt = 0; kt < AB_DH / 16; ++kt) {
+        const int o = j * AB_LD + cb + kt * 16 + 2 * t;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(Kh + o);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(Kh + o + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(Kl + o);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(Kl + o + 8);
+        mma_16816(sc[nt], ql[kt], bh0, bh1);
+        mma_16816(sc[nt], qh[kt], bl0, bl1);
+        mma_16816(sc[nt], qh[kt], bh0, bh1);
+      }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int j = nt * 8 + 2 * t;
+      if (j >= S) sc[nt][0] = sc[nt][2] = -INFINITY;
+      if (j + 1 >= S) sc[nt][1] = sc[nt][3] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = expf(sc[nt][0] - m0);
+      sc[nt][1] = expf(sc[nt][1] - m0);
+      sc[nt][2] = expf(sc[nt][2] - m1);
+      sc[nt][3] = expf(sc[nt][3] - m1);
+      l0 += sc[nt][0] + sc[nt][1];
+      l1 += sc[nt][2] + sc[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    float oc[AB_DH / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < AB_DH / 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(sc[2 * kt][0] * inv0, sc[2 * kt][1] * inv0);
+      pa[1] = pack_h2(sc[2 * kt][2] * inv1, sc[2 * kt][3] * inv1);
+      pa[2] = pack_h2(sc[2 * kt + 1][0] * inv0, sc[2 * kt + 1][1] * inv0);
+      pa[3] = pack_h2(sc[2 * kt + 1][2] * inv1, sc[2 * kt + 1][3] * inv1);
+#pragma unroll
+      for (int dt = 0; dt < AB_DH / 8; ++dt) {
+        const int d = cb + dt * 8 + g;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Vt + (size_t)d * VLD + kt * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vt + (size_t)d * VLD + kt * 16 + 8 + 2 * t);
+        mma_16816(oc[dt], pa, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int dt = 0; dt < AB_DH / 8; ++dt) {
+      const int d = cb + dt * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(Hs + (size_t)i0 * AB_LD + d) = pack_h2(oc[dt][0], oc[dt][1]);
+      *reinterpret_cast<uint32_t*>(Hs + (size_t)i1 * AB_LD + d) = pack_h2(oc[dt][2], oc[dt][3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: out = ctx W_o^T + b_o + x.  Warp w owns output columns [8w, 8w+8) ----
+  {
+    constexpr int MC = MTILES < 4 ? MTILES : 4;
+    const int n0 = warp * 8;
+    const int n = n0 + 2 * t;
+    const float2 bo = *reinterpret_cast<const float2*>(p.b_out + n);
+    for (int m0 = 0; m0 < MTILES; m0 += MC) {
+      float acc[MC][1][4];
+#pragma unroll
+      for (int mt = 0; mt < MC; ++mt) acc[mt][0][0] = acc[mt][0][1] = acc[mt][0][2] = acc[mt][0][3] = 0.f;
+      ab_gemm<MC, 1>(Hs, m0 * 16, p.w_out, p.w_out + (size_t)AB_C * AB_C, n0, acc, g, t);
+#pragma unroll
+      for (int mt = 0; mt < MC; ++mt) {
+        if (m0 + mt >= MTILES) continue;
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int r = (m0 + mt) * 16 + g + hrow * 8;
+          if (r >= S) continue;
+          const size_t o = ((size_t)b * S + r) * AB_C + n;
+          const float2 xr = *reinterpret_cast<const float2*>(p.x + o);
+          const float y0 = acc[mt][0][2 * hrow] + bo.x + xr.x, y1 = acc[mt][0][2 * hrow + 1] + bo.y + xr.y;
+          if (p.out32) *reinterpret_cast<float2*>(p.out32 + o) = make_float2(y0, y1);
+          if (p.out16) *reinterpret_cast<uint32_t*>(p.out16 + o) = pack_h2(y0, y1);
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+static size_t attn_block_smem() {
+  constexpr int SP = NT * 8;
+  return ((size_t)5 * SP * AB_LD + (size_t)AB_C * (SP + 8)) * sizeof(__half);
+}
+template <int NT>
+static int attn_block_launch(const AttnBlockParams& p, int B, cudaStream_t st) {
+  return launch_pdl(attn_block_kernel<NT>, dim3(B), dim3(AB_THREADS), attn_block_smem<NT>(), st, p);
+}
+
+bool attn_block_supported(int S, int C, int heads) {
+  return C == AB_C && heads == AB_HEADS && S >= 1 && S <= 128;
+}
+
+int attn_block_enqueue(const float* x, const float* gamma, const float* beta, const __half* w_in, const float* b_in,
+                       const __half* w_out, const float* b_out, float* out32, __half* out16, int B, int S, int C,
+                       int heads, float eps, cudaStream_t st) {
+  CM_CHECK(attn_block_supported(S, C, heads), "fused attention block: C=%d heads=%d S=%d not covered", C, heads, S);
+  AttnBlockParams p{x, gamma, beta, w_in, b_in, w_out, b_out, out32, out16, S, eps};
+  switch ((S + 15) / 16) {
+    case 1: return attn_block_launch<2>(p, B, st);
+    case 2: return attn_block_launch<4>(p, B, st);
+    case 3: return attn_block_launch<6>(p, B, st);
+    case 4: return attn_block_launch<8>(p, B, st);
+    case 5: return attn_block_launch<10>(p, B, st);
+    case 6: return attn_block_launch<12>(p, B, st);
+    case 7: return attn_block_launch<14>(p, B, st);
+    default: return attn_block_launch<16>(p, B, st);
+  }
+}
+
+template <int NT>
+static int attn_block_attr() {
+  CM_CUDA(cudaFuncSetAttribute(attn_block_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)attn_block_smem<NT>()));
+  return 0;
+}
+
 // pre-set the shared-memory attribute of every attention instantiation outside stream capture
 template <int DH, int NT>
 static int attn_attr() {
@@ -1384,6 +1733,9 @@ static int attn_init() {
 #define CM_AT(NT) if (int rc = attn_attr<16, NT>()) return rc; if (int rc = attn_attr<32, NT>()) return rc; if (int rc = attn_attr<64, NT>()) return rc;
   CM_AT(2) CM_AT(4) CM_AT(6) CM_AT(8) CM_AT(10) CM_AT(12) CM_AT(14) CM_AT(16)
 #undef CM_AT
+#define CM_AB(NT) if (int rc = attn_block_attr<NT>()) return rc;
+  CM_AB(2) CM_AB(4) CM_AB(6) CM_AB(8) CM_AB(10) CM_AB(12) CM_AB(14) CM_AB(16)
+#undef CM_AB
   return 0;
 }
 

@@ -103,6 +103,15 @@ int temb_enqueue(const TembParams& p, cudaStream_t st);
 int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int heads,
                       cudaStream_t st);
 
+// ---- fused AttentionBlock of the sampling path (layers.py:5-18): GroupNorm -> in_proj -> attention core ->
+// out_proj -> + x in one launch (one CTA per sample).  w_in / w_out: packed hi|lo fp16 rows as the 1x1 convs
+// use them ([2*3C][C] and [2*C][C]).  Covers C = 128, 4 heads, S <= 128; callers fall back to the four
+// separate kernels otherwise (and in training, where the backward needs the intermediates).
+bool attn_block_supported(int S, int C, int heads);
+int attn_block_enqueue(const float* x, const float* gamma, const float* beta, const __half* w_in, const float* b_in,
+                       const __half* w_out, const float* b_out, float* out32, __half* out16, int B, int S, int C,
+                       int heads, float eps, cudaStream_t st);
+
 // ---- chain bookkeeping: step += 1; t_dev = tsteps[step] ----
 int advance_step_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaStream_t st);
 

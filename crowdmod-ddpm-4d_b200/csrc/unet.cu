@@ -581,9 +581,35 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
             cudaEvent_t* events = nullptr) {
   const cm_unet_config& c = u->cfg;
   int op_index = 0;
-  for (Op& op : u->ops) {
+  int skip = 0;            // ops already covered by a fused launch (their profile events still tick)
+  static const bool no_attn_fuse = getenv("CM_NO_ATTN_FUSE") != nullptr;
+  for (size_t oi = 0; oi < u->ops.size(); ++oi) {
+    Op& op = u->ops[oi];
     if (events) CM_CUDA(cudaEventRecord(events[op_index], st));
     ++op_index;
+    if (skip > 0) { --skip; continue; }
+    // sampling path: the whole AttentionBlock (GroupNorm, in_proj, core, out_proj + residual) is one launch
+    if (op.type == OP_GN && !rc.train && !no_attn_fuse && oi + 3 < u->ops.size() &&
+        u->ops[oi + 2].type == OP_ATTN && u->ops[oi + 1].type == OP_CONV && u->ops[oi + 3].type == OP_CONV &&
+        u->ops[oi + 1].in == op.out_norm && op.src1 < 0) {
+      const Op& ip = u->ops[oi + 1];
+      const Op& at = u->ops[oi + 2];
+      const Op& po = u->ops[oi + 3];
+      const int Cc = u->tens[op.src0].C;
+      const int S = u->levels[u->tens[op.src0].level].pps();
+      const int terms = ip.terms ? ip.terms : c.weight_terms;
+      if (attn_block_supported(S, Cc, at.heads) && terms == 2 && ip.mode == 3 && po.mode == 3 && po.resid == op.src0 &&
+          ip.extra < 0 && po.extra < 0 && ip.cout == 3 * Cc && po.cout == Cc) {
+        if (int e = attn_block_enqueue(u->tens[op.src0].p32, u->params[op.gamma].ptr, u->params[op.beta].ptr,
+                                       u->wpack + ip.wpack_off, u->params[ip.bias].ptr, u->wpack + po.wpack_off,
+                                       u->params[po.bias].ptr, u->tens[po.out].p32, u->tens[po.out].p16, rc.batch,
+                                       S, Cc, at.heads, 1e-5f, st))
+          return e;
+        if (launches) ++*launches;
+        skip = 3;
+        continue;
+      }
+    }
     switch (op.type) {
       case OP_FIRST: {
         const Level& l0 = u->levels[0];

@@ -1,0 +1,12 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import crowdmod_ddpm_4d_b200._native as nat
+from tests.test_gpu_ops import run_conv
+os.environ["CM_DBG_REPS"] = "20"
+for dbg in (0, 67, 71, 64):
+    os.environ["CM_PLANE_DBG"] = str(dbg)
+    print(f"--- dbg={dbg}", file=sys.stderr, flush=True)
+    run_conv(nat, 0, 64, 8, 12, 36, 32, 32, 0, 2, True, impl=2)
+    run_conv(nat, 0, 64, 8, 12, 36, 96, 32, 96, 2, False, impl=2)
+    run_conv(nat, 0, 64, 4, 6, 18, 64, 64, 0, 2, True, impl=2)
