@@ -1386,7 +1386,10 @@ int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int he
 // Same operand precisions as the unfused path (fp16 activations, hi+lo weights, hi+lo Q/K).
 // =============================================================================================
 constexpr int AB_C = 128, AB_HEADS = 4, AB_DH = 32, AB_THREADS = 512, AB_WARPS = 16;
-constexpr int AB_LD = AB_C + 8;           // smem row stride (halfs) of h / ctx / Q / K
+constexpr int AB_LD = AB_C + 8;           // smem row stride (halfs) of h
+constexpr int AB_CL = AB_C / 2;           // channels (two heads) owned by one CTA of the pair
+constexpr int AB_LDL = AB_CL + 8;         // smem row stride (halfs) of Q / K / ctx (local channels)
+constexpr int AB_PLD = AB_C + 4;          // smem row stride (floats) of the out_proj partial sums
 
 struct AttnBlockParams {
   const float* x;          // [B][S][C] fp32 (block input = residual)
@@ -1402,16 +1405,16 @@ struct AttnBlockParams {
   float eps;
 };
 
-// acc[MT][NTW] (+)= A[smem, rows mt*16.., K = AB_C] . W[n][k]^T with hi and lo weight rows
-template <int MT, int NTW>
+// acc[MT][NTW] (+)= A[smem rows m_base + mt*16.., K = 16*KT] . W[nb[nt] + g][kcol0 + k]^T, hi and lo weight rows
+template <int MT, int NTW, int KT, int ALD>
 __device__ __forceinline__ void ab_gemm(const __half* __restrict__ A, int m_base, const __half* __restrict__ Whi,
-                                        const __half* __restrict__ Wlo, int n0, float (&acc)[MT][NTW][4], int g,
-                                        int t) {
+                                        const __half* __restrict__ Wlo, const int (&nb)[NTW], int kcol0,
+                                        float (&acc)[MT][NTW][4], int g, int t) {
   uint32_t bh[2][NTW][2], bl[2][NTW][2];
   auto load_b = [&](int kt, int buf) {
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt) {
-      const size_t o = (size_t)(n0 + nt * 8 + g) * AB_C + kt * 16 + 2 * t;
+      const size_t o = (size_t)(nb[nt] + g) * AB_C + kcol0 + kt * 16 + 2 * t;
       bh[buf][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(Whi + o));
       bh[buf][nt][1] = __ldg(reinterpret_cast<const uint32_t*>(Whi + o + 8));
       bl[buf][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(Wlo + o));
@@ -1420,17 +1423,17 @@ __device__ __forceinline__ void ab_gemm(const __half* __restrict__ A, int m_base
   };
   load_b(0, 0);
 #pragma unroll
-  for (int kt = 0; kt < AB_C / 16; ++kt) {
+  for (int kt = 0; kt < KT; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < AB_C / 16) load_b(kt + 1, buf ^ 1);
+    if (kt + 1 < KT) load_b(kt + 1, buf ^ 1);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const __half* ar = A + (size_t)(m_base + mt * 16 + g) * AB_LD + kt * 16 + 2 * t;
+      const __half* ar = A + (size_t)(m_base + mt * 16 + g) * ALD + kt * 16 + 2 * t;
       uint32_t a[4];
       a[0] = *reinterpret_cast<const uint32_t*>(ar);
-      a[1] = *reinterpret_cast<const uint32_t*>(ar + 8 * AB_LD);
+      a[1] = *reinterpret_cast<const uint32_t*>(ar + 8 * ALD);
       a[2] = *reinterpret_cast<const uint32_t*>(ar + 8);
-      a[3] = *reinterpret_cast<const uint32_t*>(ar + 8 * AB_LD + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(ar + 8 * ALD + 8);
 #pragma unroll
       for (int nt = 0; nt < NTW; ++nt) {
         mma_16816(acc[mt][nt], a, bl[buf][nt][0], bl[buf][nt][1]);
@@ -1440,26 +1443,36 @@ __device__ __forceinline__ void ab_gemm(const __half* __restrict__ A, int m_base
   }
 }
 
+// A pair of CTAs (thread-block cluster of 2) per sample: CTA r owns heads 2r, 2r+1 (channels [64r, 64r+64))
+// through in_proj and the attention core; out_proj is a K-split whose two partial tiles are summed in rank
+// order through distributed shared memory (deterministic), CTA r finalising output columns [64r, 64r+64).
 template <int NT>   // NT = padded tokens / 8 (even): SP = 16, 32, ... 128
 __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const AttnBlockParams p) {
+  namespace cgr = cooperative_groups;
+  cgr::cluster_group cluster = cgr::this_cluster();
   pdl_trigger();
   pdl_wait();
   constexpr int SP = NT * 8, MTILES = SP / 16;
   constexpr int VLD = SP + 8;
+  constexpr int MH = (MTILES + 1) / 2;                   // M tiles per half (phase 1 splits M over warp halves)
   extern __shared__ __align__(16) uint8_t ab_raw[];
-  __half* Hs = reinterpret_cast<__half*>(ab_raw);       // [SP][AB_LD]  h, later ctx
-  __half* Qh = Hs + SP * AB_LD;
-  __half* Ql = Qh + SP * AB_LD;
-  __half* Kh = Ql + SP * AB_LD;
-  __half* Kl = Kh + SP * AB_LD;
-  __half* Vt = Kl + SP * AB_LD;                          // [AB_C][VLD]
+  __half* Hs = reinterpret_cast<__half*>(ab_raw);       // [SP][AB_LD]   h
+  __half* Qh = Hs + SP * AB_LD;                          // [SP][AB_LDL]  local channels
+  __half* Ql = Qh + SP * AB_LDL;
+  __half* Kh = Ql + SP * AB_LDL;
+  __half* Kl = Kh + SP * AB_LDL;
+  __half* Vt = Kl + SP * AB_LDL;                         // [AB_CL][VLD]
+  __half* Cx = Vt + AB_CL * VLD;                         // [SP][AB_LDL]  ctx (local channels)
+  float* Pp = reinterpret_cast<float*>(ab_raw);          // [SP][AB_PLD]  out_proj partial (aliases h/Q/K: dead by then)
   __shared__ float red[AB_WARPS][8];
   __shared__ float gstat[2][8];
   const int S = p.S;
-  const int b = blockIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const float* xb = p.x + (size_t)b * S * AB_C;
+  const int cl0 = rank * AB_CL;                          // first channel owned by this CTA
 
   // ---- phase 0: GroupNorm.  warp = row (mod 16), lane = float4 column; group = lane / 4 (16 channels) ----
   constexpr int RPT = (SP + AB_WARPS - 1) / AB_WARPS;    // rows per warp
@@ -1520,61 +1533,68 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const AttnBlo
   }
   __syncthreads();
 
-  // ---- phase 1: qkv = h W_in^T + b_in.  Warp w owns output columns [24w, 24w+24) (3 n8 tiles) ----
+  // ---- phase 1: q|k|v (local channels) = h W_in^T + b_in: 24 n8 tiles (8 q, 8 k, 8 v).
+  //      warp = (M half, group of 3 tiles) ----
   {
-    constexpr int MC = MTILES < 4 ? MTILES : 4;          // M tiles per pass (accumulator registers)
     const float qscale = rsqrtf((float)AB_DH);
-    const int n0 = warp * 24;
-    for (int m0 = 0; m0 < MTILES; m0 += MC) {
-      float acc[MC][3][4];
+    const int mh = warp >> 3, ng = warp & 7;
+    int nb[3], wh[3], cc[3];
 #pragma unroll
-      for (int mt = 0; mt < MC; ++mt)
+    for (int nt = 0; nt < 3; ++nt) {
+      const int j = ng * 3 + nt;
+      wh[nt] = j >> 3;                                   // 0 q, 1 k, 2 v
+      cc[nt] = (j & 7) * 8;                              // local channel of the tile
+      nb[nt] = wh[nt] * AB_C + cl0 + cc[nt];             // row of W_in
+    }
+    if (mh * MH < MTILES) {
+      float acc[MH][3][4];
+#pragma unroll
+      for (int mt = 0; mt < MH; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
-      ab_gemm<MC, 3>(Hs, m0 * 16, p.w_in, p.w_in + (size_t)3 * AB_C * AB_C, n0, acc, g, t);
+      ab_gemm<MH, 3, AB_C / 16, AB_LD>(Hs, mh * MH * 16, p.w_in, p.w_in + (size_t)3 * AB_C * AB_C, nb, 0, acc, g, t);
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
-        const int n = n0 + nt * 8 + 2 * t;               // this thread's two columns (n, n + 1)
-        const float2 bi = *reinterpret_cast<const float2*>(p.b_in + n);
-        const int which = n / AB_C, c = n - which * AB_C;   // 0 q, 1 k, 2 v (uniform per n8 tile)
+        const float2 bi = *reinterpret_cast<const float2*>(p.b_in + nb[nt] + 2 * t);
+        const int c = cc[nt] + 2 * t;
 #pragma unroll
-        for (int mt = 0; mt < MC; ++mt) {
-          if (m0 + mt >= MTILES) continue;
-          const int r0 = (m0 + mt) * 16 + g, r1 = r0 + 8;
+        for (int mt = 0; mt < MH; ++mt) {
+          if (mh * MH + mt >= MTILES) continue;
+          const int r0 = (mh * MH + mt) * 16 + g, r1 = r0 + 8;
           const float v00 = acc[mt][nt][0] + bi.x, v01 = acc[mt][nt][1] + bi.y;
           const float v10 = acc[mt][nt][2] + bi.x, v11 = acc[mt][nt][3] + bi.y;
-          if (which == 2) {
+          if (wh[nt] == 2) {
             Vt[(size_t)c * VLD + r0] = __float2half_rn(v00);
             Vt[(size_t)(c + 1) * VLD + r0] = __float2half_rn(v01);
             Vt[(size_t)c * VLD + r1] = __float2half_rn(v10);
             Vt[(size_t)(c + 1) * VLD + r1] = __float2half_rn(v11);
           } else {
-            const float sc = which == 0 ? qscale : 1.0f;
-            __half* hi = which == 0 ? Qh : Kh;
-            __half* lo = which == 0 ? Ql : Kl;
+            const float sc = wh[nt] == 0 ? qscale : 1.0f;
+            __half* hi = wh[nt] == 0 ? Qh : Kh;
+            __half* lo = wh[nt] == 0 ? Ql : Kl;
             uint32_t h, l;
             split_h2(v00 * sc, v01 * sc, &h, &l);
-            *reinterpret_cast<uint32_t*>(hi + (size_t)r0 * AB_LD + c) = h;
-            *reinterpret_cast<uint32_t*>(lo + (size_t)r0 * AB_LD + c) = l;
+            *reinterpret_cast<uint32_t*>(hi + (size_t)r0 * AB_LDL + c) = h;
+            *reinterpret_cast<uint32_t*>(lo + (size_t)r0 * AB_LDL + c) = l;
             split_h2(v10 * sc, v11 * sc, &h, &l);
-            *reinterpret_cast<uint32_t*>(hi + (size_t)r1 * AB_LD + c) = h;
-            *reinterpret_cast<uint32_t*>(lo + (size_t)r1 * AB_LD + c) = l;
+            *reinterpret_cast<uint32_t*>(hi + (size_t)r1 * AB_LDL + c) = h;
+            *reinterpret_cast<uint32_t*>(lo + (size_t)r1 * AB_LDL + c) = l;
           }
         }
       }
     }
   }
-  __syncthreads();     // q/k/v complete; h is dead -> Hs becomes ctx
+  __syncthreads();     // q/k/v complete
 
-  // ---- phase 2: attention core, one (head, query tile) per warp pass ----
-  for (int pr = warp; pr < AB_HEADS * MTILES; pr += AB_WARPS) {
-    const int hd = pr % AB_HEADS, mt = pr / AB_HEADS;
+  // ---- phase 2: attention core, one (local head, query tile) per warp pass ----
+  for (int pr = warp; pr < 2 * MTILES; pr += AB_WARPS) {
+    const int hd = pr & 1, mt = pr >> 1;
     const int i0 = mt * 16 + g, i1 = i0 + 8;
     const int cb = hd * AB_DH;
     uint32_t qh[AB_DH / 16][4], ql[AB_DH / 16][4];
 #pragma unroll
     for (int kt = 0; kt < AB_DH / 16; ++kt) {
-      const int o0 = i0 * AB_LD + cb + kt * 16 + 2 * t, o1 = i1 * AB_LD + cb + kt * 16 + 2 * t;
+      const int o0 = i0 * AB_LDL + cb + kt * 16 + 2 * t, o1 = i1 * AB_LDL + cb + kt * 16 + 2 * t;
       qh[kt][0] = *reinterpret_cast<const uint32_t*>(Qh + o0);
       qh[kt][1] = *reinterpret_cast<const uint32_t*>(Qh + o1);
       qh[kt][2] = *reinterpret_cast<const uint32_t*>(Qh + o0 + 8);
@@ -1591,7 +1611,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const AttnBlo
       const int j = nt * 8 + g;
 #pragma unroll
       for (int kt = 0; kt < AB_DH / 16; ++kt) {
-        const int o = j * AB_LD + cb + kt * 16 + 2 * t;
+        const int o = j * AB_LDL + cb + kt * 16 + 2 * t;
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(Kh + o);
         const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(Kh + o + 8);
         const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(Kl + o);
@@ -1650,49 +1670,83 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const AttnBlo
 #pragma unroll
     for (int dt = 0; dt < AB_DH / 8; ++dt) {
       const int d = cb + dt * 8 + 2 * t;
-      *reinterpret_cast<uint32_t*>(Hs + (size_t)i0 * AB_LD + d) = pack_h2(oc[dt][0], oc[dt][1]);
-      *reinterpret_cast<uint32_t*>(Hs + (size_t)i1 * AB_LD + d) = pack_h2(oc[dt][2], oc[dt][3]);
+      *reinterpret_cast<uint32_t*>(Cx + (size_t)i0 * AB_LDL + d) = pack_h2(oc[dt][0], oc[dt][1]);
+      *reinterpret_cast<uint32_t*>(Cx + (size_t)i1 * AB_LDL + d) = pack_h2(oc[dt][2], oc[dt][3]);
     }
   }
-  __syncthreads();
+  __syncthreads();     // ctx complete; h / Q / K are dead -> partial-sum tile
 
-  // ---- phase 3: out = ctx W_o^T + b_o + x.  Warp w owns output columns [8w, 8w+8) ----
+  // ---- phase 3: partial[S][C] = ctx_local W_o[:, local channels]^T.  Warp w owns columns [8w, 8w+8) ----
   {
     constexpr int MC = MTILES < 4 ? MTILES : 4;
-    const int n0 = warp * 8;
-    const int n = n0 + 2 * t;
-    const float2 bo = *reinterpret_cast<const float2*>(p.b_out + n);
+    const int nb1[1] = {warp * 8};
     for (int m0 = 0; m0 < MTILES; m0 += MC) {
       float acc[MC][1][4];
 #pragma unroll
       for (int mt = 0; mt < MC; ++mt) acc[mt][0][0] = acc[mt][0][1] = acc[mt][0][2] = acc[mt][0][3] = 0.f;
-      ab_gemm<MC, 1>(Hs, m0 * 16, p.w_out, p.w_out + (size_t)AB_C * AB_C, n0, acc, g, t);
+      ab_gemm<MC, 1, AB_CL / 16, AB_LDL>(Cx, m0 * 16, p.w_out, p.w_out + (size_t)AB_C * AB_C, nb1, cl0, acc, g, t);
 #pragma unroll
       for (int mt = 0; mt < MC; ++mt) {
         if (m0 + mt >= MTILES) continue;
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-          const int r = (m0 + mt) * 16 + g + hrow * 8;
-          if (r >= S) continue;
-          const size_t o = ((size_t)b * S + r) * AB_C + n;
-          const float2 xr = *reinterpret_cast<const float2*>(p.x + o);
-          const float y0 = acc[mt][0][2 * hrow] + bo.x + xr.x, y1 = acc[mt][0][2 * hrow + 1] + bo.y + xr.y;
-          if (p.out32) *reinterpret_cast<float2*>(p.out32 + o) = make_float2(y0, y1);
-          if (p.out16) *reinterpret_cast<uint32_t*>(p.out16 + o) = pack_h2(y0, y1);
-        }
+        const int r0 = (m0 + mt) * 16 + g;
+        *reinterpret_cast<float2*>(Pp + (size_t)r0 * AB_PLD + warp * 8 + 2 * t) = make_float2(acc[mt][0][0], acc[mt][0][1]);
+        *reinterpret_cast<float2*>(Pp + (size_t)(r0 + 8) * AB_PLD + warp * 8 + 2 * t) =
+            make_float2(acc[mt][0][2], acc[mt][0][3]);
       }
     }
   }
+  cluster.sync();
+  // ---- out[:, cl0 .. cl0+64) = partial(rank 0) + partial(rank 1) + b_o + x, fixed order ----
+  {
+    const float* P0 = cluster.map_shared_rank(Pp, 0);
+    const float* P1 = cluster.map_shared_rank(Pp, 1);
+    for (int idx = tid; idx < S * (AB_CL / 4); idx += AB_THREADS) {
+      const int r = idx / (AB_CL / 4), c = cl0 + (idx - r * (AB_CL / 4)) * 4;
+      const float4 a = *reinterpret_cast<const float4*>(P0 + (size_t)r * AB_PLD + c);
+      const float4 bq = *reinterpret_cast<const float4*>(P1 + (size_t)r * AB_PLD + c);
+      const float4 bo = *reinterpret_cast<const float4*>(p.b_out + c);
+      const size_t o = ((size_t)b * S + r) * AB_C + c;
+      const float4 xr = *reinterpret_cast<const float4*>(p.x + o);
+      float4 y;
+      y.x = (a.x + bq.x) + bo.x + xr.x; y.y = (a.y + bq.y) + bo.y + xr.y;
+      y.z = (a.z + bq.z) + bo.z + xr.z; y.w = (a.w + bq.w) + bo.w + xr.w;
+      if (p.out32) *reinterpret_cast<float4*>(p.out32 + o) = y;
+      if (p.out16) {
+        uint2 u;
+        u.x = pack_h2(y.x, y.y);
+        u.y = pack_h2(y.z, y.w);
+        *reinterpret_cast<uint2*>(p.out16 + o) = u;
+      }
+    }
+  }
+  cluster.sync();      // the peer may still be reading this CTA's partial tile
 }
 
 template <int NT>
 static size_t attn_block_smem() {
   constexpr int SP = NT * 8;
-  return ((size_t)5 * SP * AB_LD + (size_t)AB_C * (SP + 8)) * sizeof(__half);
+  const size_t halfs = ((size_t)SP * AB_LD + (size_t)5 * SP * AB_LDL + (size_t)AB_CL * (SP + 8)) * sizeof(__half);
+  const size_t part = (size_t)SP * AB_PLD * sizeof(float);        // aliases the front of the half buffers
+  return halfs > part ? halfs : part;
 }
 template <int NT>
 static int attn_block_launch(const AttnBlockParams& p, int B, cudaStream_t st) {
-  return launch_pdl(attn_block_kernel<NT>, dim3(B), dim3(AB_THREADS), attn_block_smem<NT>(), st, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * B);
+  cfg.blockDim = dim3(AB_THREADS);
+  cfg.dynamicSmemBytes = attn_block_smem<NT>();
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  CM_CUDA(cudaLaunchKernelEx(&cfg, attn_block_kernel<NT>, p));
+  return 0;
 }
 
 bool attn_block_supported(int S, int C, int heads) {
