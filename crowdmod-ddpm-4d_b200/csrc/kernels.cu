@@ -982,77 +982,111 @@ int first_conv_enqueue(const float* x, const float* past, const float* w, const 
 // final conv (N = 3 is tiny; memory-bound) + reverse-step update.
 // 4 lanes per output pixel, each lane owns 8-channel slices; only future frames are produced.
 // =============================================================================================
+constexpr int FIN_FC = 3;   // output frames per 4-lane group: taps along time share the group's 5 input planes
+
 template <int COUT>
 __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float ws[];   // [27][cin][COUT]
+  // weights as [h tap][w tap][ci][time tap][co]: the 8 channels x 3 time taps x COUT outputs a lane needs
+  // for one spatial tap are contiguous (vector loads, broadcast across the warp's sites)
+  extern __shared__ __align__(16) float ws[];
   const int cin = p.cin;
   for (int idx = threadIdx.x; idx < 27 * cin * COUT; idx += blockDim.x) {
     const int co = idx % COUT;
-    const int r = idx / COUT;
-    const int ci = r % cin, tap = r / cin;
-    ws[idx] = p.w[((size_t)co * cin + ci) * 27 + tap];
+    int r = idx / COUT;
+    const int tl = r % 3;
+    r /= 3;
+    const int ci = r % cin, sp = r / cin;             // sp = th*3 + tw (rows, cols)
+    ws[idx] = p.w[((size_t)co * cin + ci) * 27 + sp * 3 + tl];
   }
   __syncthreads();
   const int F = p.L - p.P;
-  const size_t total = (size_t)p.B * p.H * p.W * F;
-  // grid-stride over groups of 256 lanes (= 64 pixels): the weights are staged once per CTA and the
-  // grid is sized to ONE resident wave (1296 CTAs on 1184 slots ran as two waves)
+  const int nchunk = (F + FIN_FC - 1) / FIN_FC;
+  const size_t sites = (size_t)p.B * p.H * p.W;
+  const size_t total = sites * nchunk;                 // 4-lane groups
+  // grid-stride over groups of 256 lanes (= 64 (site, frame chunk) groups): the weights are staged once
+  // per CTA and the grid is sized to at most one resident wave
   for (size_t gbase = blockIdx.x * (size_t)blockDim.x; gbase < total * 4; gbase += (size_t)gridDim.x * blockDim.x) {
   const size_t gid = gbase + threadIdx.x;
-  const size_t pix = gid >> 2;
+  const size_t grp = gid >> 2;
   const int sub = (int)(gid & 3);
-  const bool active = pix < total;
-  int f = 0, wc = 0, h = 0, b = 0;
+  const bool active = grp < total;
+  int f0 = 0, wc = 0, h = 0, b = 0;
   if (active) {
-    f = (int)(pix % F);
-    size_t r = pix / F;
+    f0 = (int)(grp % nchunk) * FIN_FC;
+    size_t r = grp / nchunk;
     wc = (int)(r % p.W);
     r /= p.W;
     h = (int)(r % p.H);
     b = (int)(r / p.H);
   }
-  const int l = p.P + f;
-  float acc[COUT];
+  float acc3[FIN_FC][COUT];
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+  for (int j = 0; j < FIN_FC; ++j)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc3[j][co] = 0.f;
   if (active) {
-    for (int td = 0; td < 3; ++td) {
-      const int hh = h + td - 1;
+    const int l0 = p.P + f0 - 1;                       // first of the FIN_FC + 2 input planes
+    const size_t pstride = (size_t)p.H * p.W * cin;    // elements per (b, l) plane
+    for (int th = 0; th < 3; ++th) {
+      const int hh = h + th - 1;
       if (hh < 0 || hh >= p.H) continue;
-      for (int th = 0; th < 3; ++th) {
-        const int ww = wc + th - 1;
+      for (int tw = 0; tw < 3; ++tw) {
+        const int ww = wc + tw - 1;
         if (ww < 0 || ww >= p.W) continue;
-        for (int tw = 0; tw < 3; ++tw) {
-          const int ll = l + tw - 1;
-          if (ll < 0 || ll >= p.L) continue;
-          const int tap = (td * 3 + th) * 3 + tw;
-          const __half* ap = p.act + ((((size_t)b * p.L + ll) * p.H + hh) * p.W + ww) * cin;
-          for (int c0 = sub * 8; c0 < cin; c0 += 32) {
-            const uint4 u = *reinterpret_cast<const uint4*>(ap + c0);
+        const __half* ap = p.act + (((size_t)b * p.L * p.H + hh) * p.W + ww) * cin;
+        for (int c0 = sub * 8; c0 < cin; c0 += 32) {
+          float a[FIN_FC + 2][8];
+#pragma unroll
+          for (int q = 0; q < FIN_FC + 2; ++q) {
+            const int ll = l0 + q;
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            // planes past the chunk's last valid frame + 1 are never multiplied into a stored output
+            if (ll >= 0 && ll < p.L) u = *reinterpret_cast<const uint4*>(ap + (size_t)ll * pstride + c0);
             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-            const float* wp = ws + ((size_t)tap * cin + c0) * COUT;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 a2 = __half22float2(h2[e]);
-#pragma unroll
-              for (int co = 0; co < COUT; ++co) {
-                acc[co] = fmaf(a2.x, wp[(2 * e) * COUT + co], acc[co]);
-                acc[co] = fmaf(a2.y, wp[(2 * e + 1) * COUT + co], acc[co]);
-              }
+              a[q][2 * e] = a2.x;
+              a[q][2 * e + 1] = a2.y;
             }
           }
+          const float4* wp4 = reinterpret_cast<const float4*>(ws + ((size_t)(th * 3 + tw) * cin + c0) * 3 * COUT);
+          float wv[8 * 3 * COUT];
+#pragma unroll
+          for (int q = 0; q < (8 * 3 * COUT) / 4; ++q) {
+            const float4 t4 = wp4[q];
+            wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+              for (int co = 0; co < COUT; ++co) {
+                const float wgt = wv[(e * 3 + tl) * COUT + co];
+#pragma unroll
+                for (int j = 0; j < FIN_FC; ++j) acc3[j][co] = fmaf(a[j + tl][e], wgt, acc3[j][co]);
+              }
         }
       }
     }
   }
+  float acc[COUT];
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) {
-    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
-    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
-  }
-  if (!active || sub != 0) continue;
+  for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+  for (int j = 0; j < FIN_FC; ++j)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      float v = acc3[j][co];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (j == sub) acc[co] = v;                       // lane j of the group finalises frame f0 + j
+    }
+  const int f = f0 + sub;
+  if (!active || sub >= FIN_FC || f >= F) continue;
 
   const size_t plane = (size_t)p.H * p.W * F;                       // elements per (b, c)
   const size_t e0 = ((size_t)b * COUT) * plane + ((size_t)h * p.W + wc) * F + f;
@@ -1112,9 +1146,9 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
 int final_conv_enqueue(const FinalParams& p, cudaStream_t st) {
   CM_CHECK(p.cout >= 1 && p.cout <= 4, "final conv supports 1..4 output channels (got %d)", p.cout);
   CM_CHECK(p.cin % 32 == 0, "final conv cin must be a multiple of 32");
-  const size_t total = (size_t)p.B * p.H * p.W * (p.L - p.P) * 4;
+  const size_t total = (size_t)p.B * p.H * p.W * ((p.L - p.P + FIN_FC - 1) / FIN_FC) * 4;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;          // one resident wave; the kernel grid-strides
+  if (blocks > 148 * 4) blocks = 148 * 4;          // at most one resident wave; the kernel grid-strides
   const size_t smem = (size_t)27 * p.cin * p.cout * sizeof(float);
 #define CM_FINAL(CO)                                                                           \
   case CO: {                                                                                   \
