@@ -910,8 +910,24 @@ __global__ void small_gemm_kernel(int M, int N, int K, const float* __restrict__
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   const int m = idx / N, n = idx - m * N;
-  float a = 0.f;
-  for (int k = 0; k < K; ++k) a = fmaf(A[(size_t)m * sam + (size_t)k * sak], Bm[(size_t)k * sbk + (size_t)n * sbn], a);
+  const float* ap = A + (size_t)m * sam;
+  const float* bp = Bm + (size_t)n * sbn;
+  // 8 independent loads in flight per operand and four accumulators (merged in a fixed order): the
+  // dependent one-load-per-FMA loop exposed one L2 round trip per k
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 8 <= K; k += 8) {
+    float av[8], bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      av[j] = ap[(size_t)(k + j) * sak];
+      bv[j] = bp[(size_t)(k + j) * sbk];
+    }
+    a0 = fmaf(av[0], bv[0], a0); a1 = fmaf(av[1], bv[1], a1); a2 = fmaf(av[2], bv[2], a2); a3 = fmaf(av[3], bv[3], a3);
+    a0 = fmaf(av[4], bv[4], a0); a1 = fmaf(av[5], bv[5], a1); a2 = fmaf(av[6], bv[6], a2); a3 = fmaf(av[7], bv[7], a3);
+  }
+  for (; k < K; ++k) a0 = fmaf(ap[(size_t)k * sak], bp[(size_t)k * sbk], a0);
+  const float a = (a0 + a1) + (a2 + a3);
   float* o = Cm + (size_t)m * ldc + n;
   *o = accumulate ? *o + a : a;
 }
@@ -919,6 +935,77 @@ int small_gemm_enqueue(int M, int N, int K, const float* A, int sam, int sak, co
                        int sbn, float* Cm, int ldc, int accumulate, cudaStream_t st) {
   small_gemm_kernel<<<(M * N + 127) / 128, 128, 0, st>>>(M, N, K, A, sam, sak, Bm, sbk, sbn, Cm, ldc,
                                                          accumulate);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Every block's dense_1 (layers.py:35,62) backward in two launches instead of three per block.
+//   wgrad: CTA = one column j of dtemb (= output channel c of block k): dW_k[c][e] = sum_b dtemb[b][j] * s2[b][e],
+//          db_k[c] = sum_b dtemb[b][j]                      (s2 = SiLU(h2), the dense_1 input)
+//   dgrad: CTA = one sample: ds2[b][e] = sum_j dtemb[b][j] * W_cat[j][e]
+__global__ void __launch_bounds__(128)
+temb_dense_wgrad_kernel(const float* __restrict__ dtemb, int ld, int B, const float* __restrict__ s2, int E,
+                        const int* __restrict__ couts, const int* __restrict__ offs, int nblocks,
+                        float* __restrict__ grads, const long long* __restrict__ goff_w,
+                        const long long* __restrict__ goff_b) {
+  const int j = blockIdx.y;
+  int k = 0;
+  while (k + 1 < nblocks && offs[k + 1] <= j) ++k;
+  const int c = j - offs[k];
+  if (c >= couts[k]) return;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, bs0 = 0.f, bs1 = 0.f;
+  int b = 0;
+  if (e < E) {
+    for (; b + 4 <= B; b += 4) {
+      const float d0 = dtemb[(size_t)b * ld + j], d1 = dtemb[(size_t)(b + 1) * ld + j];
+      const float d2 = dtemb[(size_t)(b + 2) * ld + j], d3 = dtemb[(size_t)(b + 3) * ld + j];
+      const float s0 = s2[(size_t)b * E + e], s1 = s2[(size_t)(b + 1) * E + e];
+      const float s2v = s2[(size_t)(b + 2) * E + e], s3 = s2[(size_t)(b + 3) * E + e];
+      a0 = fmaf(d0, s0, a0); a1 = fmaf(d1, s1, a1); a0 = fmaf(d2, s2v, a0); a1 = fmaf(d3, s3, a1);
+      bs0 += d0 + d2; bs1 += d1 + d3;
+    }
+    for (; b < B; ++b) {
+      const float d0 = dtemb[(size_t)b * ld + j];
+      a0 = fmaf(d0, s2[(size_t)b * E + e], a0);
+      bs0 += d0;
+    }
+    grads[goff_w[k] + (long long)c * E + e] = a0 + a1;
+    if (e == 0) grads[goff_b[k] + c] = bs0 + bs1;
+  }
+}
+__global__ void temb_dense_dgrad_kernel(const float* __restrict__ dtemb, int ld, const float* const* __restrict__ wd,
+                                        const int* __restrict__ couts, const int* __restrict__ offs, int nblocks,
+                                        int E, float* __restrict__ ds2) {
+  extern __shared__ float drow[];   // [ld]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) drow[i] = dtemb[(size_t)b * ld + i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < nblocks; ++k) {
+      const float* w = wd[k] + e;
+      const float* d = drow + offs[k];
+      const int co = couts[k];
+      int c = 0;
+      for (; c + 4 <= co; c += 4) {
+        a0 = fmaf(d[c], w[(size_t)c * E], a0);
+        a1 = fmaf(d[c + 1], w[(size_t)(c + 1) * E], a1);
+        a2 = fmaf(d[c + 2], w[(size_t)(c + 2) * E], a2);
+        a3 = fmaf(d[c + 3], w[(size_t)(c + 3) * E], a3);
+      }
+      for (; c < co; ++c) a0 = fmaf(d[c], w[(size_t)c * E], a0);
+    }
+    ds2[(size_t)b * E + e] = (a0 + a1) + (a2 + a3);
+  }
+}
+int temb_dense_backward_enqueue(const float* dtemb, int ld, int B, const float* s2, int E, const float* const* wd,
+                                const int* couts, const int* offs, int nblocks, float* grads,
+                                const long long* goff_w, const long long* goff_b, float* ds2, cudaStream_t st) {
+  temb_dense_wgrad_kernel<<<dim3((E + 127) / 128, ld), 128, 0, st>>>(dtemb, ld, B, s2, E, couts, offs, nblocks, grads,
+                                                                    goff_w, goff_b);
+  const int T = E < 256 ? ((E + 31) / 32) * 32 : 256;
+  temb_dense_dgrad_kernel<<<B, T, (size_t)ld * sizeof(float), st>>>(dtemb, ld, wd, couts, offs, nblocks, E, ds2);
   CM_CUDA(cudaGetLastError());
   return 0;
 }

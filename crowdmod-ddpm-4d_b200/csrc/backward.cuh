@@ -87,6 +87,10 @@ int first_conv_wgrad_enqueue(const float* x, const float* past, const float* dou
 // C[m][n] (=|+=) sum_k A(m,k) * B(k,n) with arbitrary element strides (tiny matrices only)
 int small_gemm_enqueue(int M, int N, int K, const float* A, int sam, int sak, const float* Bm, int sbk,
                        int sbn, float* Cm, int ldc, int accumulate, cudaStream_t st);
+// every block's dense_1 weight/bias gradient and the gradient of its input (SiLU(h2)) in two launches
+int temb_dense_backward_enqueue(const float* dtemb, int ld, int B, const float* s2, int E, const float* const* wd,
+                                const int* couts, const int* offs, int nblocks, float* grads,
+                                const long long* goff_w, const long long* goff_b, float* ds2, cudaStream_t st);
 // dpre = dpost * silu'(pre)
 int silu_backward_enqueue(const float* pre, const float* dpost, float* dpre, size_t n, cudaStream_t st);
 // y = silu(x)

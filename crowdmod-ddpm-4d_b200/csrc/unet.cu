@@ -105,6 +105,8 @@ struct cm_unet {
   float* temb_table = nullptr;          // [table_steps][temb_ld]
   const float** d_wd = nullptr;
   const float** d_bd = nullptr;
+  long long* d_goff_w = nullptr;        // flat-gradient offsets of every block's dense_1 weight / bias
+  long long* d_goff_b = nullptr;
   int* d_couts = nullptr;
   int* d_offs = nullptr;
   bool packed = false;
@@ -1018,17 +1020,24 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
   if (int e = silu_forward_enqueue(u->tsave_h1, u->ts1, nE, st)) return e;
   if (int e = silu_forward_enqueue(u->tsave_h2, u->ts2, nE, st)) return e;
   nl += 2;
-  for (size_t k = 0; k < u->temb_couts.size(); ++k) {
-    const int co = u->temb_couts[k], off = u->temb_offs[k];
-    const float* dt = u->dtemb + off;
-    // (dense_1.bias gradient == the conv_1 bias gradient: both are the batch sum of dtemb)
-    if (int e = rowsum_enqueue(dt, gp(u->temb_dense_b[k]), B, co, u->temb_ld, 0, st)) return e;
-    if (int e = small_gemm_enqueue(co, E, B, dt, 1, u->temb_ld, u->ts2, E, 1, gp(u->temb_dense_w[k]), E, 0, st))
+  {
+    const int nb = (int)u->temb_couts.size();
+    if (!u->d_goff_w) {
+      std::vector<long long> gw(nb), gb(nb);
+      for (int k = 0; k < nb; ++k) {
+        gw[k] = (long long)u->grad_off[u->temb_dense_w[k]];
+        gb[k] = (long long)u->grad_off[u->temb_dense_b[k]];
+      }
+      CM_CUDA(cudaMalloc(&u->d_goff_w, nb * sizeof(long long)));
+      CM_CUDA(cudaMalloc(&u->d_goff_b, nb * sizeof(long long)));
+      CM_CUDA(cudaMemcpy(u->d_goff_w, gw.data(), nb * sizeof(long long), cudaMemcpyHostToDevice));
+      CM_CUDA(cudaMemcpy(u->d_goff_b, gb.data(), nb * sizeof(long long), cudaMemcpyHostToDevice));
+    }
+    // (dense_1.bias gradient == the batch sum of dtemb; the conv_1 bias gradient is the same sum)
+    if (int e = temb_dense_backward_enqueue(u->dtemb, u->temb_ld, B, u->ts2, E, u->d_wd, u->d_couts, u->d_offs, nb,
+                                            grads, u->d_goff_w, u->d_goff_b, u->tds2, st))
       return e;
-    if (int e = small_gemm_enqueue(B, E, co, dt, u->temb_ld, 1, u->params[u->temb_dense_w[k]].ptr, E, 1,
-                                   u->tds2, E, k > 0, st))
-      return e;
-    nl += 3;
+    nl += 2;
   }
   if (int e = silu_backward_enqueue(u->tsave_h2, u->tds2, u->tdh2, nE, st)) return e;
   if (int e = rowsum_enqueue(u->tdh2, gp(u->p_b2), B, E, E, 0, st)) return e;
@@ -1091,6 +1100,8 @@ int cm_unet_destroy(cm_unet* u) {
   cudaFree(u->temb_table);
   cudaFree(u->d_wd);
   cudaFree(u->d_bd);
+  cudaFree(u->d_goff_w);
+  cudaFree(u->d_goff_b);
   cudaFree(u->d_couts);
   cudaFree(u->d_offs);
   cudaFree(u->d_step);
