@@ -719,13 +719,31 @@ final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict_
   for (int co = 0; co < COUT; ++co) bacc[co] = 0.f;
   const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
   const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
-  for (size_t pix = p0; pix < p1; ++pix) {
-    const int f = (int)(pix % F);
-    size_t r = pix / F;
-    const int wc = (int)(r % W);
+  // per-thread (tap, ci) constants hoisted out of the pixel walk (the divisions per pixel and pair made
+  // this kernel instruction-bound: 0.6 ms for 0.3 GFLOP)
+  int kdh[MAXP], kdw[MAXP], kdl[MAXP];
+  long long koff[MAXP];
+  bool kok[MAXP];
+#pragma unroll
+  for (int k = 0; k < MAXP; ++k) {
+    const int pr = threadIdx.x + k * 256;
+    kok[k] = pr < npairs;
+    const int tap = kok[k] ? pr / cin : 0, ci = kok[k] ? pr - tap * cin : 0;
+    kdh[k] = tap / 9 - 1;
+    kdw[k] = (tap / 3) % 3 - 1;
+    kdl[k] = tap % 3 - 1;
+    koff[k] = (((long long)kdl[k] * H + kdh[k]) * W + kdw[k]) * cin + ci;
+  }
+  int f = 0, wc = 0, h = 0, b = 0;
+  if (p0 < p1) {
+    f = (int)(p0 % F);
+    size_t r = p0 / F;
+    wc = (int)(r % W);
     r /= W;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
+    h = (int)(r % H);
+    b = (int)(r / H);
+  }
+  for (size_t pix = p0; pix < p1; ++pix) {
     const int l = P + f;
     float d[COUT];
 #pragma unroll
@@ -733,16 +751,22 @@ final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict_
       d[co] = deps[((size_t)b * COUT + co) * plane + ((size_t)h * W + wc) * F + f] * scale;
       bacc[co] += d[co];
     }
+    const long long base = ((((long long)b * L + l) * H + h) * W + wc) * cin;
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
-      const int pr = threadIdx.x + k * 256;
-      if (pr >= npairs) break;
-      const int tap = pr / cin, ci = pr - tap * cin;
-      const int hh = h + tap / 9 - 1, ww = wc + (tap / 3) % 3 - 1, ll = l + tap % 3 - 1;
+      if (!kok[k]) break;
+      const int hh = h + kdh[k], ww = wc + kdw[k], ll = l + kdl[k];
       if (hh < 0 || hh >= H || ww < 0 || ww >= W || ll < 0 || ll >= L) continue;
-      const float a = __half2float(act[((((size_t)b * L + ll) * H + hh) * W + ww) * cin + ci]);
+      const float a = __half2float(act[base + koff[k]]);
 #pragma unroll
       for (int co = 0; co < COUT; ++co) acc[k][co] = fmaf(a, d[co], acc[k][co]);
+    }
+    if (++f == F) {
+      f = 0;
+      if (++wc == W) {
+        wc = 0;
+        if (++h == H) { h = 0; ++b; }
+      }
     }
   }
 #pragma unroll
