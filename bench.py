@@ -404,7 +404,12 @@ def roofline(net, nat, past, n, dev, step_ms):
     fl = C.c_double()
     for i in range(nops):
         lib.cm_unet_op_info(plan.handle, i, tag, 128, C.byref(ty), C.byref(fl))
-        a = agg.setdefault(kinds[ty.value], {"ms": 0.0, "flops": 0.0, "launches": 0})
+        kind = kinds[ty.value]
+        # the sampling path runs each AttentionBlock (GroupNorm, in_proj, core, out_proj + residual) as ONE
+        # fused launch (attn_block_kernel): its four plan ops are one class, not conv / GN work
+        if ".attention." in tag.value.decode():
+            kind = "attn_block"
+        a = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
         a["ms"] += best[i]
         a["flops"] += fl.value * n
         a["launches"] += 1

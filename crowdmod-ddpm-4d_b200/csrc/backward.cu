@@ -998,29 +998,37 @@ temb_dense_wgrad_kernel(const float* __restrict__ dtemb, int ld, int B, const fl
     if (e == 0) grads[goff_b[k] + c] = bs0 + bs1;
   }
 }
+// blockDim = G * E: group gq walks the dense blocks k = gq, gq + G, ... ; the G partial sums are added in
+// group order (fixed) through shared memory
 __global__ void temb_dense_dgrad_kernel(const float* __restrict__ dtemb, int ld, const float* const* __restrict__ wd,
                                         const int* __restrict__ couts, const int* __restrict__ offs, int nblocks,
-                                        int E, float* __restrict__ ds2) {
-  extern __shared__ float drow[];   // [ld]
+                                        int E, int G, float* __restrict__ ds2) {
+  extern __shared__ float drow[];   // [ld] | [G][E]
+  float* part = drow + ld;
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < ld; i += blockDim.x) drow[i] = dtemb[(size_t)b * ld + i];
   __syncthreads();
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int k = 0; k < nblocks; ++k) {
-      const float* w = wd[k] + e;
-      const float* d = drow + offs[k];
-      const int co = couts[k];
-      int c = 0;
-      for (; c + 4 <= co; c += 4) {
-        a0 = fmaf(d[c], w[(size_t)c * E], a0);
-        a1 = fmaf(d[c + 1], w[(size_t)(c + 1) * E], a1);
-        a2 = fmaf(d[c + 2], w[(size_t)(c + 2) * E], a2);
-        a3 = fmaf(d[c + 3], w[(size_t)(c + 3) * E], a3);
-      }
-      for (; c < co; ++c) a0 = fmaf(d[c], w[(size_t)c * E], a0);
+  const int gq = threadIdx.x / E, e = threadIdx.x - gq * E;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = gq; k < nblocks; k += G) {
+    const float* w = wd[k] + e;
+    const float* d = drow + offs[k];
+    const int co = couts[k];
+    int c = 0;
+    for (; c + 4 <= co; c += 4) {
+      a0 = fmaf(d[c], w[(size_t)c * E], a0);
+      a1 = fmaf(d[c + 1], w[(size_t)(c + 1) * E], a1);
+      a2 = fmaf(d[c + 2], w[(size_t)(c + 2) * E], a2);
+      a3 = fmaf(d[c + 3], w[(size_t)(c + 3) * E], a3);
     }
-    ds2[(size_t)b * E + e] = (a0 + a1) + (a2 + a3);
+    for (; c < co; ++c) a0 = fmaf(d[c], w[(size_t)c * E], a0);
+  }
+  part[gq * E + e] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (gq == 0) {
+    float a = 0.f;
+    for (int q = 0; q < G; ++q) a += part[q * E + e];
+    ds2[(size_t)b * E + e] = a;
   }
 }
 int temb_dense_backward_enqueue(const float* dtemb, int ld, int B, const float* s2, int E, const float* const* wd,
@@ -1028,8 +1036,13 @@ int temb_dense_backward_enqueue(const float* dtemb, int ld, int B, const float* 
                                 const long long* goff_w, const long long* goff_b, float* ds2, cudaStream_t st) {
   temb_dense_wgrad_kernel<<<dim3((E + 127) / 128, ld), 128, 0, st>>>(dtemb, ld, B, s2, E, couts, offs, nblocks, grads,
                                                                     goff_w, goff_b);
-  const int T = E < 256 ? ((E + 31) / 32) * 32 : 256;
-  temb_dense_dgrad_kernel<<<B, T, (size_t)ld * sizeof(float), st>>>(dtemb, ld, wd, couts, offs, nblocks, E, ds2);
+  CM_CHECK(E <= 1024, "time-embedding width %d > 1024 unsupported", E);
+  int G = 1024 / E;
+  if (G > 8) G = 8;
+  if (G > nblocks) G = nblocks;
+  if (G < 1) G = 1;
+  temb_dense_dgrad_kernel<<<B, G * E, (size_t)(ld + G * E) * sizeof(float), st>>>(dtemb, ld, wd, couts, offs, nblocks,
+                                                                                  E, G, ds2);
   CM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,7 +7,7 @@ timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "== ref exit $?"; tail -c 600 gpurun_out/bench_ref.json
 python tools/profile_ops.py 64 gpurun_out/ops.json > gpurun_out/ops.txt 2>&1
 REPS=1 python tools/profile_ops.py 64 > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -k 'regex:conv_umma|conv_plane|gn_|attn_|first_conv|final_conv' -s 150 -c 75 --csv --log-file gpurun_out/launches.csv python tools/profile_ops.py 64 > gpurun_out/ncu_ll.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -k 'regex:conv_umma|conv_plane|gn_|attn_|first_conv|final_conv' -s 126 -c 63 --csv --log-file gpurun_out/launches.csv python tools/profile_ops.py 64 > gpurun_out/ncu_ll.log 2>&1
 echo "launchlist exit $?"
 REPS=1 python tools/profile_ops.py 64 > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k 'regex:conv_plane' -s 33 -c 3 -o gpurun_out/conv_plane_full python tools/profile_ops.py 64 > gpurun_out/ncu_full.log 2>&1
