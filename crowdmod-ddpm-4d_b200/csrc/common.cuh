@@ -172,6 +172,15 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* smem, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
 // 5-D im2col load (activations, NDHWC): coords {c, w, h, d, n} = first pixel of the column in
 // bounding-box coordinates, offsets {w, h, d} = filter tap.
 __device__ __forceinline__ void tma_load_im2col_5d(const void* desc, uint64_t* bar, void* smem,

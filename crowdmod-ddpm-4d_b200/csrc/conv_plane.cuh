@@ -37,6 +37,12 @@ struct PlaneParams {
   CUtensorMap amap;      // main source, tiled 5-D (C, W, H, D, N), box {BK, W+2, HB, R, 1}
   CUtensorMap xmap;      // optional 1x1x1 source over the same grid (same box)
   CUtensorMap bmap;      // packed weights [terms*cout][Ktot], K-major (as conv_umma)
+  CUtensorMap bmap3;     // th3 mode: the same weights as (k within slab, row, (td,th,tw) slab), box {BK, BN, 9}
+  int th3;               // 1: a stage = one (td, channel chunk): ONE A box with an H halo {BK, W+2, HB+2} whose
+                         // three th taps are row-offset descriptor views (+th*(W+2) rows), and the nine (th, tw)
+                         // weight slabs of each term in one 3-D TMA -> 3x fewer stages, 1/3 of the A ingest
+                         // (measured: every pipeline stage costs ~0.16 us on top of its MMAs)
+  int a_box_bytes;       // bytes one A load delivers (expect_tx)
   int H, W, D, Wp;       // plane geometry, Wp = W + 2
   int R, HB;             // unit = R planes x HB rows (R > 1 only with HB == H)
   int P;                 // positions per unit = R*HB*Wp
@@ -107,7 +113,8 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const int S = P.stages;
-  const int stage_bytes = P.a_stage_bytes + B_STAGE;       // multiple of 1024
+  const int b_term = (P.th3 ? 9 : 3) * B_TAP;              // bytes of one weight term per stage
+  const int stage_bytes = P.a_stage_bytes + TERMS * b_term;   // multiple of 1024
   uint8_t* tail = smem + S * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + PL_MAX_STAGES;
@@ -121,7 +128,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncm = P.cin_main / BK;
-  const int nks_main = 9 * ncm;                       // (td, th, chunk) steps
+  const int nks_main = (P.th3 ? 3 : 9) * ncm;         // (td, th, chunk) steps; th3: (td, chunk)
   const int nks = nks_main + P.cin_extra / BK;
   const uint32_t buf_cols = static_cast<uint32_t>(P.ntiles * NST);
   uint32_t tmem_cols = 32;
@@ -130,6 +137,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.amap);
     tma_prefetch_desc(&P.bmap);
+    if (P.th3) tma_prefetch_desc(&P.bmap3);
     if (P.cin_extra) tma_prefetch_desc(&P.xmap);
   }
   if (warp == 1 && lane == 0) {
@@ -165,7 +173,17 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + P.a_stage_bytes;
         if (elect_one()) {
-          if (ks < nks_main) {
+          if (ks < nks_main && P.th3) {
+            const uint32_t tx = ((P.dbg & 1) ? 0u : (uint32_t)P.a_box_bytes) + ((P.dbg & 2) ? 0u : (uint32_t)(TERMS * b_term));
+            if (tx) mbar_expect_tx(&full_bar[s], tx); else mbar_arrive(&full_bar[s]);
+            if (!(P.dbg & 1))
+              tma_load_tile_5d(&P.amap, &full_bar[s], sa, cc * BK, -1, U.h0 - 1, U.d0 + td - 1, U.n);
+            if (!(P.dbg & 2)) {
+#pragma unroll
+              for (int t = 0; t < TERMS; ++t)
+                tma_load_3d(&P.bmap3, &full_bar[s], sb + t * b_term, cc * BK, U.n_tile * BN + t * P.cout, td * 9);
+            }
+          } else if (ks < nks_main) {
             const uint32_t tx = ((P.dbg & 1) ? 0u : a_bytes) + ((P.dbg & 2) ? 0u : (uint32_t)B_STAGE);
             if (tx) mbar_expect_tx(&full_bar[s], tx); else mbar_arrive(&full_bar[s]);
             if (!(P.dbg & 1))
@@ -186,13 +204,14 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
             tma_load_tile_5d(&P.xmap, &full_bar[s], sa, xc * BK, -1, U.h0, U.d0, U.n);
 #pragma unroll
             for (int t = 0; t < TERMS; ++t)
-              tma_load_2d(&P.bmap, &full_bar[s], sb + t * B_TERM + 1 * B_TAP, 27 * P.cin_main + xc * BK,
+              tma_load_2d(&P.bmap, &full_bar[s], sb + t * b_term + 1 * B_TAP, 27 * P.cin_main + xc * BK,
                           U.n_tile * BN + t * P.cout);
           }
         }
         if (++cc == ncm) {
           cc = 0;
-          if (++th == 3) { th = 0; ++td; }
+          if (P.th3) ++td;
+          else if (++th == 3) { th = 0; ++td; }
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
@@ -221,20 +240,24 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
           if (!(P.dbg & 4)) {
             if (ks < nks_main) {
               uint32_t first = (ks == 0) ? 0u : 1u;
+              const int nth = P.th3 ? 3 : 1;
+              const uint32_t th_step = (static_cast<uint32_t>(P.Wp) * ROWB) >> 4;   // one grid row of the halo box
+              for (int th = 0; th < nth; ++th) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
+                for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-                for (int t = 0; t < TERMS; ++t) {
-                  const uint32_t b_lo = b_lo0 + ((t * B_TERM) >> 4) + 2 * k;
-                  uint32_t a_lo = a_lo0 + 2 * k;
-                  uint32_t d = d_base;
+                  for (int t = 0; t < TERMS; ++t) {
+                    const uint32_t b_lo = b_lo0 + ((t * b_term + th * 3 * B_TAP) >> 4) + 2 * k;
+                    uint32_t a_lo = a_lo0 + th * th_step + 2 * k;
+                    uint32_t d = d_base;
 #pragma unroll 2
-                  for (int r = 0; r < P.ntiles; ++r) {
-                    umma_f16_lohi(d, a_lo, b_lo, DESC_HI, IDESC, first);
-                    a_lo += TILE_LO;
-                    d += NST;
+                    for (int r = 0; r < P.ntiles; ++r) {
+                      umma_f16_lohi(d, a_lo, b_lo, DESC_HI, IDESC, first);
+                      a_lo += TILE_LO;
+                      d += NST;
+                    }
+                    first = 1u;
                   }
-                  first = 1u;
                 }
               }
             } else {
@@ -242,7 +265,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
               for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
                 for (int t = 0; t < TERMS; ++t) {
-                  const uint32_t b_lo = b_lo0 + ((t * B_TERM + B_TAP) >> 4) + 2 * k;
+                  const uint32_t b_lo = b_lo0 + ((t * b_term + B_TAP) >> 4) + 2 * k;
                   uint32_t a_lo = a_lo0 + 2 * k;
                   uint32_t d = d_base + BN;
 #pragma unroll 2

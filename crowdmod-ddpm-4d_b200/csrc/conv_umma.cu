@@ -296,6 +296,22 @@ int conv_enqueue(const ConvLaunch& L, cudaStream_t st) {
 // ================================ plane-tile conv (conv_plane.cuh) ================================
 namespace {
 
+// packed weights [rows][Ktot] viewed as (k within a tap slab, row, tap slab): box {bk, bn, 9} = the nine
+// (th, tw) slabs of one td, laid out slab-major in shared memory ([slab][bn rows][bk])
+int make_weight_map3(CUtensorMap* map, const __half* base, size_t rows, size_t ktot, int cin, int bk, int bn) {
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)rows, 27};
+  cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)cin * 2};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)bn, 9};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D weights) failed: %d (rows=%zu k=%zu cin=%d)", (int)r, rows,
+           ktot, cin);
+  return 0;
+}
+
 int make_plane_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int bk, int R,
                    int HB) {
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
@@ -354,10 +370,12 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
     CM_CUDA(cudaGetDevice(&dev));
     CM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int bk = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
+  int bk = (cin % 64 == 0 && cin_extra % 64 == 0) ? 64 : 32;
+  if (getenv("CM_PLANE_BK32")) bk = 32;                 // experiment (tools/plane_knock5.py): twice the stages, same MMAs and bytes
   int bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 32);
   while (bn > 32 && 3 * bn > 256) bn >>= 1;             // tw-stacked MMA: N = 3*BN <= 256
-  const int nst = 3 * bn, rowb = bk * 2;
+  const int nst = 3 * bn;
+  int rowb = bk * 2;
   const int max_tiles = 256 / nst;                      // two accumulator buffers in 512 TMEM columns
   if (max_tiles < 1) return 0;
   const long smem_cap = 220 * 1024;
@@ -397,23 +415,40 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
   const int P = R * HB * Wp;
   const int ntiles = (P + 127) / 128;
   PlaneParams& p = L->p;
-  if (int rc = make_plane_map(&p.amap, act, B, D, H, W, cin, bk, R, HB)) return rc;
+  // th3 mode (see PlaneParams::th3): single-plane units only; BK = 32 keeps the nine-slab weight stage small
+  static const bool no_th3 = getenv("CM_PLANE_NO_TH3") != nullptr;
+  bool th3 = !no_th3 && R == 1;
+  if (th3) {
+    // needs two stages of {A halo box, nine weight slabs per term} next to the epilogue buffers
+    const long a3 = ((long)(ntiles * 128 + 2 * Wp) * 64 + 1023) / 1024 * 1024;
+    const long stage3 = a3 + (long)terms * 3 * nst * 64;
+    if ((smem_cap - (tail_fixed + ybuf_bytes(ntiles))) / stage3 < 2) th3 = false;
+  }
+  if (th3) {
+    bk = 32;
+    rowb = bk * 2;
+  }
+  if (int rc = make_plane_map(&p.amap, act, B, D, H, W, cin, bk, R, th3 ? HB + 2 : HB)) return rc;
   if (cin_extra) {
     CM_CHECK(extra != nullptr, "extra source pointer missing");
     if (int rc = make_plane_map(&p.xmap, extra, B, D, H, W, cin_extra, bk, R, HB)) return rc;
   }
   const size_t ktot = conv_packed_k(0, cin, cin_extra);
   if (int rc = make_weight_map(&p.bmap, wpacked, (size_t)terms * cout, ktot, bk, bn)) return rc;
+  if (th3)
+    if (int rc = make_weight_map3(&p.bmap3, wpacked, (size_t)terms * cout, ktot, cin, bk, bn)) return rc;
+  p.th3 = th3 ? 1 : 0;
+  p.a_box_bytes = (th3 ? (HB + 2) * Wp : P) * rowb;
   p.H = H; p.W = W; p.D = D; p.Wp = Wp; p.R = R; p.HB = HB; p.P = P; p.ntiles = ntiles;
   p.units_per_sample = (D / R) * (H / HB);
   p.n_ntiles = cout / bn;
   p.n_units = B * p.units_per_sample * p.n_ntiles;
-  p.a_stage_bytes = (int)(((long)(ntiles * 128 + 8) * rowb + 1023) / 1024 * 1024);
+  p.a_stage_bytes = (int)(((long)(ntiles * 128 + (th3 ? 2 * Wp : 8)) * rowb + 1023) / 1024 * 1024);
   p.cin_main = cin; p.cin_extra = cin_extra; p.cout = cout; p.terms = terms;
   p.out_ld = cout;
   p.err_flag = device_error_flag();
   if (const char* e = getenv("CM_PLANE_DBG")) p.dbg = atoi(e);
-  const long stage = p.a_stage_bytes + (long)terms * nst * rowb;
+  const long stage = p.a_stage_bytes + (long)terms * (th3 ? 3 : 1) * nst * rowb;
   const long tail = tail_fixed + ybuf_bytes(ntiles);
   int stages = (int)((smem_cap - tail) / stage);
   if (stages > PL_MAX_STAGES) stages = PL_MAX_STAGES;
