@@ -29,8 +29,10 @@
 
 namespace cm {
 
-constexpr int PL_THREADS = 320;      // warp0 TMA, warp1 MMA, warps2-9 epilogue (two warps per TMEM lane quarter)
-constexpr int PL_EPI = 256;          // epilogue threads
+constexpr int PL_THREADS = 576;      // warp0 TMA, warp1 MMA, warps2-17 epilogue (four warps per TMEM lane quarter)
+constexpr int PL_EPI = 512;          // epilogue threads: with th3 stages the epilogue chain of a unit is longer than
+                                     // its main loop, so it gets 4 warps per scheduler instead of 2
+constexpr int PL_NJ = 4;             // store rows per epilogue thread (host: ntiles*128 <= PL_NJ * rows per pass)
 constexpr int PL_MAX_STAGES = 6;
 
 struct PlaneParams {
@@ -124,7 +126,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   float* colv = reinterpret_cast<float*>(tail + 256);      // [BN]
   float* side = reinterpret_cast<float*>(tail + 256 + 512);       // [ntiles*4 + 1][3][BN] block-boundary rows
   float* ybuf = side + (P.ntiles * 4 + 1) * 3 * BN;               // [ntiles*128][TLD]
-  float* sred = ybuf + (P.ntiles * 128 + 2) * TLD;                // [8 warps][BN][2] + [BN] shifts
+  float* sred = ybuf + (P.ntiles * 128 + 2) * TLD;                // [epilogue warps][BN][2] + [BN] shifts
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncm = P.cin_main / BK;
@@ -286,15 +288,17 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // TMEM lane quarter = warp % 4; the two warps of a quarter split the 16-column chunks.
+    // ===================== epilogue (warps 2..17) =====================
+    // TMEM lane quarter = warp % 4; the four warps of a quarter split the (M tile, 16-column chunk) items.
     const int quarter = warp & 3;
-    const int group = (warp - 2) >> 2;
+    const int group = (warp - 2) >> 2;                     // 0..3
     const int et = threadIdx.x - 64;
     const bool temb_uniform = P.temb != nullptr && P.temb_bstride == 0;
     constexpr int LPR = BN / 4;                            // lanes per row in the store phase
     constexpr int RPP = PL_EPI / LPR;                      // rows per store pass of the epilogue threads
-    constexpr int NJ = 8;                                  // store rows per thread (host: ntiles*128 <= NJ*RPP)
+    constexpr int NJ = PL_NJ;                              // store rows per thread (host: ntiles*128 <= NJ*RPP)
+    constexpr int NCH = BN / 16;                           // 16-column chunks per accumulator block
+    constexpr int NG = PL_EPI / 128;                       // warps per TMEM lane quarter
     const int plane = P.HB * P.Wp;
     const int sub_r = et / LPR, sub_c = (et % LPR) * 4;
     int it = 0;
@@ -359,25 +363,26 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       // (Y1 of its lane 0, Y2 of its lanes 0 and 1) and are added at read-out.  Fixed order -> the
       // result is deterministic.
 #pragma unroll 1
-      for (int r = 0; r < P.ntiles; ++r) {
+      for (int item = group; item < P.ntiles * NCH; item += NG) {
+        const int r = item / NCH, c = item - r * NCH;
         const int blk = r * 4 + quarter;
         const int row = blk * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * buf_cols + r * NST;
         float* sd = side + static_cast<size_t>(blk) * 3 * BN;
-#pragma unroll
-        for (int c0 = 0; c0 < BN / 16; c0 += 2) {
-          const int c = c0 + group;
+        {
           float y0[16], y1[16], y2[16];
           tmem_ld16_async(t_lane + c * 16, y0);
           tmem_ld16_async(t_lane + BN + c * 16, y1);
           tmem_ld16_async(t_lane + 2 * BN + c * 16, y2);
           tmem_ld_wait();
-          if (lane == 0) {
+          if (lane < 2) {                                  // 128-bit stores (side is 16-byte aligned, BN % 16 == 0)
+            float4* s1v = reinterpret_cast<float4*>(sd + c * 16);
+            float4* s2v = reinterpret_cast<float4*>(sd + (lane == 0 ? BN : 2 * BN) + c * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { sd[c * 16 + i] = y1[i]; sd[BN + c * 16 + i] = y2[i]; }
-          } else if (lane == 1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sd[2 * BN + c * 16 + i] = y2[i];
+            for (int i = 0; i < 4; ++i) {
+              if (lane == 0) s1v[i] = make_float4(y1[4 * i], y1[4 * i + 1], y1[4 * i + 2], y1[4 * i + 3]);
+              s2v[i] = make_float4(y2[4 * i], y2[4 * i + 1], y2[4 * i + 2], y2[4 * i + 3]);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -394,7 +399,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       // coalesced read-out: RPP rows per pass, LPR lanes per row
       float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = st1;   // GroupNorm partial sums of (v - cv)
 #pragma unroll
@@ -443,13 +448,13 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
           d[0] = st1.x; d[1] = st2.x; d[2] = st1.y; d[3] = st2.y;
           d[4] = st1.z; d[5] = st2.z; d[6] = st1.w; d[7] = st2.w;
         }
-        if (et < LPR) *reinterpret_cast<float4*>(sred + 8 * BN * 2 + sub_c) = cv;
+        if (et < LPR) *reinterpret_cast<float4*>(sred + (PL_EPI / 32) * BN * 2 + sub_c) = cv;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // ybuf / side are rewritten by the next unit
+      asm volatile("bar.sync 1, 512;" ::: "memory");       // ybuf / side are rewritten by the next unit
       if (P.stats_rec && et < BN) {
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-        for (int wv = 0; wv < PL_EPI / 32; ++wv) {             // fixed order over the 8 epilogue warps
+        for (int wv = 0; wv < PL_EPI / 32; ++wv) {             // fixed order over the epilogue warps
           a1 += sred[(wv * BN + et) * 2];
           a2 += sred[(wv * BN + et) * 2 + 1];
         }
@@ -457,7 +462,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
         const int uis = (U.d0 / P.R) * hblocks + U.h0 / P.HB;
         float4* rec = reinterpret_cast<float4*>(P.stats_rec) +
                       (static_cast<size_t>(U.n) * P.units_per_sample + uis) * P.cout + nn0 + et;
-        *rec = make_float4(sred[8 * BN * 2 + et], a1, a2, 0.f);
+        *rec = make_float4(sred[(PL_EPI / 32) * BN * 2 + et], a1, a2, 0.f);
       }
     }
   }

@@ -381,7 +381,7 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
   const long smem_cap = 220 * 1024;
   const long tail_fixed = 256 + 512 + 1024;
   auto ybuf_bytes = [&](int ntiles) {
-    return (long)(ntiles * 128 + 2) * (bn + 4) * 4 + (long)(ntiles * 4 + 1) * 3 * bn * 4 + (long)(8 * bn * 2 + bn) * 4;
+    return (long)(ntiles * 128 + 2) * (bn + 4) * 4 + (long)(ntiles * 4 + 1) * 3 * bn * 4 + (long)((PL_EPI / 32) * bn * 2 + bn) * 4;
   };
   // work unit: R planes x HB rows.  Score = useful MMA rows x SM fill of the last wave; ties go to
   // the larger unit (more reuse of every weight tile).
@@ -391,7 +391,7 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
     const int P = R * HB * Wp;
     const int ntiles = (P + 127) / 128;
     if (ntiles > max_tiles || R > 256 || HB > 256) return;
-    if (ntiles * 128 > 8 * (PL_EPI / (bn / 4))) return;    // NJ = 8 store rows per epilogue thread
+    if (ntiles * 128 > PL_NJ * (PL_EPI / (bn / 4))) return;    // PL_NJ store rows per epilogue thread
     const long a_stage = ((long)(ntiles * 128 + 8) * rowb + 1023) / 1024 * 1024;
     const long stage = a_stage + (long)terms * nst * rowb;
     if (2 * stage + tail_fixed + ybuf_bytes(ntiles) > smem_cap) return;
