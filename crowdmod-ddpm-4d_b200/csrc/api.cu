@@ -168,6 +168,7 @@ int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int ci
 int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, const float* gamma,
                   const float* beta, int B, int pixels, float eps, int silu, void* out_norm16,
                   void* out_raw16, void* stream) {
+  if (int e = kernels_init()) return e;   // the streaming kernels need their dynamic shared-memory attribute
   GnParams g{};
   g.src0 = src0; g.c0 = c0; g.src1 = src1; g.c1 = c1;
   g.gamma = gamma; g.beta = beta; g.B = B; g.pixels = pixels; g.eps = eps; g.silu = silu;
@@ -188,6 +189,26 @@ int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int head
   if (int e = kernels_init()) return e;
   return attn_core_enqueue(qkv, static_cast<__half*>(ctx16), B, S, C, heads,
                            static_cast<cudaStream_t>(stream));
+}
+
+int cm_op_attn_block(const float* x, const float* gamma, const float* beta, const float* w_in, const float* b_in,
+                     const float* w_out, const float* b_out, float* out32, void* out16, int B, int S, int C,
+                     int heads, float eps, void* stream) {
+  if (int e = kernels_init()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CM_CHECK(attn_block_supported(S, C, heads), "fused attention block: C=%d heads=%d S=%d not covered", C, heads, S);
+  __half* wpk = nullptr;    // hi|lo packed rows of in_proj ([2*3C][C]) then out_proj ([2*C][C])
+  CM_CUDA(cudaMalloc(&wpk, (size_t)2 * 4 * C * C * sizeof(__half)));
+  int rc = pack_conv_weights(w_in, nullptr, wpk, 3 * C, C, 0, 1, 2, 0, st);
+  if (!rc) rc = pack_conv_weights(w_out, nullptr, wpk + (size_t)6 * C * C, C, C, 0, 1, 2, 0, st);
+  if (!rc)
+    rc = attn_block_enqueue(x, gamma, beta, wpk, b_in, wpk + (size_t)6 * C * C, b_out, out32,
+                            static_cast<__half*>(out16), B, S, C, heads, eps, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(wpk);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
 }
 
 int cm_op_first_conv(const float* x, const float* past, const float* w, const float* bias,

@@ -145,6 +145,13 @@ CM_API int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, c
                   const float* beta, int B, int pixels, float eps, int silu, void* out_norm16,
                   void* out_raw16, void* stream);
 CM_API int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream);
+/* whole AttentionBlock of the sampling path (reference models/backbones/layers.py:5-18: GroupNorm(8) ->
+ * nn.MultiheadAttention(C, heads) self-attention -> + x) as ONE launch.  x, out32: fp32 [B][S][C] tokens
+ * (channels-last); w_in [3C][C] / b_in [3C] = mhsa.in_proj_weight / in_proj_bias, w_out [C][C] / b_out [C] =
+ * mhsa.out_proj.weight / .bias.  Covers C = 128, heads = 4, S <= 128 (returns an error otherwise). */
+CM_API int cm_op_attn_block(const float* x, const float* gamma, const float* beta, const float* w_in,
+                     const float* b_in, const float* w_out, const float* b_out, float* out32, void* out16,
+                     int B, int S, int C, int heads, float eps, void* stream);
 CM_API int cm_op_first_conv(const float* x, const float* past, const float* w, const float* bias,
                      float* out, int B, int H, int W, int P, int F, int cin, int cout,
                      void* stream);

@@ -139,6 +139,8 @@ def test_conv_umma_vs_scalar_restatement(nat, case):
 @pytest.mark.parametrize("B,pixels,c0,c1,silu", [
     (2, 3456, 32, 0, 1), (2, 3456, 64, 32, 1), (3, 432, 128, 64, 1), (2, 54, 128, 0, 0),
     (2, 54, 128, 128, 1), (1, 5376, 64, 32, 1),
+    # ragged slices of the streaming ring: pixel counts that do not divide by the slice / stage sizes
+    (5, 777, 32, 64, 1), (2, 1000, 96, 0, 1), (3, 2305, 32, 0, 0), (64, 432, 64, 0, 1), (1, 20000, 32, 0, 1),
 ])
 def test_gn_silu(nat, B, pixels, c0, c1, silu):
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -178,6 +180,35 @@ def test_attn_core(nat, B, S, C_):
     ref = (p @ v).transpose(1, 2).reshape(B, S, C_)
     # P, V and the output are fp16 MMA operands (2^-11 relative each); Q K^T is fp32-accurate (hi+lo)
     assert rel_l2(ctx.float(), ref) <= 7e-4
+
+
+@pytest.mark.parametrize("B,S", [(2, 54), (3, 84), (1, 12), (2, 1), (2, 16), (1, 100), (2, 128)])
+def test_attn_block_fused(nat, B, S):
+    """Fused AttentionBlock (layers.py:5-18) vs torch GroupNorm + nn.MultiheadAttention in fp32."""
+    C_, heads = 128, 4
+    torch.manual_seed(11)
+    x = torch.randn(B, S, C_, device="cuda") * 1.5 + 0.3
+    gn = torch.nn.GroupNorm(8, C_).cuda()
+    mha = torch.nn.MultiheadAttention(C_, heads, batch_first=True).cuda()
+    with torch.no_grad():
+        gn.weight.uniform_(0.5, 1.5)
+        gn.bias.uniform_(-0.5, 0.5)
+        mha.in_proj_bias.uniform_(-0.2, 0.2)
+        mha.out_proj.bias.uniform_(-0.2, 0.2)
+    out = torch.zeros(B, S, C_, device="cuda")
+    out16 = torch.zeros(B, S, C_, device="cuda", dtype=torch.half)
+    nat.check(nat.lib().cm_op_attn_block(nat.ptr(x), nat.ptr(gn.weight.data), nat.ptr(gn.bias.data),
+                                         nat.ptr(mha.in_proj_weight.data), nat.ptr(mha.in_proj_bias.data),
+                                         nat.ptr(mha.out_proj.weight.data), nat.ptr(mha.out_proj.bias.data),
+                                         nat.ptr(out), nat.ptr(out16), B, S, C_, heads, 1e-5, nat.current_stream()))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        h = gn(x.transpose(1, 2)).transpose(1, 2)            # GroupNorm over (C, tokens) per sample
+        ref = x + mha(h, h, h, need_weights=False)[0]
+    # fp16 MMA operands (h, P, V, ctx) with fp32 accumulation; the residual x is added in fp32
+    assert rel_l2(out, ref) <= 5e-4
+    assert rel_l2(out16.float(), ref) <= 1e-3
+    assert bool(torch.isfinite(out).all())
 
 
 @pytest.mark.parametrize("B,H,W,P,Fu,cin,cout", [(2, 12, 36, 5, 3, 3, 32), (1, 8, 12, 5, 3, 3, 64), (2, 4, 4, 2, 2, 4, 32)])
@@ -321,6 +352,9 @@ PLANE_CASES = [
     (0, 1, 8, 28, 24, 32, 32, 0, True),     # HERMES-CR-120 level 0
     (0, 5, 8, 8, 12, 32, 32, 0, True),      # ETH-UCY level 0
     (0, 150, 8, 12, 36, 32, 32, 0, True),   # more units than SMs: several units per persistent CTA
+    (0, 2, 8, 12, 36, 96, 32, 96, True),    # th3 stages: 3 chunks per td + 3 match_input slabs + residual
+    (0, 2, 4, 6, 18, 128, 64, 64, False),   # th3 stages at level 1: 4 chunks per td + 2 match_input slabs
+    (0, 3, 3, 12, 36, 64, 32, 0, True),     # odd depth and batch, 2 chunks per td, residual
 ]
 
 
