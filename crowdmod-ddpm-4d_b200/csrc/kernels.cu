@@ -377,10 +377,11 @@ __device__ __forceinline__ Chan3 chan_merge(const Chan3 a, const Chan3 b) {
   if (a.n == 0.f) return b;
   const float nn = a.n + b.n;
   const float delta = b.mean - a.mean;
+  const float w = __fdividef(b.n, nn);                 // one fast division per merge (these chains are serial)
   Chan3 r;
   r.n = nn;
-  r.mean = a.mean + delta * (b.n / nn);
-  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / nn);
+  r.mean = a.mean + delta * w;
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * w);
   return r;
 }
 
@@ -557,22 +558,42 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
       const float4* rp = reinterpret_cast<const float4*>(r.rec) + ((size_t)b * r.units) * cs;
       const float nk = (float)r.nvalid;
       const int uchunk = rcap / cs;
+      // every unit of a source covers the same number of rows, so the units of a channel combine without
+      // a serial chain of divisions: with d_k = mean_k - mean_0,  mean = mean_0 + sum(d_k)/U  and
+      // M2 = sum(M2_k) + n_unit * (sum(d_k^2) - sum(d_k)^2 / U)   (shifted -> no cancellation), fixed order.
+      // A thread owns channels tid and tid + GN2_T of the source (C <= 512); the sums stay in registers.
+      const float inv_nk = 1.0f / nk;
+      float m0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
       for (int u0 = 0; u0 < r.units; u0 += uchunk) {
         const int un = (r.units - u0) < uchunk ? (r.units - u0) : uchunk;
         __syncthreads();
         for (int i = tid; i < un * cs; i += GN2_T) rstage[i] = rp[(size_t)u0 * cs + i];
         __syncthreads();
-        for (int cl = tid; cl < cs; cl += GN2_T) {
-          Chan3 a{0.f, 0.f, 0.f};
-          if (u0 > 0) a = Chan3{(float)u0 * nk, chst[cbase + cl][0], chst[cbase + cl][1]};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cl = tid + e * GN2_T;
+          if (cl >= cs) break;
+          if (u0 == 0) {
+            const float4 v = rstage[cl];
+            m0[e] = v.x + v.y * inv_nk;
+          }
           for (int uidx = 0; uidx < un; ++uidx) {
             const float4 v = rstage[uidx * cs + cl];
-            const float d = v.y / nk;
-            a = chan_merge(a, Chan3{nk, v.x + d, fmaxf(v.z - v.y * d, 0.f)});
+            const float d = v.y * inv_nk;                       // unit mean - unit shift
+            const float dk = (v.x + d) - m0[e];
+            s1[e] += dk;
+            s2[e] = fmaf(dk, dk, s2[e]);
+            q[e] += fmaxf(v.z - v.y * d, 0.f);
           }
-          chst[cbase + cl][0] = a.mean;
-          chst[cbase + cl][1] = a.m2;
         }
+      }
+      const float invU = 1.0f / (float)r.units;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cl = tid + e * GN2_T;
+        if (cl >= cs) break;
+        chst[cbase + cl][0] = m0[e] + s1[e] * invU;
+        chst[cbase + cl][1] = q[e] + nk * fmaxf(s2[e] - s1[e] * s1[e] * invU, 0.f);
       }
     }
   } else {
@@ -587,9 +608,18 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   if (tid < 8) {
     Chan3 a{0.f, 0.f, 0.f};
     if (from_rec) {
-      const float nc = (float)p.pixels;
-      for (int k2 = 0; k2 < cg_ch; ++k2)
-        a = chan_merge(a, Chan3{nc, chst[tid * cg_ch + k2][0], chst[tid * cg_ch + k2][1]});
+      // the channels of a group all hold p.pixels values: same shifted equal-count combination
+      const float nc = (float)p.pixels, m0 = chst[tid * cg_ch][0];
+      float s1 = 0.f, s2 = 0.f, q = 0.f;
+      for (int k2 = 0; k2 < cg_ch; ++k2) {
+        const float dk = chst[tid * cg_ch + k2][0] - m0;
+        s1 += dk;
+        s2 = fmaf(dk, dk, s2);
+        q += chst[tid * cg_ch + k2][1];
+      }
+      a.n = nc * (float)cg_ch;
+      a.mean = m0 + s1 / (float)cg_ch;
+      a.m2 = q + nc * fmaxf(s2 - s1 * s1 / (float)cg_ch, 0.f);
     } else
     for (int sidx = 0; sidx < stat_slices; ++sidx) {
       const float* o = ptri + (sidx * 8 + tid) * 3;
