@@ -531,7 +531,34 @@ int gn_backward_enqueue(const GnBwdParams& p, float* partial, cudaStream_t st) {
   const int chunks = gn_bwd_chunks(p.B, p.pixels);
   gn_bwd_sums_kernel<<<dim3(chunks, p.B), T, (size_t)T * 32, st>>>(p, chunks, partial);
   gn_bwd_apply_kernel<<<dim3(chunks, p.B), T, (size_t)(2 * C + 16) * 4, st>>>(p, chunks, partial);
-  gn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(p.chsum, p.B, C, p.dgamma, p.dbeta);
+  // dgamma / dbeta = batch sums of chsum: per GroupNorm here, or for all of them in one launch at the end of
+  // the backward (gn_backward_params_all_enqueue) when the caller keeps one chsum region per GroupNorm
+  if (p.dgamma) gn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(p.chsum, p.B, C, p.dgamma, p.dbeta);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// one CTA per GroupNorm: tab[g] = {chsum offset (floats), C, dgamma offset, dbeta offset (floats into grads)}
+__global__ void gn_bwd_params_all_kernel(const float* __restrict__ chsum_base, const long long* __restrict__ tab,
+                                         int B, float* __restrict__ grads) {
+  const long long* t = tab + (size_t)blockIdx.x * 4;
+  const float* chsum = chsum_base + t[0];
+  const int C = (int)t[1];
+  float* dgamma = grads + t[2];
+  float* dbeta = grads + t[3];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int b = 0; b < B; ++b) {
+      a1 += chsum[((size_t)b * C + c) * 2];
+      a2 += chsum[((size_t)b * C + c) * 2 + 1];
+    }
+    dbeta[c] = a1;
+    dgamma[c] = a2;
+  }
+}
+int gn_backward_params_all_enqueue(const float* chsum_base, const long long* tab, int n_gn, int B, float* grads,
+                                   cudaStream_t st) {
+  gn_bwd_params_all_kernel<<<n_gn, 256, 0, st>>>(chsum_base, tab, B, grads);
   CM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -67,6 +67,10 @@ struct GnBwdParams {
 // partial: scratch of B * gn_bwd_chunks(B, pixels) * C * 2 floats (chunks <= 32)
 int gn_bwd_chunks(int B, int pixels);
 int gn_backward_enqueue(const GnBwdParams& p, float* partial, cudaStream_t st);
+// dgamma / dbeta of every GroupNorm in one launch (GnBwdParams::dgamma == nullptr defers them): tab[g] =
+// {chsum offset, C, dgamma offset, dbeta offset} in floats
+int gn_backward_params_all_enqueue(const float* chsum_base, const long long* tab, int n_gn, int B, float* grads,
+                                   cudaStream_t st);
 
 // ---- attention core backward (layers.py:16): qkv fp32 [B*S][3C] saved by the forward,
 //      dctx fp32 [B*S][C] -> dqkv fp32 [B*S][3C] (=) ----

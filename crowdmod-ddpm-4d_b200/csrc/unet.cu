@@ -105,6 +105,8 @@ struct cm_unet {
   float* temb_table = nullptr;          // [table_steps][temb_ld]
   const float** d_wd = nullptr;
   const float** d_bd = nullptr;
+  long long* d_gn_tab = nullptr;        // per GroupNorm {chsum offset, C, dgamma offset, dbeta offset}
+  std::vector<long long> gn_tab_host;
   long long* d_goff_w = nullptr;        // flat-gradient offsets of every block's dense_1 weight / bias
   long long* d_goff_b = nullptr;
   int* d_couts = nullptr;
@@ -761,7 +763,7 @@ int reserve_train(cm_unet* u, int batch) {
   }
   const size_t o_stats = take((size_t)u->n_gn * batch * 16 * 4);
   const size_t o_part = take((size_t)batch * 32 * Cmax * 2 * 4);
-  const size_t o_chsum = take((size_t)batch * Cmax * 2 * 4);
+  const size_t o_chsum = take((size_t)u->n_gn * batch * Cmax * 2 * 4);   // one region per GroupNorm
   const size_t o_zero = off;
   const size_t o_G = take(u->g_elems * 4);
   const size_t o_colsum = take((size_t)batch * u->colsum_per_sample * 4);
@@ -884,6 +886,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
   if (int e = auto_scale_enqueue(d_eps, n_eps, 64.f, u->loss_scale, u->max_word, st)) return e;
   nl += 2;
   std::vector<char> written(u->tens.size(), 0);
+  std::vector<long long> gn_tab;        // {chsum offset, C, dgamma offset, dbeta offset} per GroupNorm, plan order
   // bring-up: CM_BWD_TRACE=1 brackets every backward stage with CUDA events and prints a table
   static const bool trace = getenv("CM_BWD_TRACE") != nullptr;
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -935,11 +938,17 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           g.init1 = !written[op.src1];
           written[op.src1] = 1;
         }
-        g.chsum = u->gn_chsum;
-        g.dgamma = gp(op.gamma);
-        g.dbeta = gp(op.beta);
+        // per-GroupNorm channel sums; dgamma / dbeta of all of them are reduced over the batch in ONE launch
+        // after the op loop (27 tiny launches -> 1)
+        g.chsum = u->gn_chsum + (size_t)op.gn_index * B * u->max_gn_channels * 2;
+        g.dgamma = nullptr;
+        g.dbeta = nullptr;
+        gn_tab.push_back((long long)((size_t)op.gn_index * B * u->max_gn_channels * 2));
+        gn_tab.push_back((long long)(u->tens[op.src0].C + (op.src1 >= 0 ? u->tens[op.src1].C : 0)));
+        gn_tab.push_back((long long)u->grad_off[op.gamma]);
+        gn_tab.push_back((long long)u->grad_off[op.beta]);
         if (int e = gn_backward_enqueue(g, u->gn_bwd_partial, st)) return e;
-        nl += 3;
+        nl += 2;
         mark("gn_bwd " + op.tag);
       } break;
       case OP_CONV: {
@@ -1014,6 +1023,20 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
         mark("first_wgrad " + op.tag);
       } break;
     }
+  }
+  // ---- dgamma / dbeta of every GroupNorm: one launch ----
+  if (!gn_tab.empty()) {
+    const size_t bytes = gn_tab.size() * sizeof(long long);
+    if (!u->d_gn_tab || u->gn_tab_host != gn_tab) {
+      if (!u->d_gn_tab) CM_CUDA(cudaMalloc(&u->d_gn_tab, (size_t)u->n_gn * 4 * sizeof(long long)));
+      CM_CUDA(cudaMemcpyAsync(u->d_gn_tab, gn_tab.data(), bytes, cudaMemcpyHostToDevice, st));
+      CM_CUDA(cudaStreamSynchronize(st));      // gn_tab is a local: the copy must finish before it goes away
+      u->gn_tab_host = gn_tab;
+    }
+    if (int e = gn_backward_params_all_enqueue(u->gn_chsum, u->d_gn_tab, (int)(gn_tab.size() / 4), B, grads, st))
+      return e;
+    ++nl;
+    mark("gn_params all");
   }
   // ---- time-embedding MLP (embeddings.py:22-34) and the per-block dense_1 (layers.py:35,62) ----
   const size_t nE = (size_t)B * E;
@@ -1100,6 +1123,7 @@ int cm_unet_destroy(cm_unet* u) {
   cudaFree(u->temb_table);
   cudaFree(u->d_wd);
   cudaFree(u->d_bd);
+  cudaFree(u->d_gn_tab);
   cudaFree(u->d_goff_w);
   cudaFree(u->d_goff_b);
   cudaFree(u->d_couts);
