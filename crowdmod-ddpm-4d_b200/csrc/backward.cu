@@ -556,6 +556,26 @@ __global__ void gn_bwd_params_all_kernel(const float* __restrict__ chsum_base, c
     dgamma[c] = a2;
   }
 }
+// every conv's bias gradient (batch sum of its per-sample channel sums) in one launch:
+// tab[e] = {source offset (floats from base), row stride, channels, gradient offset (floats into grads)}
+__global__ void rowsum_all_kernel(const float* __restrict__ base, const long long* __restrict__ tab, int B,
+                                  float* __restrict__ grads) {
+  const long long* t = tab + (size_t)blockIdx.x * 4;
+  const float* src = base + t[0];
+  const int ld = (int)t[1], C = (int)t[2];
+  float* out = grads + t[3];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += src[(size_t)b * ld + c];
+    out[c] = a;
+  }
+}
+int rowsum_all_enqueue(const float* base, const long long* tab, int n, int B, float* grads, cudaStream_t st) {
+  rowsum_all_kernel<<<n, 128, 0, st>>>(base, tab, B, grads);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int gn_backward_params_all_enqueue(const float* chsum_base, const long long* tab, int n_gn, int B, float* grads,
                                    cudaStream_t st) {
   gn_bwd_params_all_kernel<<<n_gn, 256, 0, st>>>(chsum_base, tab, B, grads);

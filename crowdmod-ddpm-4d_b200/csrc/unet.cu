@@ -105,6 +105,8 @@ struct cm_unet {
   float* temb_table = nullptr;          // [table_steps][temb_ld]
   const float** d_wd = nullptr;
   const float** d_bd = nullptr;
+  long long* d_rs_tab = nullptr;        // per conv bias {channel-sum offset, row stride, cout, gradient offset}
+  std::vector<long long> rs_tab_host;
   long long* d_gn_tab = nullptr;        // per GroupNorm {chsum offset, C, dgamma offset, dbeta offset}
   std::vector<long long> gn_tab_host;
   long long* d_goff_w = nullptr;        // flat-gradient offsets of every block's dense_1 weight / bias
@@ -887,6 +889,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
   nl += 2;
   std::vector<char> written(u->tens.size(), 0);
   std::vector<long long> gn_tab;        // {chsum offset, C, dgamma offset, dbeta offset} per GroupNorm, plan order
+  std::vector<long long> rs_tab;        // {channel-sum offset in the training arena, row stride, cout, bias-grad offset}
   // bring-up: CM_BWD_TRACE=1 brackets every backward stage with CUDA events and prints a table
   static const bool trace = getenv("CM_BWD_TRACE") != nullptr;
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -966,13 +969,13 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
         if (int e = cast_colsum_enqueue(u->g32[op.out], u->g16[op.out], fan, fan_init, cs, cs_ld, B, pix,
                                         op.cout, st))
           return e;
-        if (op.bias >= 0) {
-          if (int e = rowsum_enqueue(cs, gp(op.bias), B, op.cout, cs_ld, 0, st)) return e;
-          ++nl;
-        }
-        if (op.bias2 >= 0) {
-          if (int e = rowsum_enqueue(cs, gp(op.bias2), B, op.cout, cs_ld, 0, st)) return e;
-          ++nl;
+        // bias gradients = batch sums of the channel sums: all convs in one launch after the op loop
+        for (int bidx : {op.bias, op.bias2}) {
+          if (bidx < 0) continue;
+          rs_tab.push_back((long long)(cs - reinterpret_cast<const float*>(u->tarena)));
+          rs_tab.push_back((long long)cs_ld);
+          rs_tab.push_back((long long)op.cout);
+          rs_tab.push_back((long long)u->grad_off[bidx]);
         }
         mark("cast_colsum " + op.tag);
         if (op.dplaunch.ok) {
@@ -1023,6 +1026,24 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
         mark("first_wgrad " + op.tag);
       } break;
     }
+  }
+  // ---- conv bias gradients: one launch ----
+  if (!rs_tab.empty()) {
+    if (!u->d_rs_tab || u->rs_tab_host != rs_tab) {
+      if (u->d_rs_tab && u->rs_tab_host.size() < rs_tab.size()) {
+        cudaFree(u->d_rs_tab);
+        u->d_rs_tab = nullptr;
+      }
+      if (!u->d_rs_tab) CM_CUDA(cudaMalloc(&u->d_rs_tab, rs_tab.size() * sizeof(long long)));
+      CM_CUDA(cudaMemcpyAsync(u->d_rs_tab, rs_tab.data(), rs_tab.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+      CM_CUDA(cudaStreamSynchronize(st));
+      u->rs_tab_host = rs_tab;
+    }
+    if (int e = rowsum_all_enqueue(reinterpret_cast<const float*>(u->tarena), u->d_rs_tab, (int)(rs_tab.size() / 4), B,
+                                   grads, st))
+      return e;
+    ++nl;
+    mark("bias_sums all");
   }
   // ---- dgamma / dbeta of every GroupNorm: one launch ----
   if (!gn_tab.empty()) {
@@ -1123,6 +1144,7 @@ int cm_unet_destroy(cm_unet* u) {
   cudaFree(u->temb_table);
   cudaFree(u->d_wd);
   cudaFree(u->d_bd);
+  cudaFree(u->d_rs_tab);
   cudaFree(u->d_gn_tab);
   cudaFree(u->d_goff_w);
   cudaFree(u->d_goff_b);
