@@ -244,8 +244,8 @@ int rowsum_enqueue(const float* in, float* out, int B, int C, int ld, int accumu
 // =============================================================================================
 // G -> nn.Conv3d weight-gradient layout
 // =============================================================================================
-__global__ void unpack_wgrad_kernel(int fwd_mode, const float* __restrict__ G, float* __restrict__ dw,
-                                    float* __restrict__ dwx, int cout, int cin, int cinx, int perm) {
+__device__ __forceinline__ void unpack_wgrad_body(int fwd_mode, const float* __restrict__ G, float* __restrict__ dw,
+                                                  float* __restrict__ dwx, int cout, int cin, int cinx, int perm) {
   const int taps = (fwd_mode == 3) ? 1 : 27;
   const size_t n_main = (size_t)cout * cin * taps;
   const size_t total = n_main + (size_t)cout * cinx;
@@ -293,6 +293,23 @@ __global__ void unpack_wgrad_kernel(int fwd_mode, const float* __restrict__ G, f
     }
     dw[idx] = v;
   }
+}
+__global__ void unpack_wgrad_kernel(int fwd_mode, const float* __restrict__ G, float* __restrict__ dw,
+                                    float* __restrict__ dwx, int cout, int cin, int cinx, int perm) {
+  unpack_wgrad_body(fwd_mode, G, dw, dwx, cout, cin, cinx, perm);
+}
+// every conv of the plan in one launch (blockIdx.y = conv): tab[e] = {fwd_mode, G offset, dw offset,
+// dwx offset or -1, cout, cin, cinx, perm}; offsets in floats from Gbase / grads
+__global__ void unpack_wgrad_all_kernel(const long long* __restrict__ tab, const float* __restrict__ Gbase,
+                                        float* __restrict__ grads) {
+  const long long* t = tab + (size_t)blockIdx.y * 8;
+  unpack_wgrad_body((int)t[0], Gbase + t[1], grads + t[2], t[3] >= 0 ? grads + t[3] : nullptr, (int)t[4], (int)t[5],
+                    (int)t[6], (int)t[7]);
+}
+int unpack_wgrad_all_enqueue(const long long* tab, int n, const float* Gbase, float* grads, cudaStream_t st) {
+  unpack_wgrad_all_kernel<<<dim3(64, n), 256, 0, st>>>(tab, Gbase, grads);
+  CM_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int unpack_wgrad_enqueue(int fwd_mode, const float* G, float* dw, float* dwx, int cout, int cin,

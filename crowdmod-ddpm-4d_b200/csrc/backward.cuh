@@ -69,6 +69,7 @@ int gn_bwd_chunks(int B, int pixels);
 int gn_backward_enqueue(const GnBwdParams& p, float* partial, cudaStream_t st);
 // dgamma / dbeta of every GroupNorm in one launch (GnBwdParams::dgamma == nullptr defers them): tab[g] =
 // {chsum offset, C, dgamma offset, dbeta offset} in floats
+int unpack_wgrad_all_enqueue(const long long* tab, int n, const float* Gbase, float* grads, cudaStream_t st);
 int rowsum_all_enqueue(const float* base, const long long* tab, int n, int B, float* grads, cudaStream_t st);
 int gn_backward_params_all_enqueue(const float* chsum_base, const long long* tab, int n_gn, int B, float* grads,
                                    cudaStream_t st);

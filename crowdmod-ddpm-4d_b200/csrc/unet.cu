@@ -105,6 +105,8 @@ struct cm_unet {
   float* temb_table = nullptr;          // [table_steps][temb_ld]
   const float** d_wd = nullptr;
   const float** d_bd = nullptr;
+  long long* d_up_tab = nullptr;        // per conv weight-gradient unpack parameters
+  std::vector<long long> up_tab_host;
   long long* d_rs_tab = nullptr;        // per conv bias {channel-sum offset, row stride, cout, gradient offset}
   std::vector<long long> rs_tab_host;
   long long* d_gn_tab = nullptr;        // per GroupNorm {chsum offset, C, dgamma offset, dbeta offset}
@@ -889,6 +891,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
   nl += 2;
   std::vector<char> written(u->tens.size(), 0);
   std::vector<long long> gn_tab;        // {chsum offset, C, dgamma offset, dbeta offset} per GroupNorm, plan order
+  std::vector<long long> up_tab;        // {mode, G offset, dw offset, dwx offset | -1, cout, cin, cinx, perm} per conv
   std::vector<long long> rs_tab;        // {channel-sum offset in the training arena, row stride, cout, bias-grad offset}
   // bring-up: CM_BWD_TRACE=1 brackets every backward stage with CUDA events and prints a table
   static const bool trace = getenv("CM_BWD_TRACE") != nullptr;
@@ -999,11 +1002,12 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
         mark("dgrad " + op.tag);
         if (int e = wgrad_enqueue(op.wlaunch, st)) return e;
         mark("wgrad " + op.tag);
-        if (int e = unpack_wgrad_enqueue(op.mode, u->G + op.g_off, gp(op.w), op.wx >= 0 ? gp(op.wx) : nullptr,
-                                         op.cout, op.cin, op.cin_extra, 1, st))
-          return e;
-        nl += 4;
-        mark("unpack " + op.tag);
+        // packed-K scratch -> nn.Conv3d weight layout: all convs in one launch after the op loop
+        for (long long v : {(long long)op.mode, (long long)op.g_off, (long long)u->grad_off[op.w],
+                            op.wx >= 0 ? (long long)u->grad_off[op.wx] : -1LL, (long long)op.cout, (long long)op.cin,
+                            (long long)op.cin_extra, 1LL})
+          up_tab.push_back(v);
+        nl += 3;
       } break;
       case OP_ATTN: {
         CM_CHECK(written[op.ctx], "backward: gradient of '%s' output missing", op.tag.c_str());
@@ -1027,11 +1031,28 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
       } break;
     }
   }
+  // ---- weight gradients out of the packed-K scratch: one launch ----
+  if (!up_tab.empty()) {
+    if (!u->d_up_tab || u->up_tab_host != up_tab) {
+      if (u->d_up_tab && u->up_tab_host.size() < up_tab.size()) {
+        cudaFree(u->d_up_tab);
+        u->d_up_tab = nullptr;
+      }
+      if (!u->d_up_tab) CM_CUDA(cudaMalloc(&u->d_up_tab, up_tab.size() * sizeof(long long)));
+      CM_CUDA(cudaMemcpyAsync(u->d_up_tab, up_tab.data(), up_tab.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+      CM_CUDA(cudaStreamSynchronize(st));
+      u->up_tab_host = up_tab;
+    }
+    if (int e = unpack_wgrad_all_enqueue(u->d_up_tab, (int)(up_tab.size() / 8), u->G, grads, st)) return e;
+    ++nl;
+    mark("unpack all");
+  }
   // ---- conv bias gradients: one launch ----
   if (!rs_tab.empty()) {
     if (!u->d_rs_tab || u->rs_tab_host != rs_tab) {
       if (u->d_rs_tab && u->rs_tab_host.size() < rs_tab.size()) {
-        cudaFree(u->d_rs_tab);
+        cudaFree(u->d_up_tab);
+  cudaFree(u->d_rs_tab);
         u->d_rs_tab = nullptr;
       }
       if (!u->d_rs_tab) CM_CUDA(cudaMalloc(&u->d_rs_tab, rs_tab.size() * sizeof(long long)));
