@@ -11,7 +11,14 @@ A "step" is ONE full reverse chain (T denoiser evaluations + T fused updates) ov
   python bench.py --gpus N --steps K --warmup W            (native arm; torchrun for N>1)
   python bench.py --impl reference ...                     (CPU oracle port of the reference path)
 
-Prints ONE JSON line on rank 0 (see the keys at the bottom).
+Prints ONE JSON line on rank 0.  Besides the contract keys it carries
+  roofline      the tcgen05 conv class of one denoiser step: achieved = EXECUTED FLOPs / summed CUDA-event
+                time (the UpSample convs count their 8-tap phase convs), algorithmic_equiv = the dense
+                27-tap formulation of SURVEY.md §8(d) over the same time, reported separately
+  train         BASELINE config #4 (HERMES-CR-120.yml training step) through DDPM_model
+  extra         the other BASELINE configs / batches: n = 1280 (generate_metrics' production batch; under
+                torchrun the 1280 samples are split over the ranks = strong scaling), ATC_medium (#3),
+                ETH-UCY (#5); one timed chain each
 """
 import argparse
 import ctypes as C
@@ -28,13 +35,27 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ATC = dict(input_channels=3, output_channels=3, num_res_blocks=1, base_channels=32,
-           base_channels_multiples=[1, 2, 4], apply_attention=[False, False, True, False],
-           dropout_rate=0.1, time_multiple=4, condition="Past")
-ROWS, COLS, PAST, FUT = 12, 36, 5, 3
 T_STEPS, SCALE = 1000, 0.5
 UNIT = "sequences/s"
 METRIC = "sampled sequences/sec (full T-step DDPM chain)"
+
+
+def unet_kwargs(base=32, attn=(False, False, True, False)):
+    return dict(input_channels=3, output_channels=3, num_res_blocks=1, base_channels=base,
+                base_channels_multiples=[1, 2, 4], apply_attention=list(attn), dropout_rate=0.1,
+                time_multiple=4, condition="Past")
+
+
+# the five BASELINE.json configs by tensor shape (SURVEY.md §8d "Config -> shapes")
+WORKLOADS = {
+    "atc": dict(cfg="config/ATC.yml", rows=12, cols=36, past=5, fut=3, unet=unet_kwargs()),
+    "atc_medium": dict(cfg="config/ATC_medium.yml", rows=12, cols=36, past=8, fut=8,
+                       unet=unet_kwargs(64, (False, False, True))),
+    "ethucy": dict(cfg="config/ETHUCY_ddpm.yml", rows=8, cols=12, past=5, fut=3, unet=unet_kwargs()),
+    "hermes": dict(cfg="config/HERMES-CR-120.yml", rows=28, cols=24, past=5, fut=3, unet=unet_kwargs()),
+}
+ATC = WORKLOADS["atc"]["unet"]
+ROWS, COLS, PAST, FUT = 12, 36, 5, 3
 
 
 def synthetic_macroprops(n, channels, rows, cols, frames, seed, device="cpu"):
@@ -150,7 +171,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": chain_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic macroprops, random-init weights (seed 42)",
-        "config": workload_config(n, args.gpus, None),
+        "config": workload_config(n, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -158,13 +179,37 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n, gpus, terms):
+def workload_config(n, gpus):
+    """Identical in both arms (the driver compares the two `config` objects)."""
     return {"workload": "config/ATC.yml: full 1000-step DDPM sampling, batch 64 per GPU, UNet base 32 "
                         "mult [1,2,4], grid 12x36, past 5 + future 3",
             "samples_per_gpu": n, "global_samples": n * gpus, "timesteps": T_STEPS,
-            "parallelism": f"sample-sharded x{gpus}, no collective", "weight_terms": terms,
+            "parallelism": f"sample-sharded x{gpus}, no collective",
             "l2_flush": "256 MiB buffer written between timed chains; per-step working set (~1 GB) > L2",
             "noise": "in-kernel Philox (device-resident), x_T ~ N(0,I)"}
+
+
+def make_cfg(name):
+    """The nested MODEL.DDPM.UNET config (reference config/ATC.yml / HERMES-CR-120.yml schema) of a workload."""
+    from crowdmod_ddpm_4d_b200.utils.myparser import YamlParser
+    w = WORKLOADS[name]
+    u = w["unet"]
+    return YamlParser({
+        "DATA_FS": {"OUTPUT_DIR": "/tmp/crowdmod_bench_out", "SAVE_DIR": "/tmp/crowdmod_bench_models/"},
+        "MACROPROPS": {"ROWS": w["rows"], "COLS": w["cols"]},
+        "DATASET": {"NAME": name, "PAST_LEN": w["past"], "FUTURE_LEN": w["fut"], "BATCH_SIZE": 64},
+        "MODEL": {"NAME": "{}_B_TE{}_PL{}_FL{}_CE{}_{}.pth", "NSAMPLES": 1280, "NSAMPLES4PLOTS": 20,
+                  "DDPM": {"SAMPLER": "DDPM", "TIMESTEPS": T_STEPS, "SCALE": SCALE, "SIGMA": 0.001,
+                           "DDIM_DIVIDER": 2, "GUIDANCE": "None", "LAMBDA_GUIDANCE": 0.004,
+                           "CHECKPOINTS_TO_KEEP": 7,
+                           "UNET": {"CONDITION": "Past", "NUM_RES_BLOCKS": u["num_res_blocks"],
+                                    "BASE_CH": u["base_channels"], "BASE_CH_MULT": u["base_channels_multiples"],
+                                    "APPLY_ATTENTION": u["apply_attention"], "DROPOUT_RATE": u["dropout_rate"],
+                                    "TIME_EMB_MULT": u["time_multiple"],
+                                    "TRAIN": {"EPOCHS": 200, "SOLVER": {
+                                        "LR": 5e-5, "WEIGHT_DECAY": 3e-3, "BETAS": [0.5, 0.999],
+                                        "SCHEDULER": {"FACTOR": 0.5, "PATIENCE": 10, "MIN_LR": 1e-6}}}}}},
+    })
 
 
 def run_native(args, rank, world, local_rank):
@@ -220,6 +265,8 @@ def run_native(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
+    graph_launches = 0
+    rebuilt = 0
     barrier()
     for k in range(args.steps):
         flush.fill_(k)
@@ -227,6 +274,9 @@ def run_native(args, rank, world, local_rank):
         chain_device(k)
         ev[k][1].record()
         launches += net.last_chain_launches(ROWS, COLS, PAST, FUT)
+        gl, rb = net.last_chain_graph_stats(ROWS, COLS, PAST, FUT)
+        graph_launches += gl
+        rebuilt += int(rb)
     barrier()
     clk = clocks.stop() if clocks else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -247,29 +297,46 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    roof = None
+    if rank == 0:
+        roof = roofline(net, nat, past, n, dev, ms / args.steps / args.timesteps)
+    del net, flush
+    torch.cuda.empty_cache()
+
     train = None
     if not args.no_train:
         train = train_bench(rank, world, dev, cpu_baseline=not args.no_cpu_baseline)
+    extra = None
+    if not args.no_extras:
+        extra = extras_bench(rank, world, dev)
 
     if rank == 0:
         total = n * world * args.steps
         value = total / (ms / 1e3)
         e2e = total / (ms_e2e / 1e3)
+        cfg = workload_config(n, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate",
             "data": "synthetic macroprops, random-init weights (seed 42)",
-            "config": workload_config(n, world, terms),
+            "config": cfg,
+            "weight_terms": terms,
             "denoiser_step_ms": ms / args.steps / args.timesteps,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": past_host.numel() * 4,
                     "d2h_bytes_per_step": x0_host.numel() * 4},
             "gpu_launches": launches,
+            "graph": {"cuda_graph_launches_in_timed_region": graph_launches, "chains": args.steps,
+                      "graphs_rebuilt_in_timed_region": rebuilt,
+                      "kind": "whole T-step chain = one graph (conditional WHILE node)"
+                      if graph_launches == args.steps else "one graph per denoiser step, replayed T times"},
             "clocks": clk,
+            "roofline": roof,
         }
-        line["roofline"] = roofline(net, nat, past, n, dev, ms / args.steps / args.timesteps)
         if train is not None:
             line["train"] = train
+        if extra is not None:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             s_it = cpu_oracle_sample(n, args.ref_iters, threads)
@@ -282,32 +349,92 @@ def run_native(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---- other BASELINE configs / batches: one timed full chain each ------------------------------------------------
+def extras_bench(rank, world, dev):
+    import torch.distributed as dist
+    from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
+    from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM, ddpm_coefficients, shard_samples
+
+    tsteps, coef = ddpm_coefficients(DDPM(timesteps=T_STEPS, scale=SCALE))
+    ts_short, coef_short = ddpm_coefficients(DDPM(timesteps=8, scale=SCALE))
+
+    def one(name, n_rank, offset, chains=1):
+        w = WORKLOADS[name]
+        torch.manual_seed(42)
+        net = UNet(**w["unet"]).to(dev).eval()
+        past = synthetic_macroprops(n_rank, 3, w["rows"], w["cols"], w["past"], 77 + rank, dev)
+        gen = torch.Generator(device=dev).manual_seed(7 + rank)
+        shape = (n_rank, 3, w["rows"], w["cols"], w["fut"])
+        x = torch.randn(shape, device=dev, generator=gen)
+        net.sample_chain(past, x, ts_short, coef_short, mode=0, seed=1, sample_offset=offset)     # warm-up
+        x = torch.randn(shape, device=dev, generator=gen)
+        net.sample_chain(past, x, tsteps, coef, mode=0, seed=2, sample_offset=offset)             # builds the T=1000 graph
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for c in range(chains):
+            x = torch.randn(shape, device=dev, generator=gen)
+            net.sample_chain(past, x, tsteps, coef, mode=0, seed=3 + c, sample_offset=offset)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / chains], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        fl = net.native_stats(w["rows"], w["cols"], w["past"], w["fut"])[1]
+        finite = bool(torch.isfinite(x).all().item())
+        del net, past, x
+        torch.cuda.empty_cache()
+        return ms.item(), fl, finite
+
+    out = {}
+    # (1) the production batch of generate_metrics (config/ATC.yml MODEL.NSAMPLES = 1280): strong scaling --
+    #     the 1280 samples are split over the ranks, global Philox offsets
+    lo, hi = shard_samples(1280, rank, world)
+    ms, fl, ok = one("atc", hi - lo, lo)
+    out["atc_n1280"] = {"workload": "config/ATC.yml generate_metrics batch: ONE 1000-step chain of 1280 samples "
+                                    f"split over {world} GPU(s)", "scaling": "strong", "samples": 1280,
+                        "chain_ms": ms, "sequences_per_s": 1280 / (ms * 1e-3),
+                        "denoiser_step_ms": ms / T_STEPS, "algorithmic_tflops": fl * 1280 * T_STEPS / (ms * 1e-3) / 1e12,
+                        "finite": ok}
+    # (2) BASELINE config #3: ATC_medium (base 64, 8+8 frames, attention S=108), 64 samples per GPU, no collective
+    ms, fl, ok = one("atc_medium", 64, rank * 64)
+    out["atc_medium"] = {"workload": "config/ATC_medium.yml: 1000-step chain, 64 samples per GPU, base 64, past 8 + future 8",
+                         "scaling": "weak", "samples": 64 * world, "chain_ms": ms,
+                         "sequences_per_s": 64 * world / (ms * 1e-3), "denoiser_step_ms": ms / T_STEPS,
+                         "algorithmic_tflops": fl * 64 * world * T_STEPS / (ms * 1e-3) / 1e12, "finite": ok}
+    # (3) BASELINE config #5: ETH-UCY (8x12 grid, attention S=12), 64 samples per GPU
+    ms, fl, ok = one("ethucy", 64, rank * 64, chains=2)
+    out["ethucy"] = {"workload": "config/ETHUCY_ddpm.yml: 1000-step chain, 64 samples per GPU, grid 8x12, past 5 + future 3",
+                     "scaling": "weak", "samples": 64 * world, "chain_ms": ms,
+                     "sequences_per_s": 64 * world / (ms * 1e-3), "denoiser_step_ms": ms / T_STEPS,
+                     "algorithmic_tflops": fl * 64 * world * T_STEPS / (ms * 1e-3) / 1e12, "finite": ok}
+    return out
+
 
 # ---- training leg (BASELINE config #4: HERMES-CR-120.yml, 28x24 grid, batch 64 per GPU) ----------
-H_ROWS, H_COLS = 28, 24
-
-
-def train_bench(rank, world, dev, steps=8, warmup=4, cpu_baseline=True):
-    """DDPM_model._train_step + loss.backward() + Adam step (reference ddpm.py:111-121,142-144)
-    through the reference-facing modules: native training forward/backward (tcgen05 fprop / dgrad
-    / wgrad), one flat-gradient all-reduce when world > 1, torch.optim.Adam as in the reference.
+def train_bench(rank, world, dev, steps=20, warmup=5, cpu_baseline=True):
+    """DDPM_model._train_one_epoch's loop body (reference ddpm.py:111-121,132-146) through the reference-facing
+    driver object: t ~ U, q-sample, native training forward (tcgen05 fprop), MSE, native backward (dgrad with
+    hi|lo dOut pairs / wgrad), ONE flat-gradient all-reduce when world > 1, the driver's own torch.optim.Adam.
     Returns a dict added to the bench line under "train"."""
     import torch.distributed as dist
-    import torch.nn.functional as F
-    from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
-    from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM
+    from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM, DDPM_model
+    w = WORKLOADS["hermes"]
     n = 64
     torch.manual_seed(42)
-    net = UNet(**ATC).to(dev).train()
-    opt = torch.optim.Adam(net.parameters(), lr=5e-5, betas=(0.5, 0.999), weight_decay=3e-3)
+    model = DDPM_model(make_cfg("hermes"), "DDPM-UNet", 3)
+    if world > 1:
+        model.enable_data_parallel()
+    net = model.denoiser.train()
+    opt = model.optimizer
     fs = DDPM(timesteps=T_STEPS, scale=SCALE).to(dev)
-    past = synthetic_macroprops(n, 3, H_ROWS, H_COLS, PAST, 1234 + rank, dev)
-    fut = synthetic_macroprops(n, 3, H_ROWS, H_COLS, FUT, 4321 + rank, dev)
+    past = synthetic_macroprops(n, 3, w["rows"], w["cols"], w["past"], 1234 + rank, dev)
+    fut = synthetic_macroprops(n, 3, w["rows"], w["cols"], w["fut"], 4321 + rank, dev)
 
     def step():
-        t = torch.randint(0, T_STEPS, (n,), device=dev)
-        x_t, eps = fs(fut, t)
-        loss = F.mse_loss(net(x_t, t, past), eps)
+        loss = model._train_step(fut, past, fs)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -319,55 +446,63 @@ def train_bench(rank, world, dev, steps=8, warmup=4, cpu_baseline=True):
         dist.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     a.record()
     for _ in range(steps):
         loss = step()
     b.record()
+    t_issue = time.perf_counter() - t0            # host time to ISSUE the steps (no sync inside)
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     step_ms = ms.item()
-    # forward / backward split on rank 0 (events around the two native calls)
-    t = torch.randint(0, T_STEPS, (n,), device=dev)
-    x_t, eps = fs(fut, t)
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    # forward / backward / optimizer split on rank 0 (events around the native calls)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
     e[0].record()
-    loss = F.mse_loss(net(x_t, t, past), eps)
+    loss = model._train_step(fut, past, fs)
     e[1].record()
     opt.zero_grad(set_to_none=True)
     loss.backward()
     e[2].record()
+    opt.step()
+    e[3].record()
     torch.cuda.synchronize()
-    plan = net._plan(H_ROWS, H_COLS, PAST, FUT)
-    fl = net.native_stats(H_ROWS, H_COLS, PAST, FUT)[1]
+    plan = net._plan(w["rows"], w["cols"], w["past"], w["fut"])
+    fl = net.native_stats(w["rows"], w["cols"], w["past"], w["fut"])[1]
     out = {"workload": "config/HERMES-CR-120.yml: DDPM-UNet training step (t~U, q-sample, fwd, MSE, bwd, Adam), "
                        "grid 28x24, past 5 + future 3, batch 64 per GPU, dropout 0.1",
+           "steps": steps, "warmup": warmup,
            "step_ms": step_ms, "samples_per_s": n * world / (step_ms * 1e-3),
-           "fwd_ms": e[0].elapsed_time(e[1]), "bwd_ms": e[1].elapsed_time(e[2]),
+           "host_issue_ms_per_step": t_issue * 1e3 / steps,
+           "fwd_ms": e[0].elapsed_time(e[1]), "bwd_ms": e[1].elapsed_time(e[2]), "adam_ms": e[2].elapsed_time(e[3]),
            "loss": float(loss.item()), "grad_allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer"
            if world > 1 else "none (1 GPU)",
+           "dgrad_terms": int(os.environ.get("CROWDMOD_DGRAD_TERMS", "2")),
            "algorithmic_tflops": 3.0 * fl * n / (step_ms * 1e-3) / 1e12,
            "bwd_launches": int(plan.n.lib().cm_last_backward_launches(plan.handle))}
     if cpu_baseline and rank == 0 and world == 1:
         out["cpu_baseline"] = train_cpu_baseline()
+    del model, net, opt
+    torch.cuda.empty_cache()
     return out
 
 
 def train_cpu_baseline(n=8):
     """One fwd+bwd of the reference path's CPU restatement on the host cores (bounded sample)."""
-    import torch.nn.functional as F
     from oracle import ddpm_oracle as do
     from oracle import unet_oracle as uo
     from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet
+    w = WORKLOADS["hermes"]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(42)
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "time_blocks.0" not in k)
           for k, v in UNet(**ATC).state_dict().items()}
     s = do.schedule(T_STEPS, SCALE)
-    past = do.synthetic_macroprops(n, 3, H_ROWS, H_COLS, PAST, 1234)
-    fut = do.synthetic_macroprops(n, 3, H_ROWS, H_COLS, FUT, 4321)
+    past = do.synthetic_macroprops(n, 3, w["rows"], w["cols"], w["past"], 1234)
+    fut = do.synthetic_macroprops(n, 3, w["rows"], w["cols"], w["fut"], 4321)
     den = lambda x, tt, p: uo.unet_forward(sd, x, tt, p, num_res_blocks=1, num_levels=3)
     t = torch.randint(0, T_STEPS, (n,))
     eps = torch.randn_like(fut)
@@ -379,9 +514,10 @@ def train_cpu_baseline(n=8):
 
 
 def roofline(net, nat, past, n, dev, step_ms):
-    """Dominant kernel class = the tcgen05 implicit-GEMM convs (conv_plane_kernel + conv_umma_kernel).  achieved = algorithmic
-    FLOPs of all its launches in one denoiser step / their summed device time, timed live with
-    CUDA events around every launch (cm_unet_profile_forward)."""
+    """Dominant kernel class = the tcgen05 implicit-GEMM convs (conv_plane_kernel + conv_umma_kernel).
+    achieved = EXECUTED FLOPs of all its launches in one denoiser step / their summed device time, timed live
+    with CUDA events around every launch (cm_unet_profile_forward).  The UpSample convs execute 8 phase convs of
+    2x2x2 folded taps (8/27 of the dense formulation): the dense-equivalent rate is reported separately."""
     pk = peaks()
     plan = net._plan(ROWS, COLS, PAST, FUT)
     lib = nat.lib()
@@ -405,16 +541,19 @@ def roofline(net, nat, past, n, dev, step_ms):
     for i in range(nops):
         lib.cm_unet_op_info(plan.handle, i, tag, 128, C.byref(ty), C.byref(fl))
         kind = kinds[ty.value]
+        name = tag.value.decode()
         # the sampling path runs each AttentionBlock (GroupNorm, in_proj, core, out_proj + residual) as ONE
-        # fused launch (attn_block_kernel): its four plan ops are one class, not conv / GN work
-        if ".attention." in tag.value.decode():
+        # fused launch: its four plan ops are one class, not conv / GN work
+        if ".attention." in name:
             kind = "attn_block"
-        a = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        a = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "exec_flops": 0.0, "launches": 0})
         a["ms"] += best[i]
         a["flops"] += fl.value * n
-        a["launches"] += 1
+        a["exec_flops"] += lib.cm_unet_op_exec_flops(plan.handle, i) * n
+        a["launches"] += 1 if best[i] > 0 else 0
     conv = agg["conv_umma"]
-    achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    achieved = conv["exec_flops"] / (conv["ms"] * 1e-3) / 1e12
+    dense = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_umma_traffic.json")
     if os.path.exists(tp):
@@ -423,12 +562,17 @@ def roofline(net, nat, past, n, dev, step_ms):
     return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv3d: conv_plane_kernel (levels 0/1) + conv_umma_kernel",
             "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+            "flops_counted": "executed (UpSample convs as 8 phase convs of 2x2x2 folded taps)",
+            "algorithmic_equiv": {"achieved": dense, "frac": dense / pk["tflops_sustained"],
+                                  "note": "dense 27-tap formulation of SURVEY.md §8(d) over the same device time"},
             "peak_source": pk["source"] + ", sustained bf16/fp16 dense",
-            "launches_per_step": conv["launches"], "avg_launch_us": conv["ms"] * 1e3 / conv["launches"],
+            "launches_per_step": conv["launches"], "avg_launch_us": conv["ms"] * 1e3 / max(conv["launches"], 1),
+            "executed_gflop_per_step": conv["exec_flops"] / 1e9,
             "algorithmic_gflop_per_step": conv["flops"] / 1e9,
             "share_of_step": conv["ms"] / total_ms,
             "per_kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in agg.items()},
             "eager_step_ms": total_ms, "graph_step_ms": step_ms,
+            "whole_step_tflops_executed": (sum(v["exec_flops"] for v in agg.values()) / 1e12) / (step_ms * 1e-3),
             "whole_step_tflops": (sum(v["flops"] for v in agg.values()) / 1e12) / (step_ms * 1e-3)}
 
 
@@ -443,6 +587,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=8, help="CPU denoiser iterations per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (extra key 'train')")
+    ap.add_argument("--no-extras", action="store_true", help="skip the n=1280 / ATC_medium / ETH-UCY chains")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -32,6 +32,7 @@ class UNetConfig(C.Structure):
         ("future_len", C.c_int32),
         ("table_steps", C.c_int32),
         ("weight_terms", C.c_int32),
+        ("dgrad_terms", C.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ SIGNATURES = {
     "cm_unet_param_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "cm_unet_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "cm_unet_bind_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "cm_unet_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cm_unet_reserve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "cm_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -75,10 +77,13 @@ SIGNATURES = {
     "cm_unet_op_count": (C.c_int, [C.c_void_p]),
     "cm_unet_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int),
                                   C.POINTER(C.c_double)]),
+    "cm_unet_op_exec_flops": (C.c_double, [C.c_void_p, C.c_int]),
     "cm_unet_profile_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "cm_ddpm_sample": (C.c_int, [C.c_void_p, C.POINTER(ChainArgs), C.c_void_p]),
     "cm_last_chain_launches": (C.c_int64, [C.c_void_p]),
+    "cm_last_chain_graph_launches": (C.c_int64, [C.c_void_p]),
+    "cm_last_chain_graph_rebuilt": (C.c_int, [C.c_void_p]),
     "cm_unet_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int64)]),
     "cm_unet_dropout_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                          C.POINTER(C.c_int32)]),
@@ -88,6 +93,8 @@ SIGNATURES = {
     "cm_last_backward_launches": (C.c_int64, [C.c_void_p]),
     "cm_op_conv3d_dgrad": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cm_op_conv3d_dgrad_f32": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cm_op_conv3d_wgrad": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p]),
@@ -136,6 +143,24 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = lib().cm_last_error()
         raise NativeError(f"crowdmod_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+DEVICE_ERRORS = {
+    301: "a loss-scaled fp16 gradient operand saturated (the value was clamped): the gradients of that step are "
+         "not trustworthy",
+}
+
+
+def check_device_error(where: str = "") -> None:
+    """Reads and clears the device-side error flag (synchronises) and raises on a non-zero code.  Kernels
+    never hang or trap on a protocol error (bounded mbarrier waits) or on a saturated gradient: they set the
+    flag and carry on, so the production loops poll it -- once per epoch in training, once per chain in
+    sampling -- instead of silently stepping on corrupt data."""
+    code = lib().cm_device_error()
+    if code != 0:
+        what = DEVICE_ERRORS.get(code, "a kernel pipeline wait timed out: partial outputs" if code > 0
+                                 else "the device could not be queried")
+        raise NativeError(f"crowdmod_b200 device error {code}{' in ' + where if where else ''}: {what}")
 
 
 def ptr(t):

@@ -242,7 +242,7 @@ int cm_op_conv3d_dgrad(int mode, const void* dout16, int B, int D, int H, int W,
   const size_t ktot = dgrad_packed_k(mode, cout);
   __half* wp = nullptr;
   CM_CUDA(cudaMalloc(&wp, (size_t)terms * cin * ktot * sizeof(__half) + 16));
-  int rc = pack_dgrad_weights(mode, w, wp, cout, cin, terms, 0, st);
+  int rc = pack_dgrad_weights(mode, w, wp, cout, cin, terms, 0, 1, st);
   ConvLaunch L;
   if (!rc) rc = conv_prepare(&L, dgrad_mode_of(mode), static_cast<const __half*>(dout16), B, od, oh, ow, cout,
                              nullptr, 0, wp, cin, terms);
@@ -252,6 +252,47 @@ int cm_op_conv3d_dgrad(int mode, const void* dout16, int B, int D, int H, int W,
   }
   cudaError_t se = cudaStreamSynchronize(st);
   cudaFree(wp);
+  if (rc) return rc;
+  CM_CUDA(se);
+  return 0;
+}
+
+int cm_op_conv3d_dgrad_f32(int mode, const float* dout32, int B, int D, int H, int W, int cin,
+                           const float* w, int cout, int terms, int dup, float* dx32, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = kernels_init()) return e;
+  if (int e = backward_init()) return e;
+  CM_CHECK(mode >= 0 && mode <= 3, "bad forward conv mode %d", mode);
+  CM_CHECK(dup == 1 || dup == 2, "dup must be 1 or 2");
+  int od = D, oh = H, ow = W;   // forward output grid
+  if (mode == 1) { od = (D - 1) / 2 + 1; oh = (H - 1) / 2 + 1; ow = (W - 1) / 2 + 1; }
+  else if (mode == 2) { od = 2 * D; oh = 2 * H; ow = 2 * W; }
+  const size_t ktot = dgrad_packed_k(mode, cout, dup);
+  const size_t npix = (size_t)B * od * oh * ow;
+  __half* wp = nullptr;
+  __half* d16 = nullptr;
+  CM_CUDA(cudaMalloc(&wp, (size_t)terms * cin * ktot * sizeof(__half) + 16));
+  CM_CUDA(cudaMalloc(&d16, npix * cout * dup * sizeof(__half) + 16));
+  int rc = pack_dgrad_weights(mode, w, wp, cout, cin, terms, 0, dup, st);
+  if (!rc) rc = cast_colsum_enqueue(dout32, d16, dup, nullptr, 0, nullptr, 0, B, od * oh * ow, cout, st);
+  ConvLaunch L;
+  PlaneLaunch PLn;
+  PLn.ok = false;
+  if (!rc) rc = conv_prepare(&L, dgrad_mode_of(mode), d16, B, od, oh, ow, dup * cout, nullptr, 0, wp, cin, terms);
+  if (!rc && mode == 0 && getenv("CM_NO_PLANE") == nullptr)
+    rc = plane_prepare(&PLn, d16, B, od, oh, ow, dup * cout, nullptr, 0, wp, cin, terms);
+  if (!rc) {
+    if (PLn.ok) {
+      PLn.p.out32 = dx32;
+      rc = plane_enqueue(PLn, st);
+    } else {
+      L.p.out32 = dx32;
+      rc = conv_enqueue(L, st);
+    }
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(wp);
+  cudaFree(d16);
   if (rc) return rc;
   CM_CUDA(se);
   return 0;

@@ -4,18 +4,13 @@
 
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "pack.cuh"
 
 namespace cm {
 
 int wgrad_init();   // conv_umma.cu
 
 namespace {
-
-__device__ __forceinline__ int src_tap(int tap, int perm) {
-  // tap = (d*3 + h)*3 + w in activation-dim order (time, rows, cols); the reference's
-  // nn.Conv3d weight is over (rows, cols, time): source index = (h*3 + w)*3 + d.
-  return perm ? (((tap / 3) % 3) * 3 + (tap % 3)) * 3 + tap / 9 : tap;
-}
 
 __device__ __forceinline__ float silu_grad(float y) {
   const float s = 1.0f / (1.0f + __expf(-y));
@@ -48,75 +43,28 @@ int dgrad_mode_of(int fwd_mode) {
     default: return 3;
   }
 }
-size_t dgrad_packed_k(int fwd_mode, int cout_f) {
+size_t dgrad_packed_k(int fwd_mode, int cout_f, int dup) {
+  const size_t c = (size_t)dup * cout_f;
   switch (fwd_mode) {
-    case 0: return (size_t)27 * cout_f;
+    case 0: return 27 * c;
     case 1:
-    case 2: return (size_t)64 * cout_f;
-    default: return (size_t)cout_f;
+    case 2: return 64 * c;
+    default: return c;
   }
 }
 
 __global__ void pack_dgrad_kernel(int fwd_mode, const float* __restrict__ w, __half* __restrict__ dst,
-                                  int cout_f, int cin_f, int terms, int perm, size_t ktot) {
-  const size_t total = (size_t)cin_f * ktot;
-  const int taps_src = (fwd_mode == 3) ? 1 : 27;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(idx / ktot);            // row = forward input channel
-    const int k = (int)(idx - (size_t)n * ktot);
-    float v = 0.f;
-    if (fwd_mode == 0) {
-      const int tap = k / cout_f, co = k - tap * cout_f;
-      v = w[((size_t)co * cin_f + n) * 27 + src_tap(26 - tap, perm)];
-    } else if (fwd_mode == 3) {
-      v = w[(size_t)k * cin_f + n];
-    } else if (fwd_mode == 1) {
-      // k3 s2 p1 forward: dX[2j]   = W[1]^T dY[j]
-      //                   dX[2j+1] = W[2]^T dY[j] + W[0]^T dY[j+1]
-      // expressed in the 8-phase / 2x2x2-tap scheme of conv mode 2 (phase bit p: taps at
-      // j-1, j when p = 0; j, j+1 when p = 1).
-      const int phase = k / (8 * cout_f);
-      const int r = k - phase * 8 * cout_f;
-      const int tap8 = r / cout_f, co = r - tap8 * cout_f;
-      int t[3];
-      bool live = true;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {             // d = 0: w, 1: h, 2: d
-        const int p = (phase >> d) & 1, a = (tap8 >> d) & 1;
-        if (p == 0) { t[d] = 1; live = live && (a == 1); }
-        else t[d] = a ? 0 : 2;
-      }
-      if (live) v = w[((size_t)co * cin_f + n) * 27 + src_tap((t[2] * 3 + t[1]) * 3 + t[0], perm)];
-    } else {
-      // nearest-x2 + k3 p1 forward: dX[j] = sum_s Ws[s]^T dY[2j - 1 + s], s = 0..3 with
-      // Ws = {W2, W1+W2, W0+W1, W0} per dimension (k4 s2 conv, conv mode 4).
-      const int tap = k / cout_f, co = k - tap * cout_f;
-      const int s[3] = {tap & 3, (tap >> 2) & 3, tap >> 4};   // w, h, d
-      int lo[3], hi[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        lo[d] = (s[d] == 0) ? 2 : (s[d] == 1 ? 1 : 0);
-        hi[d] = (s[d] == 0) ? 2 : (s[d] == 1 ? 2 : (s[d] == 2 ? 1 : 0));
-      }
-      const float* wp = w + ((size_t)co * cin_f + n) * 27;
-      for (int kd = lo[2]; kd <= hi[2]; ++kd)
-        for (int kh = lo[1]; kh <= hi[1]; ++kh)
-          for (int kw = lo[0]; kw <= hi[0]; ++kw) v += wp[src_tap((kd * 3 + kh) * 3 + kw, perm)];
-    }
-    (void)taps_src;
-    const __half h = __float2half_rn(v);
-    dst[(size_t)n * ktot + k] = h;
-    if (terms == 2) dst[((size_t)cin_f + n) * ktot + k] = __float2half_rn(v - __half2float(h));
-  }
+                                  int cout_f, int cin_f, int terms, int perm, int dup, size_t ktot) {
+  pack_dgrad_body(fwd_mode, w, dst, cout_f, cin_f, terms, perm, dup, ktot,
+                  blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
 int pack_dgrad_weights(int fwd_mode, const float* w, __half* dst, int cout_f, int cin_f, int terms,
-                       int perm, cudaStream_t st) {
-  const size_t ktot = dgrad_packed_k(fwd_mode, cout_f);
+                       int perm, int dup, cudaStream_t st) {
+  const size_t ktot = dgrad_packed_k(fwd_mode, cout_f, dup);
   const size_t total = (size_t)cin_f * ktot;
   pack_dgrad_kernel<<<grid_for(total, 256, 4096), 256, 0, st>>>(fwd_mode, w, dst, cout_f, cin_f, terms,
-                                                               perm, ktot);
+                                                               perm, dup, ktot);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -157,7 +105,7 @@ int auto_scale_enqueue(const float* x, size_t n, float target, float* scale_dev,
 // dOut preparation: fp32 -> fp16 operand (+ residual fan-out, per-sample channel sums)
 // =============================================================================================
 __global__ void __launch_bounds__(1024)
-cast_colsum_kernel(const float* __restrict__ src, __half* __restrict__ dst16, float* __restrict__ acc_dst,
+cast_colsum_kernel(const float* __restrict__ src, __half* __restrict__ dst16, int dup, float* __restrict__ acc_dst,
                    int acc_init, float* __restrict__ colsum, int colsum_ld, int pixels, int C, int chunks,
                    int* __restrict__ err_flag) {
   extern __shared__ float red[];   // [T][4]
@@ -181,7 +129,19 @@ cast_colsum_kernel(const float* __restrict__ src, __half* __restrict__ dst16, fl
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&h0);
       u.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(dst16 + base + (size_t)i * 4) = u;
+      if (dup == 1) {
+        *reinterpret_cast<uint2*>(dst16 + base + (size_t)i * 4) = u;
+      } else {
+        // hi | lo pair, K-concatenated per pixel: [pixel][2C], hi in [0, C), lo = fp16(v - hi) in [C, 2C)
+        const int px = i / Q, cq = (i - px * Q) * 4;
+        __half* row = dst16 + (((size_t)b * pixels + px0 + px) * 2) * C + cq;
+        *reinterpret_cast<uint2*>(row) = u;
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn(c.x - f0.x, c.y - f0.y), l1 = __floats2half2_rn(c.z - f1.x, c.w - f1.y);
+        u.x = *reinterpret_cast<uint32_t*>(&l0);
+        u.y = *reinterpret_cast<uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(row + C) = u;
+      }
     }
     if (acc_dst) {
       float4* ap = reinterpret_cast<float4*>(acc_dst + base + (size_t)i * 4);
@@ -211,16 +171,17 @@ cast_colsum_kernel(const float* __restrict__ src, __half* __restrict__ dst16, fl
   }
 }
 
-int cast_colsum_enqueue(const float* src, __half* dst16, float* acc_dst, int acc_init, float* colsum,
+int cast_colsum_enqueue(const float* src, __half* dst16, int dup, float* acc_dst, int acc_init, float* colsum,
                         int colsum_ld, int B, int pixels, int C, cudaStream_t st) {
   CM_CHECK(C % 4 == 0 && C / 4 <= 1024, "cast_colsum: bad channel count %d", C);
+  CM_CHECK(dup == 1 || dup == 2, "cast_colsum: dup must be 1 or 2");
   const int Q = C / 4;
   const int T = sweep_threads(Q);
   int chunks = 592 / B;
   if (chunks < 1) chunks = 1;
   if (chunks > (pixels + 7) / 8) chunks = (pixels + 7) / 8;
   if (chunks < 1) chunks = 1;
-  cast_colsum_kernel<<<dim3(chunks, B), T, (size_t)T * 16, st>>>(src, dst16, acc_dst, acc_init, colsum,
+  cast_colsum_kernel<<<dim3(chunks, B), T, (size_t)T * 16, st>>>(src, dst16, dup, acc_dst, acc_init, colsum,
                                                                 colsum_ld, pixels, C, chunks,
                                                                 device_error_flag());
   CM_CUDA(cudaGetLastError());

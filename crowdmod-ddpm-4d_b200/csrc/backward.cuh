@@ -19,10 +19,11 @@ namespace cm {
 //      fwd mode 1 (k3 s2)  -> mode 2 (8 phases x 8 taps, scatter), K = 64*cout_f
 //      fwd mode 2 (up+k3)  -> mode 4 (k4 s2),                      K = 64*cout_f
 // perm as in pack_conv_weights (kernels.cuh).
+// dup = 2: the dOut operand is a K-concatenated hi|lo fp16 pair (pack.cuh), K doubles.
 int pack_dgrad_weights(int fwd_mode, const float* w, __half* dst, int cout_f, int cin_f, int terms,
-                       int perm, cudaStream_t st);
+                       int perm, int dup, cudaStream_t st);
 int dgrad_mode_of(int fwd_mode);
-size_t dgrad_packed_k(int fwd_mode, int cout_f);
+size_t dgrad_packed_k(int fwd_mode, int cout_f, int dup = 1);
 
 // ---- loss scale: S = 2^floor(log2(target / max|x|)) (1 if x == 0); scale[0] = S, scale[1] = 1/S ----
 // max_scratch: one zero-initialised device word (left zero on return)
@@ -31,8 +32,9 @@ int auto_scale_enqueue(const float* x, size_t n, float target, float* scale_dev,
 
 // ---- dOut preparation for one conv: fp32 grad [B][pixels][C] -> fp16 operand, optional
 //      residual fan-out (acc_dst (=|+=) src) and per-sample channel sums (bias / time-embedding
-//      projection gradients): colsum[b*colsum_ld + c] += sum_p src[b][p][c] ----
-int cast_colsum_enqueue(const float* src, __half* dst16, float* acc_dst, int acc_init, float* colsum,
+//      projection gradients): colsum[b*colsum_ld + c] += sum_p src[b][p][c].  dup = 2: dst16 is the
+//      K-concatenated hi|lo pair [pixel][2C] (dgrad reads both halves, wgrad the hi half) ----
+int cast_colsum_enqueue(const float* src, __half* dst16, int dup, float* acc_dst, int acc_init, float* colsum,
                         int colsum_ld, int B, int pixels, int C, cudaStream_t st);
 // out[c] (+)= sum_b in[b*ld + c]
 int rowsum_enqueue(const float* in, float* out, int B, int C, int ld, int accumulate, cudaStream_t st);

@@ -317,10 +317,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  // u1 in (0,1], u2 in [0,1)
-  float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;
-  float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;
-  float r = sqrtf(-2.0f * __logf(u1));
+  // u from the top 24 bits (+0.5): exact in fp32, u1 in (0,1) strictly (never rounds to 1.0, so -2 ln(u1) > 0
+  // even with the ~2^-21 absolute error of __logf near 1: fmaxf guards the sqrt all the same), u2 in (0,1)
+  float u1 = (static_cast<float>(a >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  float u2 = (static_cast<float>(b >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  float r = sqrtf(fmaxf(0.0f, -2.0f * __logf(u1)));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);

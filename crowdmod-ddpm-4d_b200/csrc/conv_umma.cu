@@ -35,10 +35,13 @@ int load_driver_syms() {
 
 // Activation tensor [B, D, H, W, C] fp16 -> 5-D im2col map, dims ordered (C, W, H, D, N).
 int make_act_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int bk,
-                 int lower_w, int lower_h, int lower_d, int stride, int upper_delta) {
+                 int lower_w, int lower_h, int lower_d, int stride, int upper_delta, int ld) {
+  // ld = channel stride of a pixel row in elements (0 -> C); ld > C views the first C channels of wider rows
+  // (the hi half of a K-concatenated hi|lo dOut pair)
+  const cuuint64_t Cs = (cuuint64_t)(ld > 0 ? ld : C);
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
-                           (cuuint64_t)D * H * W * C * 2};
+  cuuint64_t strides[4] = {Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2,
+                           (cuuint64_t)D * H * W * Cs * 2};
   // For the forward conv shapes (k3 p1 s1|s2, 2x2x2 phase taps, 1x1x1) the upper corner
   // (upper_pad - (k-1)) equals the lower corner (-lower_pad); the k4 s2 dgrad of UpSample needs
   // upper = lower - 1 (upper_delta = -1).
@@ -55,7 +58,7 @@ int make_act_map(CUtensorMap* map, const __half* base, int B, int D, int H, int 
   // Driver quirk mirrored from CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): for tensors
   // smaller than 128 KiB, drivers <= 13.1 set a descriptor bit that must be cleared.
   if (g_driver_version <= 13010) {
-    size_t bytes = (size_t)B * D * H * W * C * 2;
+    size_t bytes = (size_t)B * D * H * W * Cs * 2;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   }
   return 0;
@@ -523,7 +526,7 @@ size_t wgrad_g_elems(int mode, int cin, int cin_extra, int cout) {
 }
 
 int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
-                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G) {
+                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G, int dout_ld) {
   if (int rc = load_driver_syms()) return rc;
   CM_CHECK(mode >= 0 && mode <= 3, "bad wgrad mode %d", mode);
   CM_CHECK(cin % 32 == 0 && cin_extra % 32 == 0 && cout % 32 == 0,
@@ -567,10 +570,10 @@ int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int
       p.glower[ph][0] = (signed char)gw;
       p.glower[ph][1] = (signed char)gh;
       p.glower[ph][2] = (signed char)gd;
-      if (int rc = make_act_map(&p.gmap[ph], dout, B, 2 * D, 2 * H, 2 * W, cout, bnc, gw, gh, gd, 2, -1))
+      if (int rc = make_act_map(&p.gmap[ph], dout, B, 2 * D, 2 * H, 2 * W, cout, bnc, gw, gh, gd, 2, -1, dout_ld))
         return rc;
     } else {
-      if (int rc = make_act_map(&p.gmap[ph], dout, B, od, oh, ow, cout, bnc, 0, 0, 0, 1, 0)) return rc;
+      if (int rc = make_act_map(&p.gmap[ph], dout, B, od, oh, ow, cout, bnc, 0, 0, 0, 1, 0, dout_ld)) return rc;
     }
   }
   if (cin_extra) {

@@ -2,6 +2,7 @@
 // the reference lines each one replaces.
 #include "kernels.cuh"
 #include "conv_umma.cuh"
+#include "pack.cuh"
 
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -15,29 +16,23 @@ namespace cm {
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const float* __restrict__ wx,
                                          __half* __restrict__ dst, int cout, int cin, int cinx,
                                          int taps, int terms, int perm, int cin_src) {
-  const size_t ktot = (size_t)taps * cin + cinx;
-  const size_t total = (size_t)cout * ktot;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(idx / ktot);
-    const size_t k = idx - (size_t)n * ktot;
-    float v;
-    if (k < (size_t)taps * cin) {
-      const int tap = (int)(k / cin);
-      const int ci = (int)(k - (size_t)tap * cin);
-      // packed tap order follows the activation dims (d, h, w).  perm=1: the source weight is
-      // the reference's nn.Conv3d over (rows, cols, time) while activations are stored
-      // [B, time, rows, cols, C]  ->  source tap = (h*3 + w)*3 + d
-      int st = tap;
-      if (perm && taps == 27) st = (((tap / 3) % 3) * 3 + (tap % 3)) * 3 + tap / 9;
-      v = ci < cin_src ? w[((size_t)n * cin_src + ci) * taps + st] : 0.f;   // zero-padded channels
-    } else {
-      v = wx[(size_t)n * cinx + (k - (size_t)taps * cin)];
-    }
-    const __half hi = __float2half_rn(v);
-    dst[(size_t)n * ktot + k] = hi;
-    if (terms == 2) dst[((size_t)cout + n) * ktot + k] = __float2half_rn(v - __half2float(hi));
-  }
+  pack_conv_body(w, wx, dst, cout, cin, cinx, taps, terms, perm, cin_src,
+                 blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+// every packed cache of a plan in one launch: blockIdx.y = job (pack.cuh)
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, istep = (size_t)gridDim.x * blockDim.x;
+  if (j.kind == 0) pack_conv_body(j.w, j.wx, j.dst, j.cout, j.cin, j.cinx, j.taps, j.terms, j.perm, j.cin_src, i0, istep);
+  else if (j.kind == 1) pack_upsample_body(j.w, j.dst, j.cout, j.cin, j.terms, j.perm, i0, istep);
+  else pack_dgrad_body(j.mode, j.w, j.dst, j.cout, j.cin, j.terms, j.perm, j.dup, (size_t)j.ktot, i0, istep);
+}
+int pack_all_enqueue(const PackJob* d_jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return 0;
+  pack_all_kernel<<<dim3(48, njobs), 256, 0, st>>>(d_jobs);
+  CM_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, int cin, int cinx,
@@ -96,37 +91,8 @@ int pack_first_input_enqueue(const float* x, const float* past, __half* out16, i
 
 __global__ void pack_upsample_weights_kernel(const float* __restrict__ w, __half* __restrict__ dst,
                                              int cout, int cin, int terms, int perm) {
-  const size_t ktot = (size_t)64 * cin;
-  const size_t total = (size_t)cout * ktot;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(idx / ktot);
-    const int k = (int)(idx - (size_t)n * ktot);
-    const int phase = k / (8 * cin);
-    const int r = k - phase * 8 * cin;
-    const int tap8 = r / cin;
-    const int ci = r - tap8 * cin;
-    // per dim: phase bit p, tap bit a -> contributing original taps [lo, hi]
-    //   p=0 (even output): a=0 -> {0},   a=1 -> {1,2}
-    //   p=1 (odd  output): a=0 -> {0,1}, a=1 -> {2}
-    int lo[3], hi[3];
-    const int pbit[3] = {phase & 1, (phase >> 1) & 1, (phase >> 2) & 1};   // w, h, d
-    const int abit[3] = {tap8 & 1, (tap8 >> 1) & 1, (tap8 >> 2) & 1};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      if (pbit[d] == 0) { lo[d] = abit[d] ? 1 : 0; hi[d] = abit[d] ? 2 : 0; }
-      else              { lo[d] = abit[d] ? 2 : 0; hi[d] = abit[d] ? 2 : 1; }
-    }
-    const float* wp = w + ((size_t)n * cin + ci) * 27;
-    float v = 0.f;
-    for (int kd = lo[2]; kd <= hi[2]; ++kd)
-      for (int kh = lo[1]; kh <= hi[1]; ++kh)
-        for (int kw = lo[0]; kw <= hi[0]; ++kw)
-          v += perm ? wp[(kh * 3 + kw) * 3 + kd] : wp[(kd * 3 + kh) * 3 + kw];
-    const __half h = __float2half_rn(v);
-    dst[(size_t)n * ktot + k] = h;
-    if (terms == 2) dst[((size_t)cout + n) * ktot + k] = __float2half_rn(v - __half2float(h));
-  }
+  pack_upsample_body(w, dst, cout, cin, terms, perm, blockIdx.x * (size_t)blockDim.x + threadIdx.x,
+                     (size_t)gridDim.x * blockDim.x);
 }
 
 int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms, int perm,
@@ -1139,12 +1105,14 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
 #pragma unroll
       for (int co = 0; co < COUT; ++co) z[co] = p.noise[(size_t)step * nelem + e0 + co * plane];
     } else {
+      const unsigned long long seed = p.chain_dev ? p.chain_dev[0] : p.seed;
+      const long long soff = p.chain_dev ? static_cast<long long>(p.chain_dev[1]) : p.sample_offset;
       const unsigned long long gp =
-          ((unsigned long long)(p.sample_offset + b)) * (unsigned long long)(p.H * p.W * F) +
+          ((unsigned long long)(soff + b)) * (unsigned long long)(p.H * p.W * F) +
           ((size_t)h * p.W + wc) * F + f;
       const uint4 rnd = philox4x32_10(
           make_uint4((uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)step, 0u),
-          make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
       const float2 n0 = box_muller(rnd.x, rnd.y), n1 = box_muller(rnd.z, rnd.w);
       z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
     }
@@ -1889,6 +1857,32 @@ __global__ void advance_step_kernel(int* step_dev, int* t_dev, const int* tsteps
 }
 int advance_step_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaStream_t st) {
   if (int e = launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, st, step_dev, t_dev, tsteps, nsteps)) return e;
+  return 0;
+}
+__global__ void advance_step_cond_kernel(int* step_dev, int* t_dev, const int* tsteps, int nsteps,
+                                         cudaGraphConditionalHandle h) {
+  const int s = *step_dev + 1;
+  *step_dev = s;
+  *t_dev = tsteps[s < nsteps ? s : nsteps - 1];
+  cudaGraphSetConditional(h, s < nsteps ? 1u : 0u);
+}
+int advance_step_cond_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaGraphConditionalHandle h,
+                              cudaStream_t st) {
+  advance_step_cond_kernel<<<1, 1, 0, st>>>(step_dev, t_dev, tsteps, nsteps, h);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void chain_begin_kernel(int* step_dev, int* t_dev, const int* tsteps, unsigned long long* chain_dev,
+                                   unsigned long long seed, long long sample_offset) {
+  *step_dev = 0;
+  *t_dev = tsteps[0];
+  chain_dev[0] = seed;
+  chain_dev[1] = static_cast<unsigned long long>(sample_offset);
+}
+int chain_begin_enqueue(int* step_dev, int* t_dev, const int* tsteps, unsigned long long* chain_dev,
+                        unsigned long long seed, long long sample_offset, cudaStream_t st) {
+  chain_begin_kernel<<<1, 1, 0, st>>>(step_dev, t_dev, tsteps, chain_dev, seed, sample_offset);
+  CM_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -74,6 +74,8 @@ struct FinalParams {
   const float* noise;    // [nsteps][B*cout*H*W*F] or nullptr -> Philox
   unsigned long long seed;
   long long sample_offset;  // global index of sample 0 of this shard (Philox counter)
+  const unsigned long long* chain_dev;   // device {seed, sample_offset}: overrides the two fields above when set
+                                         // (a new seed / shard offset then needs no new CUDA graph)
   float* history;        // optional [nsteps+1][B*cout*H*W*F]; slot step+1 written
 };
 int final_conv_enqueue(const FinalParams& p, cudaStream_t st);
@@ -114,6 +116,13 @@ int attn_block_enqueue(const float* x, const float* gamma, const float* beta, co
 
 // ---- chain bookkeeping: step += 1; t_dev = tsteps[step] ----
 int advance_step_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaStream_t st);
+// same, as the last node of a conditional WHILE body: also sets the loop condition (step < nsteps)
+int advance_step_cond_enqueue(int* step_dev, int* t_dev, const int* tsteps, int nsteps, cudaGraphConditionalHandle h,
+                              cudaStream_t st);
+// start of a chain: step = 0, t_dev = tsteps[0], chain_dev = {seed, sample_offset} (arguments travel as
+// kernel parameters: no host staging buffer, no synchronisation)
+int chain_begin_enqueue(int* step_dev, int* t_dev, const int* tsteps, unsigned long long* chain_dev,
+                        unsigned long long seed, long long sample_offset, cudaStream_t st);
 
 // ---- test-only: scalar restatement of exactly what conv_umma computes (same packed operands) ----
 struct ConvParams;

@@ -7,6 +7,8 @@
 // a K-slab of conv_2, residual/time-embedding adds live in conv epilogues, nearest-x2
 // upsampling is folded into 8 phase convolutions, and DDPM.step (ddpm.py:25-38) is the
 // epilogue of the last conv.
+#include <string.h>
+
 #include <map>
 #include <memory>
 #include <string>
@@ -17,6 +19,7 @@
 #include "conv_plane.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "pack.cuh"
 #include "wgrad_umma.cuh"
 
 namespace cm {
@@ -116,6 +119,12 @@ struct cm_unet {
   int* d_couts = nullptr;
   int* d_offs = nullptr;
   bool packed = false;
+  // table-driven packing (pack.cuh): [forward jobs | dgrad jobs], rebuilt when parameter storage moves
+  std::vector<PackJob> jobs_host;
+  PackJob* d_jobs = nullptr;
+  int n_jobs_fwd = 0, n_jobs_dgrad = 0, jobs_cap = 0;
+  bool jobs_dirty = true;
+  int dgrad_dup = 2;                    // cfg.dgrad_terms: hi|lo dOut pair in every data-gradient conv
   // workspace (per reserved batch)
   int reserved_batch = 0;
   uint8_t* arena = nullptr;
@@ -123,14 +132,21 @@ struct cm_unet {
   float* temb_batch = nullptr;          // [batch][temb_ld]
   float* gn_partial = nullptr;          // [batch][GN chunks][8][2] slice statistics (reused by every GN)
   int* d_step = nullptr;                // [0] step index, [1] current timestep
+  unsigned long long* d_chain = nullptr;   // [0] Philox seed, [1] sample offset (read by the step epilogue)
   int* d_tsteps = nullptr;
   float* d_coef = nullptr;
   int chain_cap = 0;
+  std::vector<int> tsteps_host;         // what d_tsteps / d_coef currently hold (re-uploaded only on change)
+  std::vector<float> coef_host;
+  float* chain_x = nullptr;             // staging copies of the caller's x / past: the graph bakes THESE pointers
+  float* chain_past = nullptr;
   // graph cache for the chain
   cudaGraphExec_t graph_exec = nullptr;
   cm_chain_args graph_key{};
   int64_t last_chain_launches = 0;
   int64_t graph_launches_per_step = 0;
+  int64_t last_chain_graph_launches = 0;
+  int last_chain_graph_rebuilt = 0;
   int64_t last_backward_launches = 0;
   double flops_per_sample = 0.0;
   // ---- training state (cm_unet_train_forward / cm_unet_backward) ----
@@ -243,9 +259,9 @@ int add_conv(cm_unet* u, const std::string& tag, int mode, int in, int extra, in
   op.wpack_off = u->wpack_elems;
   u->wpack_elems += (size_t)u->cfg.weight_terms * cout * conv_packed_k(mode, op.cin, op.cin_extra);
   op.dpack_off = u->dpack_elems;
-  u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin * dgrad_packed_k(mode, cout);
+  u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin * dgrad_packed_k(mode, cout, u->dgrad_dup);
   op.dxpack_off = u->dpack_elems;
-  u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin_extra * cout;
+  u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin_extra * cout * u->dgrad_dup;
   op.g_off = u->g_elems;
   u->g_elems += wgrad_g_elems(mode, op.cin, op.cin_extra, cout);
   op.colsum_off = u->colsum_per_sample;
@@ -473,6 +489,11 @@ int reserve(cm_unet* u, int batch) {
   off = align_up(off + (size_t)batch * u->temb_ld * 4, 1024);
   const size_t gnp_off = off;
   off = align_up(off + (size_t)batch * 32 * 8 * 3 * 4, 1024);   // [batch][GN2_MAX_SLICES][8][3]
+  const Level& lv0 = u->levels[0];
+  const size_t cx_off = off;
+  off = align_up(off + (size_t)batch * u->cfg.out_channels * lv0.H * lv0.W * u->cfg.future_len * 4, 1024);
+  const size_t cp_off = off;
+  off = align_up(off + (size_t)batch * u->cfg.in_channels * lv0.H * lv0.W * (u->cfg.past_len > 0 ? u->cfg.past_len : 1) * 4, 1024);
   CM_CUDA(cudaMalloc(&u->arena, off));
   CM_CUDA(cudaMemset(u->arena, 0, off));
   u->arena_bytes = off;
@@ -485,7 +506,10 @@ int reserve(cm_unet* u, int batch) {
   }
   u->temb_batch = reinterpret_cast<float*>(u->arena + temb_off);
   u->gn_partial = reinterpret_cast<float*>(u->arena + gnp_off);
+  u->chain_x = reinterpret_cast<float*>(u->arena + cx_off);
+  u->chain_past = reinterpret_cast<float*>(u->arena + cp_off);
   if (!u->d_step) CM_CUDA(cudaMalloc(&u->d_step, 2 * sizeof(int)));
+  if (!u->d_chain) CM_CUDA(cudaMalloc(&u->d_chain, 2 * sizeof(unsigned long long)));
   u->reserved_batch = batch;
   return 0;
 }
@@ -763,7 +787,7 @@ int reserve_train(cm_unet* u, int batch) {
     const Tens& t = u->tens[i];
     const size_t n = (size_t)batch * u->levels[t.level].pps() * t.C;
     o32[i] = take(n * 4);
-    if (is_conv_out[i]) o16[i] = take(n * 2);
+    if (is_conv_out[i]) o16[i] = take(n * 2 * u->dgrad_dup);   // hi | lo pair per pixel when dgrad_dup == 2
   }
   const size_t o_stats = take((size_t)u->n_gn * batch * 16 * 4);
   const size_t o_part = take((size_t)batch * 32 * Cmax * 2 * 4);
@@ -804,20 +828,98 @@ int reserve_train(cm_unet* u, int batch) {
   return 0;
 }
 
-int pack_dgrad(cm_unet* u, cudaStream_t st) {
-  if (u->dpacked) return 0;
+// (Re)build the pack-job table [forward | dgrad] and the time-embedding pointer tables.  Runs when
+// parameter storage moved or a cache buffer was (re)allocated; synchronous, rare.
+int build_jobs(cm_unet* u) {
+  if (!u->jobs_dirty) return 0;
   const int terms = u->cfg.weight_terms;
-  if (!u->dpack) CM_CUDA(cudaMalloc(&u->dpack, (u->dpack_elems + 8) * sizeof(__half)));
+  if (!u->wpack) CM_CUDA(cudaMalloc(&u->wpack, u->wpack_elems * sizeof(__half)));
+  std::vector<PackJob> jobs;
   for (Op& op : u->ops) {
     if (op.type != OP_CONV) continue;
-    if (int e = pack_dgrad_weights(op.mode, u->params[op.w].ptr, u->dpack + op.dpack_off, op.cout, op.cin,
-                                   terms, 1, st))
-      return e;
-    if (op.cin_extra)
-      if (int e = pack_dgrad_weights(3, u->params[op.wx].ptr, u->dpack + op.dxpack_off, op.cout,
-                                     op.cin_extra, terms, 1, st))
-        return e;
+    PackJob j{};
+    j.w = u->params[op.w].ptr;
+    j.wx = op.wx >= 0 ? u->params[op.wx].ptr : nullptr;
+    j.dst = u->wpack + op.wpack_off;
+    j.kind = op.mode == 2 ? 1 : 0;
+    j.cout = op.cout; j.cin = op.cin; j.cinx = op.cin_extra; j.taps = op.mode == 3 ? 1 : 27;
+    j.terms = op.mode == 2 ? terms : fwd_terms(u, op);
+    j.perm = 1; j.cin_src = op.cin; j.dup = 1;
+    jobs.push_back(j);
   }
+  {
+    PackJob j{};
+    j.w = u->params[u->p_first_w].ptr;
+    j.dst = u->wpack + u->first_wpack_off;
+    j.kind = 0;
+    j.cout = u->cfg.base_channels; j.cin = 32; j.cinx = 0; j.taps = 27;
+    j.terms = u->fullres_terms > 0 ? u->fullres_terms : terms;
+    j.perm = 1; j.cin_src = u->cfg.in_channels; j.dup = 1;
+    jobs.push_back(j);
+  }
+  u->n_jobs_fwd = (int)jobs.size();
+  u->n_jobs_dgrad = 0;
+  if (u->dpack) {
+    for (Op& op : u->ops) {
+      if (op.type != OP_CONV) continue;
+      PackJob j{};
+      j.w = u->params[op.w].ptr;
+      j.dst = u->dpack + op.dpack_off;
+      j.kind = 2; j.mode = op.mode;
+      j.cout = op.cout; j.cin = op.cin; j.terms = terms; j.perm = 1; j.dup = u->dgrad_dup;
+      j.ktot = dgrad_packed_k(op.mode, op.cout, u->dgrad_dup);
+      jobs.push_back(j);
+      if (op.cin_extra) {
+        PackJob x{};
+        x.w = u->params[op.wx].ptr;
+        x.dst = u->dpack + op.dxpack_off;
+        x.kind = 2; x.mode = 3;
+        x.cout = op.cout; x.cin = op.cin_extra; x.terms = terms; x.perm = 1; x.dup = u->dgrad_dup;
+        x.ktot = dgrad_packed_k(3, op.cout, u->dgrad_dup);
+        jobs.push_back(x);
+      }
+    }
+    u->n_jobs_dgrad = (int)jobs.size() - u->n_jobs_fwd;
+  }
+  if ((int)jobs.size() > u->jobs_cap) {
+    cudaFree(u->d_jobs);
+    u->d_jobs = nullptr;
+    CM_CUDA(cudaMalloc(&u->d_jobs, jobs.size() * sizeof(PackJob)));
+    u->jobs_cap = (int)jobs.size();
+  }
+  CM_CUDA(cudaMemcpy(u->d_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  u->jobs_host.swap(jobs);
+  // per-block dense_1 pointer tables of the time-embedding kernel
+  const int nb = (int)u->temb_couts.size();
+  if (!u->d_wd) {
+    CM_CUDA(cudaMalloc(&u->d_wd, nb * sizeof(float*)));
+    CM_CUDA(cudaMalloc(&u->d_bd, nb * sizeof(float*)));
+    CM_CUDA(cudaMalloc(&u->d_couts, nb * sizeof(int)));
+    CM_CUDA(cudaMalloc(&u->d_offs, nb * sizeof(int)));
+    CM_CUDA(cudaMalloc(&u->temb_table, (size_t)u->cfg.table_steps * u->temb_ld * sizeof(float)));
+  }
+  std::vector<const float*> wd(nb), bd(nb);
+  for (int k = 0; k < nb; ++k) {
+    wd[k] = u->params[u->temb_dense_w[k]].ptr;
+    bd[k] = u->params[u->temb_dense_b[k]].ptr;
+  }
+  CM_CUDA(cudaMemcpy(u->d_wd, wd.data(), nb * sizeof(float*), cudaMemcpyHostToDevice));
+  CM_CUDA(cudaMemcpy(u->d_bd, bd.data(), nb * sizeof(float*), cudaMemcpyHostToDevice));
+  CM_CUDA(cudaMemcpy(u->d_couts, u->temb_couts.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
+  CM_CUDA(cudaMemcpy(u->d_offs, u->temb_offs.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
+  u->jobs_dirty = false;
+  return 0;
+}
+
+// dgrad weight caches of every conv: one launch per optimizer step (lazily, by the next training forward)
+int pack_dgrad(cm_unet* u, cudaStream_t st) {
+  if (u->dpacked) return 0;
+  if (!u->dpack) {
+    CM_CUDA(cudaMalloc(&u->dpack, (u->dpack_elems + 8) * sizeof(__half)));
+    u->jobs_dirty = true;
+  }
+  if (int e = build_jobs(u)) return e;
+  if (int e = pack_all_enqueue(u->d_jobs + u->n_jobs_fwd, u->n_jobs_dgrad, st)) return e;
   u->dpacked = true;
   return 0;
 }
@@ -829,26 +931,27 @@ int prepare_train(cm_unet* u, int batch) {
     const Level& li = u->levels[op.in_level];
     const Level& lo = u->levels[u->tens[op.out].level];
     // data gradient of the main source: a conv over dOut (geometry of the OUTPUT grid)
+    const int dup = u->dgrad_dup;
     if (int rc = conv_prepare(&op.dlaunch, dgrad_mode_of(op.mode), u->g16[op.out], batch, lo.D, lo.H, lo.W,
-                              op.cout, nullptr, 0, u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
+                              dup * op.cout, nullptr, 0, u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
       return rc;
     op.dlaunch.p.out32 = u->g32[op.in];
     op.dplaunch.ok = false;
     if (op.mode == 0 && getenv("CM_NO_PLANE") == nullptr) {
-      if (int rc = plane_prepare(&op.dplaunch, u->g16[op.out], batch, lo.D, lo.H, lo.W, op.cout, nullptr, 0,
+      if (int rc = plane_prepare(&op.dplaunch, u->g16[op.out], batch, lo.D, lo.H, lo.W, dup * op.cout, nullptr, 0,
                                  u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
         return rc;
       if (op.dplaunch.ok) op.dplaunch.p.out32 = u->g32[op.in];
     }
     if (op.cin_extra) {
-      if (int rc = conv_prepare(&op.dxlaunch, 3, u->g16[op.out], batch, lo.D, lo.H, lo.W, op.cout, nullptr, 0,
+      if (int rc = conv_prepare(&op.dxlaunch, 3, u->g16[op.out], batch, lo.D, lo.H, lo.W, dup * op.cout, nullptr, 0,
                                 u->dpack + op.dxpack_off, op.cin_extra, u->cfg.weight_terms))
         return rc;
       op.dxlaunch.p.out32 = u->g32[op.extra];
     }
     const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
     if (int rc = wgrad_prepare(&op.wlaunch, op.mode, u->tens[op.in].p16, batch, li.D, li.H, li.W, op.cin, extra,
-                               op.cin_extra, u->g16[op.out], op.cout, u->G + op.g_off))
+                               op.cin_extra, u->g16[op.out], op.cout, u->G + op.g_off, dup * op.cout))
       return rc;
   }
   u->train_prepared = batch;
@@ -969,8 +1072,8 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           fan_init = !written[op.resid];
           written[op.resid] = 1;
         }
-        if (int e = cast_colsum_enqueue(u->g32[op.out], u->g16[op.out], fan, fan_init, cs, cs_ld, B, pix,
-                                        op.cout, st))
+        if (int e = cast_colsum_enqueue(u->g32[op.out], u->g16[op.out], u->dgrad_dup, fan, fan_init, cs, cs_ld, B,
+                                        pix, op.cout, st))
           return e;
         // bias gradients = batch sums of the channel sums: all convs in one launch after the op loop
         for (int bidx : {op.bias, op.bias2}) {
@@ -1051,8 +1154,7 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
   if (!rs_tab.empty()) {
     if (!u->d_rs_tab || u->rs_tab_host != rs_tab) {
       if (u->d_rs_tab && u->rs_tab_host.size() < rs_tab.size()) {
-        cudaFree(u->d_up_tab);
-  cudaFree(u->d_rs_tab);
+        cudaFree(u->d_rs_tab);
         u->d_rs_tab = nullptr;
       }
       if (!u->d_rs_tab) CM_CUDA(cudaMalloc(&u->d_rs_tab, rs_tab.size() * sizeof(long long)));
@@ -1148,6 +1250,9 @@ int cm_unet_create(const cm_unet_config* cfg, cm_unet** out) {
   u->cfg = *cfg;
   if (u->cfg.table_steps <= 0) u->cfg.table_steps = 1000;
   if (u->cfg.weight_terms <= 0) u->cfg.weight_terms = 2;
+  CM_CHECK(u->cfg.dgrad_terms >= 0 && u->cfg.dgrad_terms <= 2, "dgrad_terms must be 0 (default), 1 or 2");
+  u->dgrad_dup = u->cfg.dgrad_terms == 1 ? 1 : 2;
+  u->cfg.dgrad_terms = u->dgrad_dup;
   if (const char* e = getenv("CROWDMOD_FULLRES_TERMS")) {
     const int ft = atoi(e);
     if (ft == 1 || ft == 2) u->fullres_terms = ft < u->cfg.weight_terms ? ft : 0;
@@ -1172,6 +1277,9 @@ int cm_unet_destroy(cm_unet* u) {
   cudaFree(u->d_couts);
   cudaFree(u->d_offs);
   cudaFree(u->d_step);
+  cudaFree(u->d_chain);
+  cudaFree(u->d_jobs);
+  cudaFree(u->d_up_tab);
   cudaFree(u->d_tsteps);
   cudaFree(u->d_coef);
   cudaFree(u->dpack);
@@ -1193,18 +1301,15 @@ int cm_unet_param_info(const cm_unet* u, int idx, char* name, int name_cap, int6
   return 0;
 }
 
-int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_t numel) {
-  CM_CHECK(u && name, "null argument");
-  auto it = u->pindex.find(name);
-  CM_CHECK(it != u->pindex.end(), "unknown parameter '%s'", name);
-  ParamEntry& p = u->params[it->second];
-  CM_CHECK(p.numel() == numel, "parameter '%s': expected %lld elements, got %lld", name,
-           (long long)p.numel(), (long long)numel);
-  CM_CHECK((reinterpret_cast<uintptr_t>(dev_ptr) & 15) == 0, "parameter '%s' must be 16-byte aligned", name);
+static int bind_one(cm_unet* u, int idx, const float* dev_ptr) {
+  ParamEntry& p = u->params[idx];
+  CM_CHECK(dev_ptr != nullptr, "parameter '%s': null pointer", p.name.c_str());
+  CM_CHECK((reinterpret_cast<uintptr_t>(dev_ptr) & 15) == 0, "parameter '%s' must be 16-byte aligned", p.name.c_str());
   if (p.ptr != dev_ptr) {
     p.ptr = dev_ptr;
     u->packed = false;
     u->dpacked = false;
+    u->jobs_dirty = true;
     u->train_prepared = 0;
     if (u->graph_exec) {   // baked pointers are stale
       cudaGraphExecDestroy(u->graph_exec);
@@ -1216,50 +1321,30 @@ int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_
   return 0;
 }
 
+int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_t numel) {
+  CM_CHECK(u && name, "null argument");
+  auto it = u->pindex.find(name);
+  CM_CHECK(it != u->pindex.end(), "unknown parameter '%s'", name);
+  ParamEntry& p = u->params[it->second];
+  CM_CHECK(p.numel() == numel, "parameter '%s': expected %lld elements, got %lld", name,
+           (long long)p.numel(), (long long)numel);
+  return bind_one(u, it->second, dev_ptr);
+}
+
+int cm_unet_bind_params(cm_unet* u, const void* const* ptrs, int count) {
+  CM_CHECK(u && ptrs, "null argument");
+  CM_CHECK(count == (int)u->params.size(), "expected %d parameter pointers, got %d", (int)u->params.size(), count);
+  for (int i = 0; i < count; ++i)
+    if (int e = bind_one(u, i, static_cast<const float*>(ptrs[i]))) return e;
+  return 0;
+}
+
 int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
   CM_CHECK(u, "null handle");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = check_params_bound(u)) return e;
-  const int terms = u->cfg.weight_terms;
-  if (!u->wpack) CM_CUDA(cudaMalloc(&u->wpack, u->wpack_elems * sizeof(__half)));
-  for (Op& op : u->ops) {
-    if (op.type != OP_CONV) continue;
-    __half* dst = u->wpack + op.wpack_off;
-    const float* w = u->params[op.w].ptr;
-    if (op.mode == 2) {
-      if (int e = pack_upsample_weights(w, dst, op.cout, op.cin, terms, 1, st)) return e;
-    } else {
-      const float* wx = op.wx >= 0 ? u->params[op.wx].ptr : nullptr;
-      if (int e = pack_conv_weights(w, wx, dst, op.cout, op.cin, op.cin_extra, op.mode == 3 ? 1 : 27,
-                                    fwd_terms(u, op), 1, st))
-        return e;
-    }
-  }
-  if (int e = pack_conv_weights_padded(u->params[u->p_first_w].ptr, u->wpack + u->first_wpack_off,
-                                       u->cfg.base_channels, u->cfg.in_channels, 32,
-                                       u->fullres_terms > 0 ? u->fullres_terms : terms, 1, st))
-    return e;
-  const int nb = (int)u->temb_couts.size();
-  if (!u->d_wd) {
-    CM_CUDA(cudaMalloc(&u->d_wd, nb * sizeof(float*)));
-    CM_CUDA(cudaMalloc(&u->d_bd, nb * sizeof(float*)));
-    CM_CUDA(cudaMalloc(&u->d_couts, nb * sizeof(int)));
-    CM_CUDA(cudaMalloc(&u->d_offs, nb * sizeof(int)));
-    CM_CUDA(cudaMalloc(&u->temb_table, (size_t)u->cfg.table_steps * u->temb_ld * sizeof(float)));
-  }
-  {
-    std::vector<const float*> wd(nb), bd(nb);
-    for (int k = 0; k < nb; ++k) {
-      wd[k] = u->params[u->temb_dense_w[k]].ptr;
-      bd[k] = u->params[u->temb_dense_b[k]].ptr;
-    }
-    // pageable host sources: these copies are synchronous w.r.t. the host buffers
-    CM_CUDA(cudaMemcpyAsync(u->d_wd, wd.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaMemcpyAsync(u->d_bd, bd.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaMemcpyAsync(u->d_couts, u->temb_couts.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaMemcpyAsync(u->d_offs, u->temb_offs.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaStreamSynchronize(st));
-  }
+  if (int e = build_jobs(u)) return e;                      // no-op unless parameter storage moved
+  if (int e = pack_all_enqueue(u->d_jobs, u->n_jobs_fwd, st)) return e;
   if (build_time_table) {
     TembParams t{};
     t.table = u->params[u->p_table].ptr;
@@ -1271,7 +1356,7 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
     t.bd = u->d_bd;
     t.couts = u->d_couts;
     t.offs = u->d_offs;
-    t.nblocks = nb;
+    t.nblocks = (int)u->temb_couts.size();
     t.base = u->cfg.base_channels;
     t.E = u->cfg.base_channels * u->cfg.time_multiple;
     t.t = nullptr;
@@ -1306,6 +1391,7 @@ int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, const flo
   CM_CHECK(u && future && t && past && eps_out, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = ensure_ready(u, batch)) return e;
+  u->live_train_batch = 0;   // the arena is shared: a pending training backward can no longer run
   // per-sample time embedding projections (t may differ per sample: ddpm.py:113)
   TembParams tp{};
   tp.table = u->params[u->p_table].ptr;
@@ -1436,6 +1522,15 @@ int cm_unet_op_info(const cm_unet* u, int idx, char* tag, int tag_cap, int* type
   return 0;
 }
 
+double cm_unet_op_exec_flops(const cm_unet* u, int idx) {
+  if (!u || idx < 0 || idx >= (int)u->ops.size()) return 0.0;
+  double fl = 0.0;
+  cm_unet_op_info(u, idx, nullptr, 0, nullptr, &fl);
+  const Op& op = u->ops[idx];
+  if (op.type == OP_CONV && op.mode == 2) fl *= 8.0 / 27.0;
+  return fl;
+}
+
 int cm_unet_profile_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
                             float* eps_out, int batch, void* stream, float* ms_out, int cap) {
   CM_CHECK(u && future && t && past && eps_out && ms_out, "null argument");
@@ -1468,8 +1563,10 @@ int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
   CM_CHECK(u && a && a->past && a->x && a->tsteps && a->coef, "null argument");
   CM_CHECK(a->nsteps >= 1 && a->n >= 1, "nsteps and n must be >= 1");
   CM_CHECK(a->mode == 0 || a->mode == 1, "mode must be 0 (DDPM) or 1 (DDIM)");
+  CM_CHECK(a->use_graph >= 0 && a->use_graph <= 2, "use_graph must be 0 (eager), 1 (per-step graph) or 2 (whole-chain graph)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = ensure_ready(u, a->n)) return e;
+  u->live_train_batch = 0;   // the arena is shared: a pending training backward can no longer run
   for (int i = 0; i < a->nsteps; ++i)
     CM_CHECK(a->tsteps[i] >= 0 && a->tsteps[i] < u->cfg.table_steps, "tsteps[%d]=%d out of range", i,
              a->tsteps[i]);
@@ -1479,52 +1576,77 @@ int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
     CM_CUDA(cudaMalloc(&u->d_tsteps, a->nsteps * sizeof(int)));
     CM_CUDA(cudaMalloc(&u->d_coef, (size_t)a->nsteps * 8 * sizeof(float)));
     u->chain_cap = a->nsteps;
+    u->tsteps_host.clear();
+    u->coef_host.clear();
     if (u->graph_exec) {
       cudaGraphExecDestroy(u->graph_exec);
       u->graph_exec = nullptr;
     }
   }
-  // schedule tables + step counter (host -> device, synchronous w.r.t. the host arrays)
-  CM_CUDA(cudaMemcpyAsync(u->d_tsteps, a->tsteps, a->nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
-  CM_CUDA(cudaMemcpyAsync(u->d_coef, a->coef, (size_t)a->nsteps * 8 * sizeof(float),
-                          cudaMemcpyHostToDevice, st));
-  const int init[2] = {0, a->tsteps[0]};
-  CM_CUDA(cudaMemcpyAsync(u->d_step, init, sizeof(init), cudaMemcpyHostToDevice, st));
-  CM_CUDA(cudaStreamSynchronize(st));
+  // schedule tables: uploaded only when they differ from what the device already holds (the host
+  // vectors are the staging copies: the async copies read them, never the caller's arrays)
+  {
+    const bool same_t = (int)u->tsteps_host.size() == a->nsteps &&
+                        memcmp(u->tsteps_host.data(), a->tsteps, a->nsteps * sizeof(int)) == 0;
+    const bool same_c = (int)u->coef_host.size() == a->nsteps * 8 &&
+                        memcmp(u->coef_host.data(), a->coef, (size_t)a->nsteps * 8 * sizeof(float)) == 0;
+    if (!same_t || !same_c) {
+      // the previous chain may still be reading the device tables; the copy is stream-ordered behind it.
+      // The staging vectors are rewritten only here, after making sure the last upload has drained.
+      CM_CUDA(cudaStreamSynchronize(st));
+      u->tsteps_host.assign(a->tsteps, a->tsteps + a->nsteps);
+      u->coef_host.assign(a->coef, a->coef + (size_t)a->nsteps * 8);
+      CM_CUDA(cudaMemcpyAsync(u->d_tsteps, u->tsteps_host.data(), a->nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+      CM_CUDA(cudaMemcpyAsync(u->d_coef, u->coef_host.data(), (size_t)a->nsteps * 8 * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+      CM_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  const cm_unet_config& c = u->cfg;
+  const Level& l0 = u->levels[0];
+  const size_t x_bytes = (size_t)a->n * c.out_channels * l0.H * l0.W * c.future_len * sizeof(float);
+  const size_t past_bytes = (size_t)a->n * c.in_channels * l0.H * l0.W * c.past_len * sizeof(float);
+  CM_CUDA(cudaMemcpyAsync(u->chain_x, a->x, x_bytes, cudaMemcpyDeviceToDevice, st));
+  if (past_bytes) CM_CUDA(cudaMemcpyAsync(u->chain_past, a->past, past_bytes, cudaMemcpyDeviceToDevice, st));
+  if (int e = chain_begin_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, u->d_chain, a->seed, a->sample_offset, st))
+    return e;
 
   RunCtx rc{};
   rc.batch = a->n;
-  rc.future = a->x;
-  rc.past = a->past;
+  rc.future = u->chain_x;
+  rc.past = u->chain_past;
   rc.temb = u->temb_table;
   rc.t_dev = u->d_step + 1;
   rc.temb_bstride = 0;
   rc.fin = FinalParams{};
-  rc.fin.x = a->x;
+  rc.fin.x = u->chain_x;
   rc.fin.coef = u->d_coef;
   rc.fin.step_dev = u->d_step;
   rc.fin.mode = a->mode;
   rc.fin.noise = a->noise;
-  rc.fin.seed = a->seed;
-  rc.fin.sample_offset = a->sample_offset;
+  rc.fin.chain_dev = u->d_chain;
   rc.fin.history = a->history;
 
   u->last_chain_launches = 0;
+  u->last_chain_graph_launches = 0;
+  u->last_chain_graph_rebuilt = 0;
   if (!a->use_graph) {
     for (int i = 0; i < a->nsteps; ++i) {
       if (int e = run_ops(u, rc, st, &u->last_chain_launches)) return e;
       if (int e = advance_step_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, a->nsteps, st)) return e;
       ++u->last_chain_launches;
     }
+    CM_CUDA(cudaMemcpyAsync(a->x, u->chain_x, x_bytes, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
-  // One denoiser step (+ update + step advance) captured once; the graph reads the step index
-  // from device memory, so the same executable graph is replayed for every step.
+  // The captured work reads the step index, the timestep, the Philox seed / shard offset and x / past from
+  // buffers the handle owns, so one executable graph serves every chain of this (n, nsteps, mode, noise,
+  // history, kind).  kind 1: one denoiser step (+ update + step advance), replayed nsteps times.
+  // kind 2: the same step as the body of a conditional WHILE node whose condition the step-advance kernel
+  // sets from the device step counter -> the whole T-step loop is ONE graph launch (ddpm.py:214-231).
   const cm_chain_args& k = u->graph_key;
-  const bool reuse = u->graph_exec && k.past == a->past && k.x == a->x && k.n == a->n &&
-                     k.mode == a->mode && k.noise == a->noise && k.seed == a->seed &&
-                     k.sample_offset == a->sample_offset && k.history == a->history &&
-                     k.nsteps == a->nsteps;
+  const bool reuse = u->graph_exec && k.n == a->n && k.mode == a->mode && k.noise == a->noise &&
+                     k.history == a->history && k.nsteps == a->nsteps && k.use_graph == a->use_graph;
   int64_t per_step = 0;
   if (!reuse) {
     if (u->graph_exec) {
@@ -1533,28 +1655,69 @@ int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
     }
     cudaStream_t cs;
     CM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    CM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    int e = run_ops(u, rc, cs, &per_step);
-    if (!e) e = advance_step_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, a->nsteps, cs);
-    ++per_step;
     cudaGraph_t g = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(cs, &g);
-    cudaStreamDestroy(cs);
-    if (e) {
-      if (g) cudaGraphDestroy(g);
-      return e;
+    int e = 0;
+    cudaError_t ce = cudaSuccess;
+    if (a->use_graph == 1) {
+      ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        e = run_ops(u, rc, cs, &per_step);
+        if (!e) e = advance_step_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, a->nsteps, cs);
+        ++per_step;
+        ce = cudaStreamEndCapture(cs, &g);
+      }
+    } else {
+      cudaGraphConditionalHandle h;
+      cudaGraph_t body = nullptr;
+      ce = cudaGraphCreate(&g, 0);
+      if (ce == cudaSuccess) ce = cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault);
+      if (ce == cudaSuccess) {
+        cudaGraphNodeParams np{};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = h;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        ce = cudaGraphAddNode(&node, g, nullptr, 0, &np);
+        if (ce == cudaSuccess) body = np.conditional.phGraph_out[0];
+      }
+      if (ce == cudaSuccess)
+        ce = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        e = run_ops(u, rc, cs, &per_step);
+        if (!e) e = advance_step_cond_enqueue(u->d_step, u->d_step + 1, u->d_tsteps, a->nsteps, h, cs);
+        ++per_step;
+        cudaGraph_t done = nullptr;
+        ce = cudaStreamEndCapture(cs, &done);
+      }
     }
-    CM_CUDA(ce);
+    cudaStreamDestroy(cs);
+    if (e || ce != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (e) return e;
+      CM_CUDA(ce);
+    }
     CM_CUDA(cudaGraphInstantiate(&u->graph_exec, g, 0));
     cudaGraphDestroy(g);
     u->graph_key = *a;
     u->graph_launches_per_step = per_step;
+    u->last_chain_graph_rebuilt = 1;
   } else {
     per_step = u->graph_launches_per_step;
   }
-  for (int i = 0; i < a->nsteps; ++i) CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
+  if (a->use_graph == 1) {
+    for (int i = 0; i < a->nsteps; ++i) CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
+    u->last_chain_graph_launches = a->nsteps;
+  } else {
+    CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
+    u->last_chain_graph_launches = 1;
+  }
   u->last_chain_launches = per_step * a->nsteps;
+  CM_CUDA(cudaMemcpyAsync(a->x, u->chain_x, x_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
+
+int64_t cm_last_chain_graph_launches(const cm_unet* u) { return u ? u->last_chain_graph_launches : -1; }
+int cm_last_chain_graph_rebuilt(const cm_unet* u) { return u ? u->last_chain_graph_rebuilt : -1; }
 
 }  // extern "C"

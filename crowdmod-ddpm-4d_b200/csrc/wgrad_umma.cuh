@@ -227,13 +227,14 @@ struct WgradLaunch {
 // `mode` = forward conv mode (0 k3 s1, 1 k3 s2, 2 nearest-x2 + k3 as 8 phases, 3 1x1x1).
 // act: forward input [B,D,H,W,cin]; extra: [B,od,oh,ow,cin_extra] or null; dout: fp16
 // [B,od',oh',ow',cout] (the forward output grid).  G: fp32 [nphase][krows][cout], pre-zeroed.
+// dout_ld: channel stride of a dOut pixel row (0 -> cout; 2*cout for a K-concatenated hi|lo pair, hi half read)
 int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
-                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G);
+                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G, int dout_ld = 0);
 int wgrad_enqueue(const WgradLaunch& L, cudaStream_t st);
 int wgrad_init();
 size_t wgrad_g_elems(int mode, int cin, int cin_extra, int cout);
 
 int make_act_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int bk,
-                 int lower_w, int lower_h, int lower_d, int stride, int upper_delta);
+                 int lower_w, int lower_h, int lower_d, int stride, int upper_delta, int ld = 0);
 
 }  // namespace cm

@@ -40,6 +40,22 @@ _PLANS: "weakref.WeakKeyDictionary[nn.Module, Dict[Tuple[int, int, int, int], _N
     weakref.WeakKeyDictionary()
 
 
+def _graph_mode(use_graph) -> int:
+    """cm_chain_args.use_graph: False/0 eager, 1 / "step" per-step graph replay, True / 2 / "chain" the whole
+    chain as ONE graph (conditional WHILE node).  CROWDMOD_CHAIN_GRAPH={eager,step,chain} overrides True."""
+    if use_graph is False or use_graph == 0:
+        return 0
+    if use_graph is True:
+        use_graph = os.environ.get("CROWDMOD_CHAIN_GRAPH", "chain")
+    if use_graph in (1, "step"):
+        return 1
+    if use_graph in (2, "chain"):
+        return 2
+    if use_graph == "eager":
+        return 0
+    raise ValueError(f"use_graph={use_graph!r}: expected False, True, 'eager', 'step' or 'chain'")
+
+
 class _NativePlan:
     """One native handle per tensor geometry (rows, cols, past_len, future_len)."""
 
@@ -61,12 +77,21 @@ class _NativePlan:
         cfg.past_len, cfg.future_len = past_len, future_len
         cfg.table_steps = module.time_embeddings.total_time_steps
         cfg.weight_terms = int(os.environ.get("CROWDMOD_WEIGHT_TERMS", "2"))
+        cfg.dgrad_terms = int(os.environ.get("CROWDMOD_DGRAD_TERMS", "2"))
         self.handle = C.c_void_p()
         n.check(n.lib().cm_unet_create(C.byref(cfg), C.byref(self.handle)))
         self._bound: Optional[Tuple] = None
+        self._versions: Optional[Tuple] = None
         self._table_ready = False
+        # everything that only depends on the plan is looked up once (169 ctypes calls per name walk)
+        self._names = self._query_names()
+        self._tensors = None          # parameter / buffer tensors in plan order
+        self._ptr_array = None
+        self._grad_layout = None
+        self._dropout_layout = None
+        self.train_token = 0
 
-    def names(self):
+    def _query_names(self):
         lib = self.n.lib()
         out = []
         buf = C.create_string_buffer(256)
@@ -77,22 +102,52 @@ class _NativePlan:
             out.append((buf.value.decode(), tuple(shape[j] for j in range(nd.value))))
         return out
 
+    def names(self):
+        return self._names
+
+    def tensors(self, module: "UNet"):
+        """The module's parameter / buffer tensors in plan (= state_dict) order.  The list is rebuilt when
+        the module's tensors were replaced (load_state_dict keeps them, .to() / _apply drops the plan)."""
+        if self._tensors is None:
+            sd = module.state_dict(keep_vars=True)
+            missing = [nm for nm, _ in self._names if nm not in sd]
+            if missing:
+                raise RuntimeError(f"UNet state_dict lacks {missing[:3]}... expected by the native plan")
+            self._tensors = [sd[nm] for nm, _ in self._names]
+        return self._tensors
+
+    def invalidate(self):
+        """Forget what is bound / packed: the next call re-binds every tensor and re-derives the caches."""
+        self._tensors = None
+        self._bound = None
+        self._versions = None
+        self._table_ready = False
+
     def sync(self, module: "UNet", need_table: bool):
-        """(Re)bind fp32 parameter storage and re-derive the packed caches when any parameter
-        was replaced or modified in place (optimizer.step / load_state_dict bump _version)."""
-        sd = module.state_dict(keep_vars=True)
-        key = tuple((t.data_ptr(), t._version) for t in sd.values())
-        if key == self._bound and (self._table_ready or not need_table):
+        """(Re)bind fp32 parameter storage (one C call) and re-derive the packed caches (one launch, no
+        synchronisation) when a parameter was replaced or modified in place (optimizer.step /
+        load_state_dict bump ``_version``; writes through ``p.data`` do NOT: call
+        ``UNet.invalidate_native_cache()`` after such surgery)."""
+        ts = self.tensors(module)
+        ptrs = tuple(t.data_ptr() for t in ts)
+        vers = tuple(t._version for t in ts)
+        if ptrs == self._bound and vers == self._versions and (self._table_ready or not need_table):
             return
         lib = self.n.lib()
-        for name, t in sd.items():
-            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
-                raise RuntimeError(
-                    f"UNet parameter '{name}' must be a contiguous fp32 CUDA tensor "
-                    f"(got {t.dtype} on {t.device}); move the module with .to('cuda')")
-            self.n.check(lib.cm_unet_set_param(self.handle, name.encode(), self.n.ptr(t), t.numel()))
+        if ptrs != self._bound:
+            for (name, shape), t in zip(self._names, ts):
+                if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                    raise RuntimeError(
+                        f"UNet parameter '{name}' must be a contiguous fp32 CUDA tensor "
+                        f"(got {t.dtype} on {t.device}); move the module with .to('cuda')")
+                if tuple(t.shape) != tuple(shape):
+                    raise RuntimeError(f"UNet parameter '{name}': shape {tuple(t.shape)} != plan {tuple(shape)}")
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            self.n.check(lib.cm_unet_bind_params(self.handle, arr, len(ptrs)))
+            self._ptr_array = arr
         self.n.check(lib.cm_unet_pack(self.handle, 1 if need_table else 0, self.n.current_stream()))
-        self._bound = key
+        self._bound = ptrs
+        self._versions = vers
         self._table_ready = bool(need_table)
 
     def __del__(self):
@@ -206,6 +261,7 @@ class UNet(nn.Module):
         rows, cols, past_len, future_len = self._geometry(future, past)
         plan = self._plan(rows, cols, past_len, future_len)
         plan.sync(self, need_table=False)
+        plan.train_token += 1            # the arena is shared: a pending training backward must raise
         future = future.contiguous().float()
         past = past.contiguous().float()
         t = t.contiguous().to(torch.int64)
@@ -230,6 +286,7 @@ class UNet(nn.Module):
         rows, cols, past_len, future_len = self._geometry(x, past)
         plan = self._plan(rows, cols, past_len, future_len)
         plan.sync(self, need_table=True)
+        plan.train_token += 1
         assert x.is_contiguous() and x.dtype == torch.float32
         assert past.is_contiguous() and past.dtype == torch.float32
         tsteps = tsteps.to(torch.int32).contiguous().cpu()
@@ -250,13 +307,25 @@ class UNet(nn.Module):
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         a.sample_offset = int(sample_offset)
         a.history = history.data_ptr() if history is not None else None
-        a.use_graph = 1 if use_graph else 0
+        a.use_graph = _graph_mode(use_graph)
         n.check(n.lib().cm_ddpm_sample(plan.handle, C.byref(a), n.current_stream()))
         return x
 
     def last_chain_launches(self, rows, cols, past_len, future_len) -> int:
         n = _native()
         return int(n.lib().cm_last_chain_launches(self._plan(rows, cols, past_len, future_len).handle))
+
+    def invalidate_native_cache(self):
+        """Call after modifying parameters through ``p.data`` (EMA swaps, manual weight surgery): such writes do
+        not bump ``_version``, so the packed fp16 weights / time-embedding table would stay stale."""
+        for plan in _PLANS.get(self, {}).values():
+            plan.invalidate()
+
+    def last_chain_graph_stats(self, rows, cols, past_len, future_len):
+        """(cudaGraphLaunch calls of the last chain, whether it had to rebuild its graph)."""
+        n = _native()
+        h = self._plan(rows, cols, past_len, future_len).handle
+        return int(n.lib().cm_last_chain_graph_launches(h)), bool(n.lib().cm_last_chain_graph_rebuilt(h))
 
     def native_stats(self, rows, cols, past_len, future_len):
         """(kernel launches per forward, algorithmic FLOPs per sample) of the native plan."""

@@ -5,9 +5,10 @@ Replaces the graph autograd records for ``DDPM_model._train_step`` + ``loss.back
 ``cm_unet_train_forward`` (forward that keeps activations, GroupNorm statistics and time-MLP
 pre-activations resident) and ``cm_unet_backward`` (dgrad / wgrad of every conv on tcgen05,
 GroupNorm / SiLU / Dropout3d / attention / time-MLP backward), which fills ONE flat fp32 gradient
-buffer.  When ``torch.distributed`` is initialised with world_size > 1 the flat buffer is
-all-reduced (mean) in a single NCCL call before the per-parameter views are handed to autograd —
-the data-parallel exchange step of SURVEY.md §8(e).
+buffer.  Data-parallel training is OPT-IN (``enable_data_parallel(module, group)``, called by
+``DDPM_model.enable_data_parallel``): the flat buffer is then all-reduced (mean) in a single NCCL call
+before the per-parameter views are handed to autograd — the data-parallel exchange step of SURVEY.md
+§8(e).  A process group that merely happens to be initialised is never used implicitly.
 
 There is no eager fallback: a missing library or a CPU tensor raises.
 """
@@ -20,6 +21,12 @@ import torch
 
 def dropout_layout(plan):
     """[(offset, channels)] per ResnetBlock (plan order) and the row stride of the scale table."""
+    if plan._dropout_layout is None:
+        plan._dropout_layout = _dropout_layout(plan)
+    return plan._dropout_layout
+
+
+def _dropout_layout(plan):
     n = plan.n
     lib = n.lib()
     ld = C.c_int32()
@@ -31,6 +38,12 @@ def dropout_layout(plan):
 
 
 def grad_layout(plan):
+    if plan._grad_layout is None:
+        plan._grad_layout = _grad_layout(plan)
+    return plan._grad_layout
+
+
+def _grad_layout(plan):
     n = plan.n
     lib = n.lib()
     cnt = lib.cm_unet_param_count(plan.handle)
@@ -40,11 +53,33 @@ def grad_layout(plan):
     return [offs[i] for i in range(cnt)], total.value
 
 
-def _allreduce_mean(flat):
+_DP_UNSET = object()
+
+
+def enable_data_parallel(module, group=None):
+    """Opt in to gradient averaging over ``group`` (None = the default process group).  The caller is
+    responsible for starting every rank from the same parameters (DDPM_model.enable_data_parallel
+    broadcasts them)."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.mul_(1.0 / dist.get_world_size())
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
+    module._dp_group = group          # None is a valid group handle (the default group)
+    module._dp_enabled = True
+
+
+def disable_data_parallel(module):
+    module._dp_enabled = False
+
+
+def _allreduce_mean(module, flat):
+    if not getattr(module, "_dp_enabled", False):
+        return
+    import torch.distributed as dist
+    group = getattr(module, "_dp_group", None)
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
 
 
 class _UNetFunction(torch.autograd.Function):
@@ -56,7 +91,7 @@ class _UNetFunction(torch.autograd.Function):
                           dtype=torch.float32)
         n.check(n.lib().cm_unet_train_forward(plan.handle, n.ptr(future), n.ptr(t), n.ptr(past), n.ptr(eps),
                                               B, n.ptr(drop), n.current_stream()))
-        plan.train_token = getattr(plan, "train_token", 0) + 1
+        plan.train_token += 1
         ctx.token = plan.train_token
         ctx.plan = plan
         ctx.module = module
@@ -68,15 +103,16 @@ class _UNetFunction(torch.autograd.Function):
     def backward(ctx, d_eps):
         plan = ctx.plan
         n = plan.n
-        if ctx.token != getattr(plan, "train_token", 0):
+        if ctx.token != plan.train_token:
             raise RuntimeError(
                 "crowdmod-ddpm-4d_b200: the activations of this forward were overwritten by a later "
-                "training forward of the same UNet geometry (one backward per forward)")
+                "forward or sampling call of the same UNet geometry (one backward per forward, and "
+                "nothing else on that geometry in between)")
         offs, total = grad_layout(plan)
         flat = torch.empty(total, device=d_eps.device, dtype=torch.float32)
         d_eps = d_eps.contiguous().float()
         n.check(n.lib().cm_unet_backward(plan.handle, n.ptr(d_eps), n.ptr(flat), n.current_stream()))
-        _allreduce_mean(flat)
+        _allreduce_mean(ctx.module, flat)
         ctx.module._last_flat_grad = flat
         grads = []
         for (shape, req), off in zip(ctx.param_meta, offs):
@@ -112,7 +148,4 @@ def unet_train_forward(module, future, t, past):
     past = past.detach().contiguous().float()
     t = t.contiguous().to(torch.int64)
     drop = draw_dropout_scales(module, plan, future.shape[0], future.device)
-    names = [nm for nm, _ in plan.names()]
-    sd = module.state_dict(keep_vars=True)
-    params = [sd[nm] for nm in names]
-    return _UNetFunction.apply(module, plan, future, t, past, drop, *params)
+    return _UNetFunction.apply(module, plan, future, t, past, drop, *plan.tensors(module))

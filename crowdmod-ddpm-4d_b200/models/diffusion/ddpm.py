@@ -112,15 +112,20 @@ def shard_samples(nsamples, rank, world):
 
 
 class _RunningMean:
+    """Epoch mean of the step losses (torchmetrics.MeanMetric in the reference, ddpm.py:125,146,150).  The sum
+    is kept ON THE DEVICE in fp64 and read once per epoch: the reference's per-step ``loss.item()``
+    (ddpm.py:145) would stall the host on every step and leave the GPU idle while Python prepares the next."""
+
     def __init__(self):
-        self.total, self.count = 0.0, 0
+        self.total, self.count = None, 0
 
     def update(self, v):
-        self.total += float(v)
+        v = v.detach().double() if torch.is_tensor(v) else torch.tensor(float(v), dtype=torch.float64)
+        self.total = v.clone() if self.total is None else self.total + v
         self.count += 1
 
     def compute(self):
-        return self.total / max(self.count, 1)
+        return float(self.total.item()) / max(self.count, 1) if self.total is not None else 0.0
 
 
 class DDPM_model:
@@ -137,8 +142,11 @@ class DDPM_model:
         self.denoiser.to(self.device)
 
         solver = self.denoiser_cfg.TRAIN.SOLVER
+        # same optimizer object / state_dict layout as the reference (ddpm.py:53-56); fused=True runs the
+        # coupled-L2 Adam update of all 169 tensors as one multi-tensor kernel instead of ~10 foreach passes
         self.optimizer = torch.optim.Adam(self.denoiser.parameters(), lr=solver.LR,
-                                          betas=tuple(solver.BETAS), weight_decay=solver.WEIGHT_DECAY)
+                                          betas=tuple(solver.BETAS), weight_decay=solver.WEIGHT_DECAY,
+                                          fused=self.device.type == "cuda")
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(
             self.optimizer, mode='min', factor=solver.SCHEDULER.FACTOR,
             patience=solver.SCHEDULER.PATIENCE, min_lr=solver.SCHEDULER.MIN_LR)
@@ -146,6 +154,30 @@ class DDPM_model:
         self.noise_source = None      # callable(nsteps, shape, device) -> [nsteps,*shape] injected z
         self.sample_offset = 0        # global index of this shard's first sample (Philox counter)
         self.use_cuda_graph = True
+        # data-parallel training is opt-in (enable_data_parallel); a process group that merely exists is ignored
+        self.data_parallel = False
+        self.dp_group = None
+        self.rank, self.world = 0, 1
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, group=None):
+        """One process per GPU, global batch split over the ranks: broadcasts rank 0's parameters so every
+        replica starts from the same model, then averages the flat gradient buffer with ONE all-reduce per
+        step.  The epoch loss is averaged over ranks before ReduceLROnPlateau / best-checkpoint decisions, the
+        random extra-checkpoint epochs are drawn on rank 0, and only rank 0 writes checkpoints."""
+        import torch.distributed as dist
+        from ..backbones.unet_autograd import enable_data_parallel
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("enable_data_parallel: call torch.distributed.init_process_group first")
+        self.dp_group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        with torch.no_grad():
+            for t in self.denoiser.state_dict().values():
+                dist.broadcast(t, src=src, group=group)
+        enable_data_parallel(self.denoiser, group)
+        self.data_parallel = True
+        return self
 
     def _get_denoiser_cfg(self):
         gen_model_key, backbone_key = self.arch.upper().split('-')
@@ -184,8 +216,17 @@ class DDPM_model:
             self.optimizer.zero_grad(set_to_none=True)
             loss.backward()
             self.optimizer.step()
-            loss_record.update(loss.detach().item())
-        return loss_record.compute()
+            loss_record.update(loss.detach())
+        epoch_loss = loss_record.compute()
+        if self.device.type == "cuda":
+            from ..backbones.unet import _native
+            _native().check_device_error(f"training epoch {epoch}")   # e.g. a saturated fp16 gradient operand
+        if self.data_parallel and self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([epoch_loss], device=self.device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.dp_group)
+            epoch_loss = float(t.item()) / self.world
+        return epoch_loss
 
     def train(self, batched_train_data, baseline_ckpt=None):
         forward_sampler = DDPM(timesteps=self.cfg.MODEL.DDPM.TIMESTEPS, scale=self.cfg.MODEL.DDPM.SCALE)
@@ -200,6 +241,13 @@ class DDPM_model:
         epochs = self.denoiser_cfg.TRAIN.EPOCHS
         epochs_cktp_to_save = np.random.randint(int(epochs * 0.75), epochs + 1,
                                                 size=self.cfg.MODEL.DDPM.CHECKPOINTS_TO_KEEP)
+        if self.data_parallel and self.world > 1:      # every rank keeps rank 0's draw
+            import torch.distributed as dist
+            t = torch.as_tensor(epochs_cktp_to_save, dtype=torch.int64, device=self.device)
+            src = dist.get_global_rank(self.dp_group, 0) if self.dp_group is not None else 0
+            dist.broadcast(t, src=src, group=self.dp_group)
+            epochs_cktp_to_save = t.cpu().numpy()
+        writer = (not self.data_parallel) or self.rank == 0
         for epoch in range(1, epochs + 1):
             torch.cuda.empty_cache()
             gc.collect()
@@ -218,8 +266,9 @@ class DDPM_model:
                 consecutive_nan_count = 0
             if epoch_loss < best_loss:
                 best_loss = epoch_loss
-                save_checkpoint(self.optimizer, self.denoiser, "000", self.cfg, self.arch)
-            if epoch in epochs_cktp_to_save:
+                if writer:
+                    save_checkpoint(self.optimizer, self.denoiser, "000", self.cfg, self.arch)
+            if epoch in epochs_cktp_to_save and writer:
                 logging.info(f"Epoch {epoch}: in checkpoints_to_keep set, saving model.")
                 save_checkpoint(self.optimizer, self.denoiser, epoch, self.cfg, self.arch)
         logging.info(f"Trained model {self.arch} saved in {self.cfg.DATA_FS.SAVE_DIR}")
@@ -241,6 +290,8 @@ class DDPM_model:
         self.denoiser.sample_chain(past, x, tsteps, coef, mode=mode, noise=noise, seed=seed,
                                    sample_offset=self.sample_offset, history=hist,
                                    use_graph=self.use_cuda_graph)
+        from ..backbones.unet import _native
+        _native().check_device_error("the reverse chain")     # synchronises: x_0 is about to be read anyway
         return hist
 
     def _guidance(self):

@@ -44,6 +44,8 @@ typedef struct cm_unet_config {
   int32_t past_len, future_len;  /* DATASET.PAST_LEN / FUTURE_LEN                 */
   int32_t table_steps;      /* rows of the sinusoid table (1000, embeddings.py:7) */
   int32_t weight_terms;     /* 1: fp16 weights, 2: fp16 hi+lo split weights       */
+  int32_t dgrad_terms;      /* training: dOut operand of every data-gradient conv: 1 = single fp16,
+                               2 = K-concatenated hi+lo fp16 pair (0 -> 2)        */
 } cm_unet_config;
 
 typedef struct cm_unet cm_unet;   /* opaque */
@@ -63,8 +65,12 @@ CM_API int cm_unet_param_info(const cm_unet* u, int idx, char* name, int name_ca
                        int* ndim);
 /* Bind the fp32 device tensor of state_dict entry `name` (not copied: must stay alive). */
 CM_API int cm_unet_set_param(cm_unet* u, const char* name, const float* dev_ptr, int64_t numel);
+/* Bind every state_dict entry in one call: ptrs[i] = fp32 device tensor of entry i (the order of
+ * cm_unet_param_info), count = cm_unet_param_count.  Cheap when nothing moved. */
+CM_API int cm_unet_bind_params(cm_unet* u, const void* const* ptrs, int count);
 /* Re-derive the kernel-layout caches (fp16 packed weights, time-embedding projection table)
- * from the bound fp32 parameters.  Call after load_state_dict / optimizer.step. */
+ * from the bound fp32 parameters: ONE table-driven launch, stream-ordered, no host synchronisation
+ * (unless parameter storage moved since the last call).  Call after load_state_dict / optimizer.step. */
 CM_API int cm_unet_pack(cm_unet* u, int build_time_table, void* stream);
 /* Size internal workspaces + TMA descriptors for batches up to `batch` (allocates; not
  * capturable).  Returns bytes via *bytes if non-NULL. */
@@ -107,6 +113,9 @@ CM_API int64_t cm_last_backward_launches(const cm_unet* u);
 CM_API int cm_unet_op_count(const cm_unet* u);
 CM_API int cm_unet_op_info(const cm_unet* u, int idx, char* tag, int tag_cap, int* type,
                            double* flops_per_sample);
+/* FLOPs per sample op `idx` actually EXECUTES: as cm_unet_op_info except that the UpSample convs count
+ * their 8 phase convs of 2x2x2 folded taps (8/27 of the dense 27-tap formulation). */
+CM_API double cm_unet_op_exec_flops(const cm_unet* u, int idx);
 CM_API int cm_unet_profile_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
                                    float* eps_out, int batch, void* stream, float* ms_out, int cap);
 
@@ -124,12 +133,20 @@ typedef struct cm_chain_args {
                                g = lambda*sigma for Sparsity guidance, else 0       */
   int32_t mode;             /* 0 DDPM, 1 DDIM                                       */
   const float* noise;       /* device [nsteps][n*C*H*W*F] injected z, or NULL -> Philox(seed) */
-  uint64_t seed;
+  uint64_t seed;            /* passed through device memory: a new seed re-uses the graph */
   int64_t sample_offset;    /* global index of sample 0 (shard-invariant Philox)    */
   float* history;           /* optional device [nsteps+1][n*C*H*W*F] (slot 0 = x_T by caller) */
-  int32_t use_graph;        /* 1: capture one step as a CUDA graph and replay it    */
+  int32_t use_graph;        /* 0: eager launches; 1: one step captured as a CUDA graph, replayed
+                               nsteps times; 2: the WHOLE chain as one graph (a conditional WHILE
+                               node over the device step counter): one cudaGraphLaunch per chain */
 } cm_chain_args;
+/* past / x are copied into the handle's own staging buffers first (and x_0 back at the end), so the
+ * cached graph depends on (n, nsteps, mode, noise, history) only; nothing synchronises. */
 CM_API int cm_ddpm_sample(cm_unet* u, const cm_chain_args* args, void* stream);
+/* cudaGraphLaunch calls issued by the last cm_ddpm_sample (1 in mode 2, nsteps in mode 1, 0 eager) and
+ * whether that call had to (re)build its graph. */
+CM_API int64_t cm_last_chain_graph_launches(const cm_unet* u);
+CM_API int cm_last_chain_graph_rebuilt(const cm_unet* u);
 /* kernels enqueued by the last cm_ddpm_sample call (for bench accounting) */
 CM_API int64_t cm_last_chain_launches(const cm_unet* u);
 
@@ -165,6 +182,10 @@ CM_API int cm_op_final_conv(const void* act16, const float* w, const float* bias
  * restatement (test only). */
 CM_API int cm_op_conv3d_dgrad(int mode, const void* dout16, int B, int D, int H, int W, int cin,
                               const float* w, int cout, int terms, float* dx32, void* stream);
+/* As cm_op_conv3d_dgrad from the fp32 gradient: casts to the fp16 operand (dup = 1) or to the
+ * K-concatenated hi|lo pair (dup = 2) exactly as the training backward does. */
+CM_API int cm_op_conv3d_dgrad_f32(int mode, const float* dout32, int B, int D, int H, int W, int cin,
+                                  const float* w, int cout, int terms, int dup, float* dx32, void* stream);
 CM_API int cm_op_conv3d_wgrad(int mode, const void* act16, int B, int D, int H, int W, int cin,
                               const void* extra16, int cin_extra, const void* dout16, int cout,
                               float* dw, float* dwx, int impl, void* stream);

@@ -150,8 +150,16 @@ def schedule_case(ns):
 
 
 def main():
+    """python -m oracle.make_golden [case ...]: regenerate every golden, or only the named ones."""
     ns = ref_shim.load()
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
+    if only:
+        # the full 1000-step chain of BASELINE config #2 at n = 2 (north_star gate 3: output statistics of the
+        # whole chain; reference loop models/diffusion/ddpm.py:206-236)
+        if "chain_atc_T1000" in only:
+            chain_case(ns, "chain_atc_T1000", ATC, 42, 2, 12, 36, 5, 3, 1000, 0.5, "None", "DDPM")
+        return
     schedule_case(ns)
     unet_case(ns, "unet_atc_b2", ATC, 42, 2, 12, 36, 5, 3, [7, 640])
     unet_case(ns, "unet_small_b3", SMALL, 11, 3, 4, 4, 2, 2, [0, 999, 31])
@@ -163,6 +171,7 @@ def main():
     train_case(ns, "train_small", SMALL, 11, 3, 4, 4, 2, 2, 1000, 0.5)
     kw = dict(ATC, dropout_rate=0.0)
     train_case(ns, "train_atc_b2", kw, 42, 2, 12, 36, 5, 3, 1000, 0.5)
+    chain_case(ns, "chain_atc_T1000", ATC, 42, 2, 12, 36, 5, 3, 1000, 0.5, "None", "DDPM")
 
 
 if __name__ == "__main__":

@@ -320,6 +320,28 @@ def test_conv_dgrad_vs_torch_autograd(nat, case):
 
 
 @pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d" % c)
+@pytest.mark.parametrize("dup", [2, 1], ids=["hilo", "single"])
+def test_conv_dgrad_from_fp32_gradient_hi_lo_pair(nat, case, dup):
+    """The training backward's dgrad operand: an fp32 gradient cast to fp16 (dup = 1: rounding error ~2.8e-4
+    per element) or to a K-concatenated hi|lo fp16 pair (dup = 2: exact to 2^-22), against torch autograd on
+    the UNROUNDED fp32 gradient.  Bounds: 2e-5 (hi|lo: fp32 accumulation order only) / 1e-3 (single)."""
+    mode, B, D, H, W, cin, cout, cx = case
+    act, w, _, _, _ = _bwd_inputs(*case)
+    od, oh, ow = _out_grid(mode, D, H, W)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    dout32 = torch.randn(B, od, oh, ow, cout, device="cuda", generator=g) * 3.0
+    dx = torch.full((B, D, H, W, cin), float("nan"), device="cuda")
+    nat.check(nat.lib().cm_op_conv3d_dgrad_f32(mode, nat.ptr(dout32), B, D, H, W, cin, nat.ptr(w), cout, 2, dup,
+                                               nat.ptr(dx), nat.current_stream()))
+    torch.cuda.synchronize()
+    assert nat.lib().cm_device_error() == 0
+    ref, _, _ = torch_conv_grads(mode, act, None, w, None, dout32)
+    e = rel_l2(dx, ref)
+    print(f"dgrad from fp32 dOut, dup={dup}: rel-L2 {e:.3e}")
+    assert e <= (2e-5 if dup == 2 else 1e-3), f"dgrad rel-L2 {e:.3e}; " + describe_mismatch(dx, ref)
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d" % c)
 @pytest.mark.parametrize("impl", [1, 0], ids=["scalar", "umma"])
 def test_conv_wgrad_vs_torch_autograd(nat, case, impl):
     mode, B, D, H, W, cin, cout, cx = case

@@ -3,14 +3,12 @@ autograd (cm_unet_train_forward / cm_unet_backward through the C ABI) against (a
 autograd on identical weights, t, eps — per-parameter-tensor gradients — and (b) the golden
 loss / gradient norms / random projections generated from the unmodified reference.
 
-Tolerances (BASELINE.json north_star: "training loss and gradients within 1e-3"): loss relative
-error <= 1e-3; global gradient-vector rel-L2 <= GRAD_TOL; every parameter tensor rel-L2 <=
-TENSOR_TOL (fp16 MMA operands, fp32 accumulation, fp32 everything else).  TENSOR_TOL is looser than
-the global bound because the smallest tensors (the 32..128-element GroupNorm affine gradients) carry
-the fp16 operand noise of a whole dgrad chain on a tiny norm: across numerically equivalent orders of the
-GroupNorm statistics merge the worst one moved between 2.0e-3 and 3.0e-3 while the global figure stayed
-at 7e-4..9e-4.
+Tolerances (BASELINE.json north_star: "training loss and gradients within 1e-3"): loss
+relative error <= 1e-3; global gradient-vector rel-L2 <= GRAD_TOL = 1e-3; EVERY parameter tensor rel-L2 <=
+TENSOR_TOL = 1e-3, except the tensors named in TENSOR_EXCEPTIONS, each with its own measured bound and the
+reason (see the table).  There is no blanket loosening.
 """
+import os
 import pytest
 import torch
 import torch.nn.functional as F
@@ -23,7 +21,10 @@ pytestmark = pytest.mark.gpu
 
 LOSS_TOL = 1e-3
 GRAD_TOL = 1e-3
-TENSOR_TOL = 4e-3
+TENSOR_TOL = 1e-3
+# name (regex) -> (bound, why).  Filled from measurements on B200 (profiles/r2_train_grad_parity.txt).
+TENSOR_EXCEPTIONS = {}
+REPORT_ONLY = os.environ.get("CM_TEST_REPORT_ONLY") == "1"     # bring-up: print every tensor, assert the global gate only
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -64,14 +65,24 @@ def _compare(lo, go, ln, gn):
     worst = sorted(((rel_l2(gn[k], go[k]), k) for k in go), reverse=True)
     print("global grad rel-L2 = %.3e; worst tensors: %s" % ((num / den) ** 0.5,
           ", ".join("%s %.2e" % (k, e) for e, k in worst[:6])))
+    if REPORT_ONLY:
+        for e, k in worst:
+            if e > 0.5 * TENSOR_TOL:
+                print("TENSOR %-60s rel-L2 %.3e  numel %d  |g| %.3e" % (k, e, go[k].numel(), go[k].double().norm().item()))
     assert (num / den) ** 0.5 <= GRAD_TOL
+    import re
     for e, k in worst:
         # tensors whose gradient is numerically zero in the reference (e.g. k/q biases of the
         # attention softmax shift) are compared in absolute terms
         if go[k].double().norm().item() < 1e-9 * den ** 0.5:
             assert gn[k].double().norm().item() < 1e-6 * den ** 0.5, k
             continue
-        assert e <= TENSOR_TOL, f"{k}: rel-L2 {e:.3e}"
+        bound = TENSOR_TOL
+        for pat, (b, _why) in TENSOR_EXCEPTIONS.items():
+            if re.fullmatch(pat, k):
+                bound = b
+        if not REPORT_ONLY:
+            assert e <= bound, f"{k}: rel-L2 {e:.3e} > {bound:.1e}"
 
 
 @pytest.mark.parametrize("name", ["train_small", "train_atc_b2"])
@@ -91,8 +102,10 @@ def test_train_step_vs_oracle_and_reference_golden(name):
         n_ref, p_ref = float(a["grad_norms"][i]), float(a["grad_proj"][i])
         if n_ref < 1e-12:
             continue
-        assert abs(gn[k].double().norm().item() - n_ref) <= TENSOR_TOL * n_ref, k
-        assert abs((gn[k].double() * r.double()).sum().item() - p_ref) <= TENSOR_TOL * n_ref * r.norm().item(), k
+        if REPORT_ONLY:
+            continue
+        assert abs(gn[k].double().norm().item() - n_ref) <= 2 * TENSOR_TOL * n_ref, k
+        assert abs((gn[k].double() * r.double()).sum().item() - p_ref) <= 2 * TENSOR_TOL * n_ref * r.norm().item(), k
 
 
 def test_train_step_fresh_batch_b5_with_injected_dropout():
@@ -134,6 +147,46 @@ def test_optimizer_step_repacks_weights_and_loss_decreases():
         losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0], losses
+
+
+def test_eval_forward_or_sampling_between_forward_and_backward_raises():
+    """The activation arena is shared: a no_grad forward or a sampling call on the same geometry between a
+    training forward and its backward would silently corrupt the gradients -> it must raise instead."""
+    from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM, ddpm_coefficients
+    meta, a = load_golden("train_small")
+    net = build_unet(meta).cuda().train()
+    x = torch.randn(meta["B"], 3, meta["rows"], meta["cols"], meta["F"], device="cuda")
+    t = torch.zeros(meta["B"], dtype=torch.long, device="cuda")
+    p = a["past"].cuda()
+    y = net(x, t, p)
+    with torch.no_grad():
+        net(x, t, p)
+    with pytest.raises(RuntimeError):
+        y.sum().backward()
+    y = net(x, t, p)
+    ts, coef = ddpm_coefficients(DDPM(timesteps=3, scale=0.5))
+    net.sample_chain(p.contiguous(), x.clone(), ts, coef, mode=0, seed=1)
+    with pytest.raises(RuntimeError):
+        y.sum().backward()
+    y = net(x, t, p)
+    y.sum().backward()                                   # undisturbed pair still works
+    torch.cuda.synchronize()
+
+
+def test_in_place_parameter_surgery_needs_explicit_invalidate():
+    """Writes through p.data do not bump _version: invalidate_native_cache() re-derives the packed weights."""
+    meta, a = load_golden("unet_small_b3")
+    net = build_unet(meta).cuda().eval()
+    args = (a["future"].cuda(), a["t"].cuda(), a["past"].cuda())
+    with torch.no_grad():
+        e0 = net(*args).clone()
+        net.first.weight.data.mul_(0.5)
+        net.invalidate_native_cache()
+        e1 = net(*args).clone()
+        net.first.weight.mul_(2.0)                       # a tracked in-place update: picked up by itself
+        e2 = net(*args).clone()
+    assert not torch.equal(e0, e1)
+    assert torch.allclose(e0, e2, rtol=1e-5, atol=1e-6)
 
 
 def test_second_forward_invalidates_first_backward():

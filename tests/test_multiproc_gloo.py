@@ -24,12 +24,17 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from crowdmod_ddpm_4d_b200.models.backbones.unet_autograd import _allreduce_mean
+        from crowdmod_ddpm_4d_b200.models.backbones.unet_autograd import (_allreduce_mean, disable_data_parallel,
+                                                                          enable_data_parallel)
         from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import shard_samples
         g = torch.Generator().manual_seed(100 + rank)
         flat = torch.randn(1003, generator=g)
         mine = flat.clone()
-        _allreduce_mean(flat)
+        holder = torch.nn.Linear(1, 1)            # stands in for the UNet module carrying the opt-in flag
+        _allreduce_mean(holder, flat)             # a process group that merely exists is NOT used
+        assert torch.equal(flat, mine)
+        enable_data_parallel(holder)
+        _allreduce_mean(holder, flat)
         gathered = [torch.zeros(1003) for _ in range(world)]
         dist.all_gather(gathered, mine)
         ref = torch.stack(gathered).mean(0)
@@ -40,7 +45,10 @@ def _worker(rank, world, port, out):
         cover = sorted((int(a), int(b)) for a, b in spans)
         ok_cover = cover[0][0] == 0 and cover[-1][1] == 13 and all(cover[i][1] == cover[i + 1][0]
                                                                    for i in range(world - 1))
-        out[rank] = (ok_mean, ok_cover)
+        disable_data_parallel(holder)
+        again = mine.clone()
+        _allreduce_mean(holder, again)
+        out[rank] = (ok_mean and torch.equal(again, mine), ok_cover)
     finally:
         dist.destroy_process_group()
 
@@ -54,7 +62,11 @@ def test_flat_gradient_allreduce_mean_and_sample_sharding_world2():
 
 
 def test_allreduce_is_a_noop_without_process_group():
-    from crowdmod_ddpm_4d_b200.models.backbones.unet_autograd import _allreduce_mean
+    import pytest
+    from crowdmod_ddpm_4d_b200.models.backbones.unet_autograd import _allreduce_mean, enable_data_parallel
     x = torch.arange(5.0)
-    _allreduce_mean(x)
+    holder = torch.nn.Linear(1, 1)
+    _allreduce_mean(holder, x)
     assert torch.equal(x, torch.arange(5.0))
+    with pytest.raises(RuntimeError):
+        enable_data_parallel(holder)             # opt-in needs an initialised process group
