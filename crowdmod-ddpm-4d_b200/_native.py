@@ -33,6 +33,7 @@ class UNetConfig(C.Structure):
         ("table_steps", C.c_int32),
         ("weight_terms", C.c_int32),
         ("dgrad_terms", C.c_int32),
+        ("train_act_terms", C.c_int32),
     ]
 
 
@@ -77,6 +78,9 @@ SIGNATURES = {
     "cm_unet_op_count": (C.c_int, [C.c_void_p]),
     "cm_unet_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int),
                                   C.POINTER(C.c_double)]),
+    "cm_unet_debug_op_tensor": (C.c_int, [C.c_void_p, C.c_int]),
+    "cm_unet_debug_tensor_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "cm_unet_op_exec_flops": (C.c_double, [C.c_void_p, C.c_int]),
     "cm_unet_profile_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int]),

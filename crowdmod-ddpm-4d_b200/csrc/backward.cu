@@ -726,8 +726,8 @@ final_conv_dact_kernel(const float* __restrict__ deps, const float* __restrict__
 template <int COUT>
 __global__ void __launch_bounds__(256)
 final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict__ scale_dev,
-                        const __half* __restrict__ act, float* __restrict__ dw, float* __restrict__ db,
-                        int B, int H, int W, int L, int P, int cin, int pix_per_cta) {
+                        const __half* __restrict__ act, int ald, int alo, float* __restrict__ dw,
+                        float* __restrict__ db, int B, int H, int W, int L, int P, int cin, int pix_per_cta) {
   constexpr int MAXP = 8;                      // (tap, ci) pairs per thread: 27*cin <= 2048
   const float scale = scale_dev ? scale_dev[0] : 1.f;
   const int F = L - P;
@@ -757,7 +757,7 @@ final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict_
     kdh[k] = tap / 9 - 1;
     kdw[k] = (tap / 3) % 3 - 1;
     kdl[k] = tap % 3 - 1;
-    koff[k] = (((long long)kdl[k] * H + kdh[k]) * W + kdw[k]) * cin + ci;
+    koff[k] = (((long long)kdl[k] * H + kdh[k]) * W + kdw[k]) * ald + ci;
   }
   int f = 0, wc = 0, h = 0, b = 0;
   if (p0 < p1) {
@@ -776,13 +776,14 @@ final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict_
       d[co] = deps[((size_t)b * COUT + co) * plane + ((size_t)h * W + wc) * F + f] * scale;
       bacc[co] += d[co];
     }
-    const long long base = ((((long long)b * L + l) * H + h) * W + wc) * cin;
+    const long long base = ((((long long)b * L + l) * H + h) * W + wc) * ald;
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
       if (!kok[k]) break;
       const int hh = h + kdh[k], ww = wc + kdw[k], ll = l + kdl[k];
       if (hh < 0 || hh >= H || ww < 0 || ww >= W || ll < 0 || ll >= L) continue;
-      const float a = __half2float(act[base + koff[k]]);
+      float a = __half2float(act[base + koff[k]]);
+      if (alo > 0) a += __half2float(act[base + koff[k] + alo]);      // hi|lo pair operand: exact activation
 #pragma unroll
       for (int co = 0; co < COUT; ++co) acc[k][co] = fmaf(a, d[co], acc[k][co]);
     }
@@ -808,9 +809,10 @@ final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict_
   }
 }
 
-int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act,
+int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act, int act_ld, int act_lo,
                                 const float* w, float* dact, float* dw, float* db, int B, int H, int W,
                                 int L, int P, int cin, int cout, cudaStream_t st) {
+  const int ald = act_ld > 0 ? act_ld : cin;
   CM_CHECK(cout >= 1 && cout <= 4, "final conv supports 1..4 output channels (got %d)", cout);
   CM_CHECK(cin % 32 == 0 && 27 * cin <= 2048, "final conv backward: cin must be a multiple of 32, <= 64");
   const size_t total = (size_t)B * L * H * W * (cin / 8);
@@ -822,7 +824,7 @@ int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const
 #define CM_FB(CO)                                                                                   \
   case CO:                                                                                          \
     final_conv_dact_kernel<CO><<<blocks, 256, smem, st>>>(deps, scale_dev, w, dact, B, H, W, L, P, cin); \
-    final_conv_wgrad_kernel<CO><<<wblocks, 256, 0, st>>>(deps, scale_dev, act, dw, db, B, H, W, L, P, cin, ppc); \
+    final_conv_wgrad_kernel<CO><<<wblocks, 256, 0, st>>>(deps, scale_dev, act, ald, act_lo, dw, db, B, H, W, L, P, cin, ppc); \
     break;
   switch (cout) { CM_FB(1) CM_FB(2) CM_FB(3) CM_FB(4) }
 #undef CM_FB

@@ -83,7 +83,8 @@ int attn_core_backward_enqueue(const float* qkv, const float* dctx, float* dqkv,
 
 // ---- final conv backward (unet.py:121,165-167): deps API layout [B][cout][H][W][F], times *scale;
 //      dact (=) fp32 [B][L][H][W][cin]; dw [cout][cin][27] / db [cout] accumulated with atomics ----
-int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act,
+// act: fp16 [B][L][H][W][act_ld] (act_ld 0 -> cin); act_lo > 0: hi|lo pair rows, the lo half is added
+int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act, int act_ld, int act_lo,
                                 const float* w, float* dact, float* dw, float* db, int B, int H, int W,
                                 int L, int P, int cin, int cout, cudaStream_t st);
 // ---- first conv weight / bias gradient (unet.py:32; inputs need no gradient) ----

@@ -64,6 +64,8 @@ struct PlaneParams {
   float* out32;
   __half* out16;
   int out_ld;
+  int out16_ld, out16_lo;   // fp16 copy: row stride in elements (0 -> out_ld); out16_lo > 0: also write the lo half
+                            // fp16(v - hi) out16_lo elements further (hi|lo pair operand of the training forward)
   // GroupNorm statistics records of the values this launch writes (nullptr = none): per (sample, unit
   // of the sample, output channel) a float4 {shift, sum(v - shift), sum((v - shift)^2), 0} over the
   // unit's R*HB*W valid rows; units belong to ONE sample, so the consumer (gn_apply2_kernel) merges
@@ -431,7 +433,15 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
           uint2 uu;
           uu.x = *reinterpret_cast<uint32_t*>(&h0);
           uu.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(P.out16 + m * P.out_ld + nn0 + sub_c) = uu;
+          __half* o16 = P.out16 + m * (P.out16_ld > 0 ? P.out16_ld : P.out_ld) + nn0 + sub_c;
+          *reinterpret_cast<uint2*>(o16) = uu;
+          if (P.out16_lo > 0) {
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            uu.x = *reinterpret_cast<uint32_t*>(&l0);
+            uu.y = *reinterpret_cast<uint32_t*>(&l1);
+            *reinterpret_cast<uint2*>(o16 + P.out16_lo) = uu;
+          }
         }
       }
       if (P.stats_rec) {

@@ -526,7 +526,8 @@ size_t wgrad_g_elems(int mode, int cin, int cin_extra, int cout) {
 }
 
 int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
-                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G, int dout_ld) {
+                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G, int dout_ld,
+                  int act_ld, int extra_ld) {
   if (int rc = load_driver_syms()) return rc;
   CM_CHECK(mode >= 0 && mode <= 3, "bad wgrad mode %d", mode);
   CM_CHECK(cin % 32 == 0 && cin_extra % 32 == 0 && cout % 32 == 0,
@@ -563,7 +564,7 @@ int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int
     p.lower[ph][0] = (signed char)lw;
     p.lower[ph][1] = (signed char)lh;
     p.lower[ph][2] = (signed char)ld;
-    if (int rc = make_act_map(&p.amap[ph], act, B, D, H, W, cin, bkc, lw, lh, ld, stride, 0)) return rc;
+    if (int rc = make_act_map(&p.amap[ph], act, B, D, H, W, cin, bkc, lw, lh, ld, stride, 0, act_ld)) return rc;
     if (mode == 2) {
       // dOut lives on the 2x grid; phase ph owns the pixels (2z+pz, 2p+pp, 2q+pq)
       const int gw = ph & 1, gh = (ph >> 1) & 1, gd = (ph >> 2) & 1;
@@ -578,7 +579,7 @@ int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int
   }
   if (cin_extra) {
     CM_CHECK(extra != nullptr, "extra source pointer missing");
-    if (int rc = make_act_map(&p.xmap, extra, B, od, oh, ow, cin_extra, bkc, 0, 0, 0, 1, 0)) return rc;
+    if (int rc = make_act_map(&p.xmap, extra, B, od, oh, ow, cin_extra, bkc, 0, 0, 0, 1, 0, extra_ld)) return rc;
   }
   p.M = B * od * oh * ow;
   p.od = od;

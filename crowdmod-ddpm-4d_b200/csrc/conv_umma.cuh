@@ -52,8 +52,10 @@ struct ConvParams {
   int temb_bstride;      // per-sample row stride (training: temb_ld, sampling: 0)
   const float* resid;    // fp32 [M][cout] or nullptr
   float* out32;          // fp32 [rows][out_ld] or nullptr
-  __half* out16;         // fp16 [rows][out_ld] or nullptr
+  __half* out16;         // fp16 [rows][out16_ld] or nullptr
   int out_ld;
+  int out16_ld, out16_lo;   // fp16 copy: row stride in elements (0 -> out_ld); out16_lo > 0: also write the lo half
+                            // fp16(v - hi) out16_lo elements further (hi|lo pair operand of the training forward)
   int scatter;           // 1: rows are low-res pixels, written to (2z+pz, 2p+pp, 2q+pq)
   // split-K (M-starved deep-K layers): gridDim.z = ksplit CTAs of one thread-block cluster share
   // an output tile, each accumulating kb_per_split k-blocks; the partial tiles are reduced in a
@@ -356,7 +358,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
           *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
       if (P.out16) {
-        __half* op = P.out16 + orow * P.out_ld + n;
+        __half* op = P.out16 + orow * (P.out16_ld > 0 ? P.out16_ld : P.out_ld) + n;
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
           __half2 h0 = __floats2half2_rn(v[i], v[i + 1]);
@@ -369,6 +371,19 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
           u.z = *reinterpret_cast<uint32_t*>(&h2);
           u.w = *reinterpret_cast<uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(op + i) = u;
+          if (P.out16_lo > 0) {
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2),
+                         f3 = __half22float2(h3);
+            __half2 l0 = __floats2half2_rn(v[i] - f0.x, v[i + 1] - f0.y);
+            __half2 l1 = __floats2half2_rn(v[i + 2] - f1.x, v[i + 3] - f1.y);
+            __half2 l2 = __floats2half2_rn(v[i + 4] - f2.x, v[i + 5] - f2.y);
+            __half2 l3 = __floats2half2_rn(v[i + 6] - f3.x, v[i + 7] - f3.y);
+            u.x = *reinterpret_cast<uint32_t*>(&l0);
+            u.y = *reinterpret_cast<uint32_t*>(&l1);
+            u.z = *reinterpret_cast<uint32_t*>(&l2);
+            u.w = *reinterpret_cast<uint32_t*>(&l3);
+            *reinterpret_cast<uint4*>(op + P.out16_lo + i) = u;
+          }
         }
       }
     }
@@ -430,7 +445,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
           uint2 u;
           u.x = *reinterpret_cast<uint32_t*>(&h0);
           u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(P.out16 + static_cast<size_t>(m) * P.out_ld + n) = u;
+          __half* o16 = P.out16 + static_cast<size_t>(m) * (P.out16_ld > 0 ? P.out16_ld : P.out_ld) + n;
+          *reinterpret_cast<uint2*>(o16) = u;
+          if (P.out16_lo > 0) {
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            __half2 l0 = __floats2half2_rn(acc.x - f0.x, acc.y - f0.y), l1 = __floats2half2_rn(acc.z - f1.x, acc.w - f1.y);
+            u.x = *reinterpret_cast<uint32_t*>(&l0);
+            u.y = *reinterpret_cast<uint32_t*>(&l1);
+            *reinterpret_cast<uint2*>(o16 + P.out16_lo) = u;
+          }
         }
       }
     }

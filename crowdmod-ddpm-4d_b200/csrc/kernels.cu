@@ -15,8 +15,8 @@ namespace cm {
 // =============================================================================================
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const float* __restrict__ wx,
                                          __half* __restrict__ dst, int cout, int cin, int cinx,
-                                         int taps, int terms, int perm, int cin_src) {
-  pack_conv_body(w, wx, dst, cout, cin, cinx, taps, terms, perm, cin_src,
+                                         int taps, int terms, int perm, int cin_src, int dup) {
+  pack_conv_body(w, wx, dst, cout, cin, cinx, taps, terms, perm, cin_src, dup,
                  blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
@@ -24,8 +24,8 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const floa
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
   const PackJob j = jobs[blockIdx.y];
   const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, istep = (size_t)gridDim.x * blockDim.x;
-  if (j.kind == 0) pack_conv_body(j.w, j.wx, j.dst, j.cout, j.cin, j.cinx, j.taps, j.terms, j.perm, j.cin_src, i0, istep);
-  else if (j.kind == 1) pack_upsample_body(j.w, j.dst, j.cout, j.cin, j.terms, j.perm, i0, istep);
+  if (j.kind == 0) pack_conv_body(j.w, j.wx, j.dst, j.cout, j.cin, j.cinx, j.taps, j.terms, j.perm, j.cin_src, j.dup, i0, istep);
+  else if (j.kind == 1) pack_upsample_body(j.w, j.dst, j.cout, j.cin, j.terms, j.perm, j.dup, i0, istep);
   else pack_dgrad_body(j.mode, j.w, j.dst, j.cout, j.cin, j.terms, j.perm, j.dup, (size_t)j.ktot, i0, istep);
 }
 int pack_all_enqueue(const PackJob* d_jobs, int njobs, cudaStream_t st) {
@@ -36,10 +36,10 @@ int pack_all_enqueue(const PackJob* d_jobs, int njobs, cudaStream_t st) {
 }
 
 int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, int cin, int cinx,
-                      int taps, int terms, int perm, cudaStream_t st) {
-  const size_t total = (size_t)cout * ((size_t)taps * cin + cinx);
+                      int taps, int terms, int perm, cudaStream_t st, int dup) {
+  const size_t total = (size_t)cout * ((size_t)taps * cin + cinx) * dup;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, wx, dst, cout, cin, cinx, taps, terms, perm, cin);
+  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, wx, dst, cout, cin, cinx, taps, terms, perm, cin, dup);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -48,7 +48,7 @@ int pack_conv_weights_padded(const float* w, __half* dst, int cout, int cin_src,
                              int perm, cudaStream_t st) {
   const size_t total = (size_t)cout * 27 * cin_packed;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, nullptr, dst, cout, cin_packed, 0, 27, terms, perm, cin_src);
+  pack_conv_weights_kernel<<<blocks, 256, 0, st>>>(w, nullptr, dst, cout, cin_packed, 0, 27, terms, perm, cin_src, 1);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -57,7 +57,7 @@ int pack_conv_weights_padded(const float* w, __half* dst, int cout, int cin_src,
 // channels-last, time-major operand [B, P+F, H, W, 32] of the first conv (the other channels stay
 // zero from the arena's initialisation).  One thread per pixel, one 8-byte store.
 __global__ void pack_first_input_kernel(const float* __restrict__ x, const float* __restrict__ past,
-                                        __half* __restrict__ out, int B, int H, int W, int P, int F, int cin) {
+                                        __half* __restrict__ out, int B, int H, int W, int P, int F, int cin, int dup) {
   const int L = P + F;
   const size_t total = (size_t)B * L * H * W;
   for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
@@ -76,30 +76,38 @@ __global__ void pack_first_input_kernel(const float* __restrict__ x, const float
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(out + pix * 32) = u;
+    *reinterpret_cast<uint2*>(out + pix * 32 * dup) = u;
+    if (dup == 2) {
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+      u.x = *reinterpret_cast<uint32_t*>(&l0);
+      u.y = *reinterpret_cast<uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(out + pix * 64 + 32) = u;
+    }
   }
 }
 int pack_first_input_enqueue(const float* x, const float* past, __half* out16, int B, int H, int W, int P, int F,
-                             int cin, cudaStream_t st) {
+                             int cin, int dup, cudaStream_t st) {
   CM_CHECK(cin >= 1 && cin <= 4, "first conv supports 1..4 input channels (got %d)", cin);
   const size_t total = (size_t)B * (P + F) * H * W;
   const int blocks = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
-  pack_first_input_kernel<<<blocks, 256, 0, st>>>(x, past, out16, B, H, W, P, F, cin);
+  CM_CHECK(dup == 1 || dup == 2, "pack_first_input: dup must be 1 or 2");
+  pack_first_input_kernel<<<blocks, 256, 0, st>>>(x, past, out16, B, H, W, P, F, cin, dup);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void pack_upsample_weights_kernel(const float* __restrict__ w, __half* __restrict__ dst,
-                                             int cout, int cin, int terms, int perm) {
-  pack_upsample_body(w, dst, cout, cin, terms, perm, blockIdx.x * (size_t)blockDim.x + threadIdx.x,
+                                             int cout, int cin, int terms, int perm, int dup) {
+  pack_upsample_body(w, dst, cout, cin, terms, perm, dup, blockIdx.x * (size_t)blockDim.x + threadIdx.x,
                      (size_t)gridDim.x * blockDim.x);
 }
 
 int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms, int perm,
-                          cudaStream_t st) {
-  const size_t total = (size_t)cout * 64 * cin;
+                          cudaStream_t st, int dup) {
+  const size_t total = (size_t)cout * 64 * cin * dup;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_upsample_weights_kernel<<<blocks, 256, 0, st>>>(w, dst, cout, cin, terms, perm);
+  pack_upsample_weights_kernel<<<blocks, 256, 0, st>>>(w, dst, cout, cin, terms, perm, dup);
   CM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -114,6 +122,23 @@ int cast_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t st) {
   cast_f32_to_f16_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(src, dst, n);
   CM_CUDA(cudaGetLastError());
   return 0;
+}
+
+// 4 consecutive channels of one pixel -> the fp16 operand row: hi at dst, and (dup == 2) lo = fp16(v - hi) at
+// dst + lo_off (the K-concatenated hi|lo pair the training forward multiplies, exact to 2^-22)
+__device__ __forceinline__ void store_h4(__half* dst, int lo_off, float y0, float y1, float y2, float y3) {
+  __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(dst) = u;
+  if (lo_off) {
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    __half2 l0 = __floats2half2_rn(y0 - f0.x, y1 - f0.y), l1 = __floats2half2_rn(y2 - f1.x, y3 - f1.y);
+    u.x = *reinterpret_cast<uint32_t*>(&l0);
+    u.y = *reinterpret_cast<uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(dst + lo_off) = u;
+  }
 }
 
 // =============================================================================================
@@ -273,25 +298,17 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(const GnParams p) {
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
   const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z,
                                 be.w - mean * sc.w);
-  __half* on = p.out_norm + pix_base * C + c;
-  __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
+  const int dup = p.dup == 2 ? 2 : 1, lo_off = dup == 2 ? C : 0;
+  __half* on = p.out_norm + pix_base * C * dup + c;
+  __half* orw = p.out_raw ? p.out_raw + pix_base * C * dup + c : nullptr;
   auto emit = [&](int i, const float4& v) {
     float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z),
           y3 = fmaf(v.w, sc.w, sh.w);
     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
     y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w;
-    const size_t o = (size_t)(i / Q) * C;
-    __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(on + o) = u;
-    if (orw) {
-      __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
-      u.x = *reinterpret_cast<uint32_t*>(&r0);
-      u.y = *reinterpret_cast<uint32_t*>(&r1);
-      *reinterpret_cast<uint2*>(orw + o) = u;
-    }
+    const size_t o = (size_t)(i / Q) * C * dup;
+    store_h4(on + o, lo_off, y0, y1, y2, y3);
+    if (orw) store_h4(orw + o, lo_off, v.x, v.y, v.z, v.w);
   };
 #pragma unroll
   for (int j = 0; j < GN_CACHE; ++j) {
@@ -616,11 +633,13 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
   const bool from0 = c < p.c0;
   const int ld = from0 ? p.c0 : p.c1;
   const int soff = from0 ? c : rg.RS * p.c0 + (c - p.c0);
-  const size_t out_base = ((size_t)b * p.pixels + px0) * C + c;
+  const int dup = p.dup == 2 ? 2 : 1, lo_off = dup == 2 ? C : 0;
+  const int Cd = C * dup;                                   // elements per output pixel row
+  const size_t out_base = ((size_t)b * p.pixels + px0) * Cd + c;
   __half* on = p.out_norm + out_base;
   __half* orw = p.out_raw ? p.out_raw + out_base : nullptr;
   const bool silu = p.silu != 0;
-  const int ostep = rpi * C;                                // output elements between a thread's rows
+  const int ostep = rpi * Cd;                               // output elements between a thread's rows
   for (int s = 0; s < rg.total; ++s) {
     const int slot = s % GN3_NS;
     mbar_wait(&full_bar[slot], (uint32_t)((s / GN3_NS) & 1), nullptr, 0);
@@ -632,8 +651,8 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
 #pragma unroll
       for (int j = 0; j < GN3_V; ++j)
         if (r + j * rpi < nr) v[j] = *reinterpret_cast<const float4*>(sb + j * sstep);
-      __half* o = on + (size_t)(s * rg.RS + r) * C;
-      __half* orr = orw ? orw + (size_t)(s * rg.RS + r) * C : nullptr;
+      __half* o = on + (size_t)(s * rg.RS + r) * Cd;
+      __half* orr = orw ? orw + (size_t)(s * rg.RS + r) * Cd : nullptr;
 #pragma unroll
       for (int j = 0; j < GN3_V; ++j) {
         if (r + j * rpi < nr) {
@@ -646,17 +665,8 @@ __global__ void __launch_bounds__(GN2_T) gn_apply2_kernel(const GnParams p, int 
             y3 = silu_ex2(y3, fmaf(v[j].w, zc.w, zh.w));
           }
           if (drop) { y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w; }
-          __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(o + j * ostep) = u;
-          if (orr) {
-            __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
-            u.x = *reinterpret_cast<uint32_t*>(&r0);
-            u.y = *reinterpret_cast<uint32_t*>(&r1);
-            *reinterpret_cast<uint2*>(orr + j * ostep) = u;
-          }
+          store_h4(o + j * ostep, lo_off, y0, y1, y2, y3);
+          if (orr) store_h4(orr + j * ostep, lo_off, v[j].x, v[j].y, v[j].z, v[j].w);
         }
       }
     }
@@ -754,8 +764,9 @@ __global__ void __launch_bounds__(1024) gn_small_kernel(const GnParams p) {
   const float4 zc = make_float4(sc.x * NL2E, sc.y * NL2E, sc.z * NL2E, sc.w * NL2E);
   const float4 zh = make_float4(sh.x * NL2E, sh.y * NL2E, sh.z * NL2E, sh.w * NL2E);
   const bool silu = p.silu != 0, drop = p.drop_scale != nullptr;
-  __half* on = p.out_norm + pix_base * C + c;
-  __half* orw = p.out_raw ? p.out_raw + pix_base * C + c : nullptr;
+  const int dup = p.dup == 2 ? 2 : 1, lo_off = dup == 2 ? C : 0;
+  __half* on = p.out_norm + pix_base * C * dup + c;
+  __half* orw = p.out_raw ? p.out_raw + pix_base * C * dup + c : nullptr;
 #pragma unroll
   for (int j = 0; j < GNS_CACHE; ++j) {
     const int pj = px0 + j * rows_per_iter;
@@ -769,18 +780,9 @@ __global__ void __launch_bounds__(1024) gn_small_kernel(const GnParams p) {
       y3 = silu_ex2(y3, fmaf(v[j].w, zc.w, zh.w));
     }
     if (drop) { y0 *= ds.x; y1 *= ds.y; y2 *= ds.z; y3 *= ds.w; }
-    const size_t o = (size_t)pj * C;
-    __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(on + o) = u;
-    if (orw) {
-      __half2 r0 = __floats2half2_rn(v[j].x, v[j].y), r1 = __floats2half2_rn(v[j].z, v[j].w);
-      u.x = *reinterpret_cast<uint32_t*>(&r0);
-      u.y = *reinterpret_cast<uint32_t*>(&r1);
-      *reinterpret_cast<uint2*>(orw + o) = u;
-    }
+    const size_t o = (size_t)pj * C * dup;
+    store_h4(on + o, lo_off, y0, y1, y2, y3);
+    if (orw) store_h4(orw + o, lo_off, v[j].x, v[j].y, v[j].z, v[j].w);
   }
 }
 
@@ -1024,28 +1026,34 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
     for (int co = 0; co < COUT; ++co) acc3[j][co] = 0.f;
   if (active) {
     const int l0 = p.P + f0 - 1;                       // first of the FIN_FC + 2 input planes
-    const size_t pstride = (size_t)p.H * p.W * cin;    // elements per (b, l) plane
+    const int ald = p.act_ld > 0 ? p.act_ld : cin;     // pixel row stride (2*cin for hi|lo pair operands)
+    const size_t pstride = (size_t)p.H * p.W * ald;    // elements per (b, l) plane
     for (int th = 0; th < 3; ++th) {
       const int hh = h + th - 1;
       if (hh < 0 || hh >= p.H) continue;
       for (int tw = 0; tw < 3; ++tw) {
         const int ww = wc + tw - 1;
         if (ww < 0 || ww >= p.W) continue;
-        const __half* ap = p.act + (((size_t)b * p.L * p.H + hh) * p.W + ww) * cin;
+        const __half* ap = p.act + (((size_t)b * p.L * p.H + hh) * p.W + ww) * ald;
         for (int c0 = sub * 8; c0 < cin; c0 += 32) {
           float a[FIN_FC + 2][8];
 #pragma unroll
           for (int q = 0; q < FIN_FC + 2; ++q) {
             const int ll = l0 + q;
-            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            uint4 u = make_uint4(0u, 0u, 0u, 0u), ul = u;
             // planes past the chunk's last valid frame + 1 are never multiplied into a stored output
-            if (ll >= 0 && ll < p.L) u = *reinterpret_cast<const uint4*>(ap + (size_t)ll * pstride + c0);
+            if (ll >= 0 && ll < p.L) {
+              u = *reinterpret_cast<const uint4*>(ap + (size_t)ll * pstride + c0);
+              if (p.act_lo > 0) ul = *reinterpret_cast<const uint4*>(ap + (size_t)ll * pstride + p.act_lo + c0);
+            }
             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&ul);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 a2 = __half22float2(h2[e]);
-              a[q][2 * e] = a2.x;
-              a[q][2 * e + 1] = a2.y;
+              const float2 b2 = __half22float2(l2[e]);
+              a[q][2 * e] = a2.x + b2.x;
+              a[q][2 * e + 1] = a2.y + b2.y;
             }
           }
           const float4* wp4 = reinterpret_cast<const float4*>(ws + ((size_t)(th * 3 + tw) * cin + c0) * 3 * COUT);
@@ -1242,7 +1250,7 @@ __device__ __forceinline__ void split_h2(float x, float y, uint32_t* hi, uint32_
 // NT = key tiles of 8 (S_pad = 8*NT, multiple of 16)
 template <int DH, int NT>
 __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const float* __restrict__ qkv, __half* __restrict__ ctx,
-                                                          int S, int C, int heads) {
+                                                          int S, int C, int heads, int dup) {
   pdl_trigger();
   pdl_wait();
   const int dh = C / heads;
@@ -1360,36 +1368,51 @@ __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const float* __restri
       mma_16816(oc[dt], pa, b0, b1);
     }
   }
-  __half* ob = ctx + (size_t)b * S * C + hd * dh;
+  const int Cd = C * dup;                              // dup = 2: hi | lo pair per token (training forward)
+  __half* ob = ctx + (size_t)b * S * Cd + hd * dh;
 #pragma unroll
   for (int dt = 0; dt < DH / 8; ++dt) {
     const int d = dt * 8 + 2 * t;
     if (d >= dh) continue;
+    if (dup == 2) {
+      uint32_t hi, lo;
+      if (i0 < S) {
+        split_h2(oc[dt][0], oc[dt][1], &hi, &lo);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)i0 * Cd + d) = hi;
+        *reinterpret_cast<uint32_t*>(ob + (size_t)i0 * Cd + C + d) = lo;
+      }
+      if (i1 < S) {
+        split_h2(oc[dt][2], oc[dt][3], &hi, &lo);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)i1 * Cd + d) = hi;
+        *reinterpret_cast<uint32_t*>(ob + (size_t)i1 * Cd + C + d) = lo;
+      }
+      continue;
+    }
     if (i0 < S) *reinterpret_cast<uint32_t*>(ob + (size_t)i0 * C + d) = pack_h2(oc[dt][0], oc[dt][1]);
     if (i1 < S) *reinterpret_cast<uint32_t*>(ob + (size_t)i1 * C + d) = pack_h2(oc[dt][2], oc[dt][3]);
   }
 }
 
 template <int DH, int NT>
-static int attn_launch(const float* qkv, __half* ctx, int B, int S, int C, int heads, cudaStream_t st) {
+static int attn_launch(const float* qkv, __half* ctx, int B, int S, int C, int heads, int dup, cudaStream_t st) {
   constexpr int SP = NT * 8;
   const size_t smem = ((size_t)2 * SP * (DH + 8) + (size_t)DH * (SP + 8)) * sizeof(__half);
-  if (int e = launch_pdl(attn_mma_kernel<DH, NT>, dim3(B * heads), dim3(NT * 16), smem, st, qkv, ctx, S, C, heads)) return e;
+  if (int e = launch_pdl(attn_mma_kernel<DH, NT>, dim3(B * heads), dim3(NT * 16), smem, st, qkv, ctx, S, C, heads, dup)) return e;
   return 0;
 }
 
 template <int DH>
-static int attn_dispatch(const float* qkv, __half* ctx, int B, int S, int C, int heads, cudaStream_t st) {
+static int attn_dispatch(const float* qkv, __half* ctx, int B, int S, int C, int heads, int dup, cudaStream_t st) {
   const int sp16 = (S + 15) / 16;       // query tiles = warps
   switch (sp16) {
-    case 1: return attn_launch<DH, 2>(qkv, ctx, B, S, C, heads, st);
-    case 2: return attn_launch<DH, 4>(qkv, ctx, B, S, C, heads, st);
-    case 3: return attn_launch<DH, 6>(qkv, ctx, B, S, C, heads, st);
-    case 4: return attn_launch<DH, 8>(qkv, ctx, B, S, C, heads, st);
-    case 5: return attn_launch<DH, 10>(qkv, ctx, B, S, C, heads, st);
-    case 6: return attn_launch<DH, 12>(qkv, ctx, B, S, C, heads, st);
-    case 7: return attn_launch<DH, 14>(qkv, ctx, B, S, C, heads, st);
-    case 8: return attn_launch<DH, 16>(qkv, ctx, B, S, C, heads, st);
+    case 1: return attn_launch<DH, 2>(qkv, ctx, B, S, C, heads, dup, st);
+    case 2: return attn_launch<DH, 4>(qkv, ctx, B, S, C, heads, dup, st);
+    case 3: return attn_launch<DH, 6>(qkv, ctx, B, S, C, heads, dup, st);
+    case 4: return attn_launch<DH, 8>(qkv, ctx, B, S, C, heads, dup, st);
+    case 5: return attn_launch<DH, 10>(qkv, ctx, B, S, C, heads, dup, st);
+    case 6: return attn_launch<DH, 12>(qkv, ctx, B, S, C, heads, dup, st);
+    case 7: return attn_launch<DH, 14>(qkv, ctx, B, S, C, heads, dup, st);
+    case 8: return attn_launch<DH, 16>(qkv, ctx, B, S, C, heads, dup, st);
     default:
       CM_CHECK(false, "attention: sequence length %d > 128 tokens is not supported", S);
   }
@@ -1397,13 +1420,14 @@ static int attn_dispatch(const float* qkv, __half* ctx, int B, int S, int C, int
 }
 
 int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int heads,
-                      cudaStream_t st) {
+                      cudaStream_t st, int dup) {
+  CM_CHECK(dup == 1 || dup == 2, "attention: dup must be 1 or 2");
   CM_CHECK(C % heads == 0, "embed dim %d / heads %d unsupported", C, heads);
   const int dh = C / heads;
   CM_CHECK(dh % 2 == 0 && dh <= 64, "attention: head dim %d unsupported (even, <= 64)", dh);
-  if (dh <= 16) return attn_dispatch<16>(qkv, ctx, B, S, C, heads, st);
-  if (dh <= 32) return attn_dispatch<32>(qkv, ctx, B, S, C, heads, st);
-  return attn_dispatch<64>(qkv, ctx, B, S, C, heads, st);
+  if (dh <= 16) return attn_dispatch<16>(qkv, ctx, B, S, C, heads, dup, st);
+  if (dh <= 32) return attn_dispatch<32>(qkv, ctx, B, S, C, heads, dup, st);
+  return attn_dispatch<64>(qkv, ctx, B, S, C, heads, dup, st);
 }
 
 // =============================================================================================

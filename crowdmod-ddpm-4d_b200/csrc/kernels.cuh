@@ -11,17 +11,18 @@ namespace cm {
 // perm = 1: w is a reference nn.Conv3d weight over (rows, cols, time) and the activations are
 // stored [B, time, rows, cols, C]; perm = 0: w taps are ordered like the activation dims.
 int pack_conv_weights(const float* w, const float* wx, __half* dst, int cout, int cin, int cinx,
-                      int taps, int terms, int perm, cudaStream_t st);
+                      int taps, int terms, int perm, cudaStream_t st, int dup = 1);
 // nearest-x2 + k3 conv folded into 8 phase convs with 2x2x2 combined taps
 // (layers.py:92-94).  dst: [terms*cout][64*cin], column = phase*8*cin + tap8*cin + ci.
 // k3 conv weights whose cin_src (< 32) input channels are zero-padded to cin_packed packed channels
 int pack_conv_weights_padded(const float* w, __half* dst, int cout, int cin_src, int cin_packed, int terms,
                              int perm, cudaStream_t st);
 // first-conv operand: API tensors -> channels 0..cin-1 of fp16 [B, P+F, H, W, 32] (other channels untouched)
+// dup = 2: rows of 64 (hi | lo halves of the 32 padded channels)
 int pack_first_input_enqueue(const float* x, const float* past, __half* out16, int B, int H, int W, int P, int F,
-                             int cin, cudaStream_t st);
+                             int cin, int dup, cudaStream_t st);
 int pack_upsample_weights(const float* w, __half* dst, int cout, int cin, int terms, int perm,
-                          cudaStream_t st);
+                          cudaStream_t st, int dup = 1);
 
 // ---- GroupNorm(8) [+SiLU] [+Dropout3d scale] -> fp16 operand (layers.py:30,41,57,70; :9,14) ----
 // GroupNorm statistics records written by a producing plane-tile conv (PlaneParams::stats_rec)
@@ -41,8 +42,11 @@ struct GnParams {
   int silu;
   const float* drop_scale;  // [B][drop_ld] (+ channel) per-(sample,channel) multiplier or nullptr
   int drop_ld;
-  __half* out_norm;         // [B][pixels][C]
-  __half* out_raw;          // optional raw fp16 copy of the (concatenated) input
+  __half* out_norm;         // [B][pixels][dup*C]
+  __half* out_raw;          // optional raw fp16 copy of the (concatenated) input, same row layout
+  int dup;                  // 1: single fp16 operand; 2: K-concatenated hi|lo pair per pixel ([0,C) = hi,
+                            // [C,2C) = fp16(v - hi)): the training forward's operands are exact to 2^-22
+                            // (0 is read as 1)
   float* stats;             // optional [B][8][2] (mean, rstd) for backward
   GnRec rec0, rec1;         // both sources have records -> no statistics pass over the data
 };
@@ -60,7 +64,9 @@ int first_conv_enqueue(const float* x, const float* past, const float* w, const 
 
 // ---- final conv base->3 fused with the DDPM/DDIM update (unet.py:118-122,165-167; ddpm.py:25-38,262-265) ----
 struct FinalParams {
-  const __half* act;     // fp16 channels-last, time-major [B][L][H][W][cin], already GN+SiLU'ed
+  const __half* act;     // fp16 channels-last, time-major [B][L][H][W][act_ld], already GN+SiLU'ed
+  int act_ld;            // row stride in elements (0 -> cin); act_lo > 0: a lo half sits act_lo elements
+  int act_lo;            // after the hi half of every pixel row and is added (hi|lo pair operands)
   const float* w;        // [cout][cin][27] fp32
   const float* bias;
   int B, H, W, L, P;     // L = P + F; only frames l >= P are produced
@@ -101,9 +107,9 @@ struct TembParams {
 int temb_enqueue(const TembParams& p, cudaStream_t st);
 
 // ---- attention core softmax(QK^T/sqrt(dh))V per (sample, head) (layers.py:16) ----
-// qkv: fp32 [B*S][3*C] (q | k | v), ctx: fp16 [B*S][C]
+// qkv: fp32 [B*S][3*C] (q | k | v), ctx: fp16 [B*S][dup*C] (dup = 2: hi | lo pair per token)
 int attn_core_enqueue(const float* qkv, __half* ctx, int B, int S, int C, int heads,
-                      cudaStream_t st);
+                      cudaStream_t st, int dup = 1);
 
 // ---- fused AttentionBlock of the sampling path (layers.py:5-18): GroupNorm -> in_proj -> attention core ->
 // out_proj -> + x in one launch (one CTA per sample).  w_in / w_out: packed hi|lo fp16 rows as the 1x1 convs

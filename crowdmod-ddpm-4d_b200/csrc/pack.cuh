@@ -17,42 +17,55 @@ __device__ __forceinline__ int src_tap_of(int tap, int perm) {
 
 // dst: [terms*cout][taps*cin + cinx], column = tap*cin + ci, then taps*cin + cx; channels ci >= cin_src
 // are zero (first conv: 3 API channels padded to 32).
+// dup = 2: the activation operand is a K-concatenated hi|lo fp16 pair per pixel ([0,cin) = hi, [cin,2cin) = lo):
+// every tap slab becomes [W(ci) for the hi half | W(ci) for the lo half]; the lo WEIGHT term carries zeros against
+// the lo half (see pack_dgrad_body).  cin / cinx are the LOGICAL channel counts; K per row = dup*(taps*cin + cinx).
 __device__ __forceinline__ void pack_conv_body(const float* __restrict__ w, const float* __restrict__ wx,
                                                __half* __restrict__ dst, int cout, int cin, int cinx, int taps,
-                                               int terms, int perm, int cin_src, size_t i0, size_t istep) {
-  const size_t ktot = (size_t)taps * cin + cinx;
+                                               int terms, int perm, int cin_src, int dup, size_t i0, size_t istep) {
+  const size_t kmain = (size_t)taps * cin * dup;
+  const size_t ktot = kmain + (size_t)cinx * dup;
   const size_t total = (size_t)cout * ktot;
   for (size_t idx = i0; idx < total; idx += istep) {
     const int n = (int)(idx / ktot);
     const size_t k = idx - (size_t)n * ktot;
     float v;
-    if (k < (size_t)taps * cin) {
-      const int tap = (int)(k / cin);
-      const int ci = (int)(k - (size_t)tap * cin);
+    bool lo_half;
+    if (k < kmain) {
+      const int tap = (int)(k / ((size_t)cin * dup));
+      const int c2 = (int)(k - (size_t)tap * cin * dup);
+      lo_half = c2 >= cin;
+      const int ci = lo_half ? c2 - cin : c2;
       const int st = (taps == 27) ? src_tap_of(tap, perm) : tap;
       v = ci < cin_src ? w[((size_t)n * cin_src + ci) * taps + st] : 0.f;
     } else {
-      v = wx[(size_t)n * cinx + (k - (size_t)taps * cin)];
+      const int c2 = (int)(k - kmain);
+      lo_half = c2 >= cinx;
+      v = wx[(size_t)n * cinx + (lo_half ? c2 - cinx : c2)];
     }
     const __half hi = __float2half_rn(v);
     dst[(size_t)n * ktot + k] = hi;
-    if (terms == 2) dst[((size_t)cout + n) * ktot + k] = __float2half_rn(v - __half2float(hi));
+    if (terms == 2)
+      dst[((size_t)cout + n) * ktot + k] = lo_half ? __float2half_rn(0.f) : __float2half_rn(v - __half2float(hi));
   }
 }
 
 // nearest-x2 + k3 p1 (layers.py:92-94) folded into 8 phase convs with 2x2x2 combined taps.
-// dst: [terms*cout][64*cin], column = phase*8*cin + tap8*cin + ci.
+// dst: [terms*cout][64*dup*cin], column = phase*8*dup*cin + tap8*dup*cin + c2 (c2 < cin: hi half, else lo half).
 __device__ __forceinline__ void pack_upsample_body(const float* __restrict__ w, __half* __restrict__ dst, int cout,
-                                                   int cin, int terms, int perm, size_t i0, size_t istep) {
-  const size_t ktot = (size_t)64 * cin;
+                                                   int cin, int terms, int perm, int dup, size_t i0, size_t istep) {
+  const int cw = cin * dup;                       // packed channels per tap slab (hi | lo halves when dup = 2)
+  const size_t ktot = (size_t)64 * cw;
   const size_t total = (size_t)cout * ktot;
   for (size_t idx = i0; idx < total; idx += istep) {
     const int n = (int)(idx / ktot);
     const int k = (int)(idx - (size_t)n * ktot);
-    const int phase = k / (8 * cin);
-    const int r = k - phase * 8 * cin;
-    const int tap8 = r / cin;
-    const int ci = r - tap8 * cin;
+    const int phase = k / (8 * cw);
+    const int r = k - phase * 8 * cw;
+    const int tap8 = r / cw;
+    const int c2 = r - tap8 * cw;
+    const bool lo_half = c2 >= cin;
+    const int ci = lo_half ? c2 - cin : c2;
     // per dim: phase bit p, tap bit a -> contributing original taps [lo, hi]
     //   p=0 (even output): a=0 -> {0},   a=1 -> {1,2}
     //   p=1 (odd  output): a=0 -> {0,1}, a=1 -> {2}
@@ -71,7 +84,8 @@ __device__ __forceinline__ void pack_upsample_body(const float* __restrict__ w, 
         for (int kw = lo[0]; kw <= hi[0]; ++kw) v += wp[src_tap_of((kd * 3 + kh) * 3 + kw, perm)];
     const __half h = __float2half_rn(v);
     dst[(size_t)n * ktot + k] = h;
-    if (terms == 2) dst[((size_t)cout + n) * ktot + k] = __float2half_rn(v - __half2float(h));
+    if (terms == 2)
+      dst[((size_t)cout + n) * ktot + k] = lo_half ? __float2half_rn(0.f) : __float2half_rn(v - __half2float(h));
   }
 }
 

