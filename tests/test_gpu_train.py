@@ -5,8 +5,11 @@ loss / gradient norms / random projections generated from the unmodified referen
 
 Tolerances (BASELINE.json north_star: "training loss and gradients within 1e-3"): loss
 relative error <= 1e-3; global gradient-vector rel-L2 <= GRAD_TOL = 1e-3; EVERY parameter tensor rel-L2 <=
-TENSOR_TOL = 1e-3, except the tensors named in TENSOR_EXCEPTIONS, each with its own measured bound and the
-reason (see the table).  There is no blanket loosening.
+TENSOR_TOL = 1e-3.  No exceptions are needed: the training forward multiplies hi|lo fp16 activation pairs
+(cm_unet_config.train_act_terms = 2) and the data-gradient convs hi|lo dOut pairs (dgrad_terms = 2), which
+took the worst tensor from 2.6e-3 (round 1, single fp16 operands: the error was the forward's activation
+rounding propagating into every deep-layer gradient -- shown by the CPU emulation in
+profiles/r2_train_grad_parity.txt) to 5.8e-4 / 3.4e-4 / 3.2e-4 on the three cases below (measured on B200).
 """
 import os
 import pytest
@@ -22,7 +25,7 @@ pytestmark = pytest.mark.gpu
 LOSS_TOL = 1e-3
 GRAD_TOL = 1e-3
 TENSOR_TOL = 1e-3
-# name (regex) -> (bound, why).  Filled from measurements on B200 (profiles/r2_train_grad_parity.txt).
+# name (regex) -> (bound, why): empty -- every tensor meets TENSOR_TOL (see the module docstring)
 TENSOR_EXCEPTIONS = {}
 REPORT_ONLY = os.environ.get("CM_TEST_REPORT_ONLY") == "1"     # bring-up: print every tensor, assert the global gate only
 
@@ -104,8 +107,8 @@ def test_train_step_vs_oracle_and_reference_golden(name):
             continue
         if REPORT_ONLY:
             continue
-        assert abs(gn[k].double().norm().item() - n_ref) <= 2 * TENSOR_TOL * n_ref, k
-        assert abs((gn[k].double() * r.double()).sum().item() - p_ref) <= 2 * TENSOR_TOL * n_ref * r.norm().item(), k
+        assert abs(gn[k].double().norm().item() - n_ref) <= TENSOR_TOL * n_ref, k
+        assert abs((gn[k].double() * r.double()).sum().item() - p_ref) <= TENSOR_TOL * n_ref * r.norm().item(), k
 
 
 def test_train_step_fresh_batch_b5_with_injected_dropout():
