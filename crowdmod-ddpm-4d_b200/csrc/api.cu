@@ -5,10 +5,12 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/crowdmod_b200.h"
 #include "backward.cuh"
 #include "conv_plane.cuh"
+#include "conv_res32.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 #include "wgrad_umma.cuh"
@@ -67,6 +69,96 @@ int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int ci
   if (mode == 2) rc = pack_upsample_weights(w, wp, cout, cin, terms, 0, st);
   else rc = pack_conv_weights(w, wx, wp, cout, cin, cin_extra, mode == 3 ? 1 : 27, terms, 0, st);
   ConvLaunch L;
+  if (!rc && impl == 3) {
+    // weights-resident 32 -> 32 kernel (conv_res32.cuh).  Fails if the shape is not covered.
+    Res32Launch R;
+    rc = (mode == 0) ? res32_prepare(&R, static_cast<const __half*>(act16), B, D, H, W, cin,
+                                     static_cast<const __half*>(extra16), cin_extra, wp, cout, terms)
+                     : 2;
+    if (!rc && !R.ok) {
+      set_error("weights-resident conv does not cover this shape");
+      rc = 2;
+    }
+    if (!rc) {
+      R.p.bias = bias;
+      R.p.resid = resid;
+      R.p.out32 = out32;
+      R.p.out16 = static_cast<__half*>(out16);
+      rc = res32_enqueue(R, st);
+      if (const char* e = getenv("CM_DBG_REPS")) {
+        const int reps = atoi(e);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaStreamSynchronize(st);
+        cudaEventRecord(a, st);
+        for (int i = 0; i < reps && !rc; ++i) rc = res32_enqueue(R, st);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "CM_DBG res32 B=%d D=%d H=%d W=%d cin=%d+%d cout=%d HB=%d units=%d stages=%d grid=%d smem=%zu: %.2f us/launch (%.1f TF/s)\n",
+                B, D, H, W, cin, cin_extra, cout, R.p.HB, R.p.n_units, R.p.stages, R.grid.x, R.smem, ms * 1e3f / reps,
+                R.flops / (ms * 1e-3 / reps) * 1e-12);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+      }
+    }
+    if (!rc && getenv("CM_PLANE_TRACE")) {   // bring-up: event trace of CTA 0 (producer / MMA issuer / drain warp / store warp)
+      const size_t n = (size_t)4 * PL_TRACE_CAP * 2;
+      long long* tr = nullptr;
+      cudaMalloc(&tr, n * 8);
+      cudaMemset(tr, 0, n * 8);
+      R.p.trace = tr;
+      unsigned long long* ct = nullptr;
+      cudaMalloc(&ct, (size_t)R.grid.x * 16);
+      cudaMemset(ct, 0, (size_t)R.grid.x * 16);
+      R.p.cta_times = ct;
+      cudaStreamSynchronize(st);
+      rc = res32_enqueue(R, st);
+      cudaStreamSynchronize(st);
+      {
+        std::vector<unsigned long long> hc((size_t)R.grid.x * 2);
+        cudaMemcpy(hc.data(), ct, hc.size() * 8, cudaMemcpyDeviceToHost);
+        unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0, dmin = ~0ull, dmax = 0;
+        for (unsigned i = 0; i < R.grid.x; ++i) {
+          const unsigned long long a = hc[2 * i], b = hc[2 * i + 1];
+          if (a < s0) s0 = a;
+          if (a > s1) s1 = a;
+          if (b < e0) e0 = b;
+          if (b > e1) e1 = b;
+          if (b - a < dmin) dmin = b - a;
+          if (b - a > dmax) dmax = b - a;
+        }
+        fprintf(stderr, "CTA_TIMES ns: first start 0, last start %llu, first end %llu, last end %llu; CTA duration min %llu max %llu\n",
+                s1 - s0, e0 - s0, e1 - s0, dmin, dmax);
+      }
+      R.p.cta_times = nullptr;
+      cudaFree(ct);
+      std::vector<long long> h(n);
+      cudaMemcpy(h.data(), tr, n * 8, cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (size_t i = 0; i < n; i += 2)
+        if (h[i] && (t0 == 0 || h[i + 1] < t0)) t0 = h[i + 1];
+      static const char* role[4] = {"prod", "mma", "drain", "store"};
+      for (int r = 0; r < 4; ++r) {
+        long long prev = t0;
+        for (int i = 0; i < PL_TRACE_CAP; ++i) {
+          const long long code = h[((size_t)r * PL_TRACE_CAP + i) * 2], t = h[((size_t)r * PL_TRACE_CAP + i) * 2 + 1];
+          if (!code) break;
+          fprintf(stderr, "PL_TRACE %s i=%d code=%lld t=%lld dt=%lld\n", role[r], i, code, t - t0, t - prev);
+          prev = t;
+        }
+      }
+      R.p.trace = nullptr;
+      cudaFree(tr);
+    }
+    cudaError_t se3 = cudaStreamSynchronize(st);
+    cudaFree(wp);
+    if (rc) return rc;
+    CM_CUDA(se3);
+    return 0;
+  }
   if (!rc && impl == 2) {
     // plane-tile kernel (conv_plane.cuh); mode 0 only.  Fails if the geometry is not covered.
     PlaneLaunch PLn;
@@ -100,6 +192,33 @@ int cm_op_conv3d(int mode, const void* act16, int B, int D, int H, int W, int ci
                 PLn.p.stages, PLn.grid.x, ms * 1e3f / reps, PLn.flops / (ms * 1e-3 / reps) * 1e-12);
         cudaEventDestroy(a);
         cudaEventDestroy(b);
+      }
+      if (!rc && getenv("CM_PLANE_TRACE")) {   // bring-up: event trace of CTA 0 (producer / MMA issuer / epilogue warp 2)
+        const size_t n = (size_t)3 * PL_TRACE_CAP * 2;
+        long long* tr = nullptr;
+        cudaMalloc(&tr, n * 8);
+        cudaMemset(tr, 0, n * 8);
+        PLn.p.trace = tr;
+        cudaStreamSynchronize(st);
+        rc = plane_enqueue(PLn, st);
+        cudaStreamSynchronize(st);
+        std::vector<long long> h(n);
+        cudaMemcpy(h.data(), tr, n * 8, cudaMemcpyDeviceToHost);
+        long long t0 = 0;
+        for (size_t i = 0; i < n; i += 2)
+          if (h[i] && (t0 == 0 || h[i + 1] < t0)) t0 = h[i + 1];
+        static const char* role[3] = {"prod", "mma", "epi"};
+        for (int r = 0; r < 3; ++r) {
+          long long prev = t0;
+          for (int i = 0; i < PL_TRACE_CAP; ++i) {
+            const long long code = h[((size_t)r * PL_TRACE_CAP + i) * 2], t = h[((size_t)r * PL_TRACE_CAP + i) * 2 + 1];
+            if (!code) break;
+            fprintf(stderr, "PL_TRACE %s i=%d code=%lld t=%lld dt=%lld\n", role[r], i, code, t - t0, t - prev);
+            prev = t;
+          }
+        }
+        PLn.p.trace = nullptr;
+        cudaFree(tr);
       }
     }
     cudaError_t se2 = cudaStreamSynchronize(st);

@@ -72,7 +72,17 @@ struct PlaneParams {
   // them in a fixed order -> bit-reproducible wherever the sample sits in the batch.
   float* stats_rec;
   int* err_flag;
+  long long* trace;      // bring-up (CM_PLANE_TRACE): CTA 0 records (code, clock64) pairs, 3 regions of PL_TRACE_CAP
 };
+constexpr int PL_TRACE_CAP = 256;
+#define PL_TRACE(region, code)                                                        \
+  do {                                                                                \
+    if (tr_on && tr_n < PL_TRACE_CAP) {                                               \
+      P.trace[((region) * PL_TRACE_CAP + tr_n) * 2] = (code);                         \
+      P.trace[((region) * PL_TRACE_CAP + tr_n) * 2 + 1] = clock64();                  \
+      ++tr_n;                                                                         \
+    }                                                                                 \
+  } while (0)
 
 __device__ __forceinline__ void tma_load_tile_5d(const void* desc, uint64_t* bar, void* smem, int c0,
                                                  int c1, int c2, int c3, int c4) {
@@ -131,6 +141,8 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
   float* sred = ybuf + (P.ntiles * 128 + 2) * TLD;                // [epilogue warps][BN][2] + [BN] shifts
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tr_on = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && warp <= 2;
+  int tr_n = 0;
   const int ncm = P.cin_main / BK;
   const int nks_main = (P.th3 ? 3 : 9) * ncm;         // (td, th, chunk) steps; th3: (td, chunk)
   const int nks = nks_main + P.cin_extra / BK;
@@ -174,6 +186,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       int td = 0, th = 0, cc = 0;
       for (int ks = 0; ks < nks; ++ks) {
         if (!mbar_wait(&empty_bar[s], ph ^ 1, P.err_flag, 401)) { alive = false; break; }
+        PL_TRACE(0, 1);
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + P.a_stage_bytes;
         if (elect_one()) {
@@ -212,6 +225,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
                           U.n_tile * BN + t * P.cout);
           }
         }
+        PL_TRACE(0, 2);
         if (++cc == ncm) {
           cc = 0;
           if (P.th3) ++td;
@@ -233,9 +247,11 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       // wait until the epilogue has drained this accumulator buffer (first two units: free)
       if (it >= 2 && !mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1, P.err_flag, 404)) break;
       tc_fence_after();
+      PL_TRACE(1, 3);
       const uint32_t d_base = tmem_base + buf * buf_cols;
       for (int ks = 0; ks < nks; ++ks) {
         if (!mbar_wait(&full_bar[s], ph, P.err_flag, 402)) { alive = false; break; }
+        PL_TRACE(1, 4);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -286,6 +302,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
           if (ks == nks - 1) umma_commit(&tmem_full[buf]);     // accumulators of this unit complete
         }
         __syncwarp();
+        PL_TRACE(1, 6);
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
@@ -303,56 +320,70 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
     constexpr int NG = PL_EPI / 128;                       // warps per TMEM lane quarter
     const int plane = P.HB * P.Wp;
     const int sub_r = et / LPR, sub_c = (et % LPR) * 4;
+    // Unit-independent part of the read-out, computed once per thread (measured, tools/plane_trace.py: the
+    // per-unit index divisions and the dependent loads of the column constants were 2100 of the 6800
+    // cycles of a unit's epilogue chain): the offset of each of this thread's NJ store rows inside a
+    // unit (-1: pad column / beyond the unit), and the per-column constants when they do not depend on
+    // the unit (one N tile, batch-uniform or no time embedding).
+    int roff[NJ];
+    {
+      int q = sub_r;
+      int dl = q / plane;
+      int rem = q - dl * plane;
+      int hl = rem / P.Wp;
+      int w = rem - hl * P.Wp;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        roff[j] = (q < P.P && w < P.W && !(P.dbg & 8)) ? (dl * P.H + hl) * P.W + w : -1;
+        q += RPP;
+        w += RPP;
+        while (w >= P.Wp) {
+          w -= P.Wp;
+          if (++hl == P.HB) { hl = 0; ++dl; }
+        }
+      }
+    }
+    const int trow_u = (temb_uniform && P.t_dev) ? *P.t_dev : 0;
+    auto load_cv = [&](int nn, int n) {
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f), b2 = c, t4 = c;
+      if (P.bias) c = *reinterpret_cast<const float4*>(P.bias + nn);
+      if (P.bias2) b2 = *reinterpret_cast<const float4*>(P.bias2 + nn);
+      if (P.temb) {
+        const size_t trow = temb_uniform ? static_cast<size_t>(trow_u) * P.temb_ld : static_cast<size_t>(n) * P.temb_bstride;
+        t4 = *reinterpret_cast<const float4*>(P.temb + trow + nn);
+      }
+      c.x += b2.x; c.y += b2.y; c.z += b2.z; c.w += b2.w;      // same order as before: (bias + bias2) + temb
+      c.x += t4.x; c.y += t4.y; c.z += t4.z; c.w += t4.w;
+      return c;
+    };
+    const bool cv_const = P.n_ntiles == 1 && (P.temb == nullptr || temb_uniform);
+    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cv_const) cv = load_cv(sub_c, 0);
     int it = 0;
     bool alive = true;
     for (int u = blockIdx.x; u < P.n_units && alive; u += gridDim.x, ++it) {
+      PL_TRACE(2, 10);
       const PlaneUnit U = plane_unit(P, u);
       const int buf = it & 1;
       const int nn0 = U.n_tile * BN;
-      // Everything that does not depend on the accumulators is fetched before waiting for them:
-      // per-column constants of this thread's 4 output channels, the output row of each of its
-      // NJ store rows and the residual values there.
-      float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-      {
-        const int nn = nn0 + sub_c;
-        if (P.bias) cv = *reinterpret_cast<const float4*>(P.bias + nn);
-        if (P.bias2) {
-          const float4 t4 = *reinterpret_cast<const float4*>(P.bias2 + nn);
-          cv.x += t4.x; cv.y += t4.y; cv.z += t4.z; cv.w += t4.w;
-        }
-        if (P.temb) {
-          const size_t trow = temb_uniform ? static_cast<size_t>(P.t_dev ? *P.t_dev : 0) * P.temb_ld
-                                           : static_cast<size_t>(U.n) * P.temb_bstride;
-          const float4 t4 = *reinterpret_cast<const float4*>(P.temb + trow + nn);
-          cv.x += t4.x; cv.y += t4.y; cv.z += t4.z; cv.w += t4.w;
-        }
-      }
+      // Everything that does not depend on the accumulators is fetched before waiting for them: the
+      // residual values of this thread's NJ store rows (and the column constants when they vary).
+      if (!cv_const) cv = load_cv(nn0 + sub_c, U.n);
       int mi[NJ];
       float4 rv[NJ];
       {
-        int q = sub_r;
-        int dl = q / plane;
-        int rem = q - dl * plane;
-        int hl = rem / P.Wp;
-        int w = rem - hl * P.Wp;
+        const int base = ((U.n * P.D + U.d0) * P.H + U.h0) * P.W;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          mi[j] = -1;
+          mi[j] = roff[j] < 0 ? -1 : base + roff[j];
           rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < P.P && w < P.W && !(P.dbg & 8)) {
-            mi[j] = ((U.n * P.D + U.d0 + dl) * P.H + U.h0 + hl) * P.W + w;
-            if (P.resid)
-              rv[j] = *reinterpret_cast<const float4*>(P.resid + static_cast<size_t>(mi[j]) * P.cout + nn0 + sub_c);
-          }
-          q += RPP;
-          w += RPP;
-          while (w >= P.Wp) {
-            w -= P.Wp;
-            if (++hl == P.HB) { hl = 0; ++dl; }
-          }
+          if (mi[j] >= 0 && P.resid)
+            rv[j] = *reinterpret_cast<const float4*>(P.resid + static_cast<size_t>(mi[j]) * P.cout + nn0 + sub_c);
         }
       }
+      PL_TRACE(2, 11);
       if (!mbar_wait(&tmem_full[buf], (it >> 1) & 1, P.err_flag, 403)) { alive = false; break; }
+      PL_TRACE(2, 12);
       tc_fence_after();
       if (P.dbg & 64) {            // bring-up: no epilogue work at all
         tc_fence_before();
@@ -401,7 +432,9 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      PL_TRACE(2, 13);
       asm volatile("bar.sync 1, 512;" ::: "memory");
+      PL_TRACE(2, 14);
       // coalesced read-out: RPP rows per pass, LPR lanes per row
       float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = st1;   // GroupNorm partial sums of (v - cv)
 #pragma unroll
@@ -460,7 +493,9 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
         }
         if (et < LPR) *reinterpret_cast<float4*>(sred + (PL_EPI / 32) * BN * 2 + sub_c) = cv;
       }
+      PL_TRACE(2, 15);
       asm volatile("bar.sync 1, 512;" ::: "memory");       // ybuf / side are rewritten by the next unit
+      PL_TRACE(2, 16);
       if (P.stats_rec && et < BN) {
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "wgrad_umma.cuh"
 #include "conv_plane.cuh"
+#include "conv_res32.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -476,6 +477,83 @@ int plane_enqueue(const PlaneLaunch& L, cudaStream_t st) {
   if (L.bn == 128) return plane_launch_t<128, 32>(L, st);
   if (L.bn == 64) return plane_launch_t<64, 32>(L, st);
   return plane_launch_t<32, 32>(L, st);
+}
+
+// ================================ weights-resident 32 -> 32 conv (conv_res32.cuh) ================================
+int res32_init() {
+  static bool done = false;
+  if (done) return 0;
+  if (int rc = load_driver_syms()) return rc;
+  CM_CUDA(cudaFuncSetAttribute(conv_res32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  done = true;
+  return 0;
+}
+
+int res32_prepare(Res32Launch* L, const __half* act, int B, int D, int H, int W, int cin, const __half* extra,
+                  int cin_extra, const __half* wpacked, int cout, int terms) {
+  if (int rc = res32_init()) return rc;
+  memset(L, 0, sizeof(*L));
+  L->ok = false;
+  static const bool off = getenv("CM_NO_RES32") != nullptr;
+  if (off || cin != R32_C || cout != R32_C || terms != 2 || cin_extra % R32_C || cin_extra > 3 * R32_C) return 0;
+  const int Wp = W + 2;
+  if (Wp > 128) return 0;
+  int HB = 0;
+  for (int hb = 1; hb <= H; ++hb)
+    if (H % hb == 0 && hb * Wp <= 128) HB = hb;
+  if (HB == 0 || HB + 2 > 256 || (double)HB * W / 128.0 < 0.6) return 0;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    CM_CUDA(cudaGetDevice(&dev));
+    CM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  Res32Params& p = L->p;
+  const int nx = cin_extra / R32_C;
+  // a stage holds one haloed plane box; the th = 2 view of a 128-row MMA reads up to row 2*Wp + 127
+  const int stage_bytes = (int)(((long)(2 * Wp + 128) * 64 + 1023) / 1024 * 1024);
+  const long tail = 256 + 2 * R32_C * 4 + 2 * 8 * R32_C * 2 * 4 + 2 * 5 * 3 * R32_C * 4 + 2L * 128 * R32_TLD * 4;
+  const long fixed = 9L * R32_WBLK + (long)nx * R32_WX + tail + 1024;
+  int stages = (int)((227L * 1024 - fixed) / stage_bytes);
+  if (stages > R32_MAX_STAGES) stages = R32_MAX_STAGES;
+  if (const char* e = getenv("CM_RES32_STAGES")) stages = atoi(e);
+  if (stages < 3 || stages > R32_MAX_STAGES) return 0;
+  if (int rc = make_plane_map(&p.amap, act, B, D, H, W, R32_C, 32, 1, HB + 2)) return rc;
+  if (nx) {
+    CM_CHECK(extra != nullptr, "extra source pointer missing");
+    if (int rc = make_plane_map(&p.xmap, extra, B, D, H, W, cin_extra, 32, 1, HB)) return rc;
+  }
+  const size_t ktot = conv_packed_k(0, cin, cin_extra);
+  {
+    // packed weights [2*32 rows][Ktot] viewed as (k within a tap slab, row, tap slab): box {32, 64, 3} = the
+    // three tw slabs of one (td, th), hi rows then lo rows -> [tw][hi|lo][co] rows of 64 B in shared memory
+    cuuint64_t dims[3] = {(cuuint64_t)R32_C, (cuuint64_t)(2 * R32_C), 27};
+    cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)R32_C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)R32_C, (cuuint32_t)(2 * R32_C), 3};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)wpacked, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (resident weights) failed: %d (k=%zu)", (int)r, ktot);
+  }
+  if (nx)
+    if (int rc = make_weight_map(&p.wxmap, wpacked, (size_t)2 * R32_C, ktot, 32, 2 * R32_C)) return rc;
+  p.H = H; p.W = W; p.D = D; p.Wp = Wp; p.HB = HB; p.P = HB * Wp;
+  p.units_per_sample = D * (H / HB);
+  p.n_units = B * p.units_per_sample;
+  p.nx = nx;
+  p.stages = stages;
+  p.stage_bytes = stage_bytes;
+  p.err_flag = device_error_flag();
+  L->smem = (size_t)fixed + (size_t)stages * stage_bytes;
+  L->grid = dim3(p.n_units < n_sm ? p.n_units : n_sm, 1, 1);
+  L->flops = 2.0 * B * D * H * W * cout * (27.0 * cin + cin_extra);
+  L->ok = true;
+  return 0;
+}
+
+int res32_enqueue(const Res32Launch& L, cudaStream_t st) {
+  return launch_pdl(conv_res32_kernel<2>, L.grid, dim3(R32_THREADS), L.smem, st, L.p);
 }
 
 // ================================ weight gradient (wgrad_umma.cuh) ================================

@@ -1863,6 +1863,17 @@ int kernels_init() {
   CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CM_CUDA(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN3_SMEM));
   CM_CUDA(cudaFuncSetAttribute(gn_apply2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN3_SMEM));
+  if (getenv("CM_CARVEOUT")) {
+    // experiment: the conv kernels use 227 KB of shared memory; give the bandwidth kernels between them the same
+    // L1 / shared-memory carve-out so that consecutive launches do not reconfigure the SMs
+    const int mx = cudaSharedmemCarveoutMaxShared;
+    CM_CUDA(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CM_CUDA(cudaFuncSetAttribute(gn_apply2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CM_CUDA(cudaFuncSetAttribute(gn_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CM_CUDA(cudaFuncSetAttribute(final_conv_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CM_CUDA(cudaFuncSetAttribute(pack_first_input_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CM_CUDA(cudaFuncSetAttribute(attn_block_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  }
   if (int rc = attn_init()) return rc;
   if (int rc = conv_init()) return rc;
   done = true;

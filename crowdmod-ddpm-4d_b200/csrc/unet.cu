@@ -17,6 +17,7 @@
 #include "../../include/crowdmod_b200.h"
 #include "backward.cuh"
 #include "conv_plane.cuh"
+#include "conv_res32.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 #include "pack.cuh"
@@ -62,6 +63,7 @@ struct Op {
   int terms = 0;            // weight terms of THIS conv's forward (0 = cfg.weight_terms)
   ConvLaunch launch;
   PlaneLaunch plaunch;      // plane-tile kernel (conv_plane.cuh) when it covers the geometry
+  Res32Launch rlaunch;      // weights-resident 32 -> 32 kernel (conv_res32.cuh) when it covers the shape (sampling / eval)
   // ATTN
   int qkv = -1, ctx = -1, heads = 4;
   // training (backward) bookkeeping
@@ -103,6 +105,7 @@ struct cm_unet {
   int fullres_terms = 0;    // CROWDMOD_FULLRES_TERMS (0 = same as cfg.weight_terms)
   size_t first_wpack_off = 0;
   PlaneLaunch first_plane;
+  Res32Launch first_res;
   // device state
   __half* wpack = nullptr;
   size_t wpack_elems = 0;
@@ -532,6 +535,7 @@ int prepare_convs(cm_unet* u, int batch, int dup) {
   {
     const Level& l0 = u->levels[0];
     u->first_plane.ok = false;
+    u->first_res.ok = false;
     static const bool no_tc_first = getenv("CM_NO_PLANE") != nullptr || getenv("CM_FIRST_SIMT") != nullptr;
     if (!no_tc_first) {
       if (int rc = plane_prepare(&u->first_plane, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32 * dup, nullptr, 0,
@@ -542,12 +546,24 @@ int prepare_convs(cm_unet* u, int batch, int dup) {
         u->first_plane.p.bias = u->params[u->p_first_b].ptr;
         u->first_plane.p.out32 = nullptr;   // set per run (tensor of the OP_FIRST op)
       }
+      const int first_terms = (u->fullres_terms > 0 && dup == 1) ? u->fullres_terms : u->cfg.weight_terms;
+      if (u->first_plane.ok && dup == 1) {
+        if (int rc = res32_prepare(&u->first_res, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32, nullptr, 0,
+                                   wbase + u->first_wpack_off, u->cfg.base_channels, first_terms))
+          return rc;
+        if (u->first_res.ok) u->first_res.p.bias = u->params[u->p_first_b].ptr;
+      }
       for (Op& fo : u->ops) {
         if (fo.type != OP_FIRST) continue;
         Tens& t = u->tens[fo.out];
         t.rec_units = 0;
         static const bool no_rec = getenv("CM_NO_GNREC") != nullptr;
-        if (u->first_plane.ok && t.rec && !no_rec) {
+        if (u->first_res.ok && t.rec && !no_rec) {
+          Res32Params& q = u->first_res.p;
+          q.stats_rec = t.rec;
+          t.rec_units = q.units_per_sample;
+          t.rec_nvalid = q.HB * q.W;
+        } else if (u->first_plane.ok && t.rec && !no_rec) {
           PlaneParams& q = u->first_plane.p;
           q.stats_rec = t.rec;
           t.rec_units = q.units_per_sample;
@@ -583,11 +599,29 @@ int prepare_convs(cm_unet* u, int batch, int dup) {
         q.out16_lo = dup == 2 ? op.cout : 0;
       }
     }
+    op.rlaunch.ok = false;
+    if (op.mode == 0 && dup == 1 && op.plaunch.ok) {
+      if (int rc = res32_prepare(&op.rlaunch, tin.p16, batch, li.D, li.H, li.W, op.cin, extra, op.cin_extra, wp, op.cout, terms))
+        return rc;
+      if (op.rlaunch.ok) {
+        Res32Params& q = op.rlaunch.p;
+        q.bias = op.bias >= 0 ? u->params[op.bias].ptr : nullptr;
+        q.bias2 = op.bias2 >= 0 ? u->params[op.bias2].ptr : nullptr;
+        q.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
+        q.out32 = u->tens[op.out].p32;
+        q.out16 = u->tens[op.out].p16;
+      }
+    }
     {
       Tens& t = u->tens[op.out];
       t.rec_units = 0;
       static const bool no_rec = getenv("CM_NO_GNREC") != nullptr;
-      if (op.plaunch.ok && t.rec && !no_rec) {
+      if (op.rlaunch.ok && t.rec && !no_rec) {
+        Res32Params& q = op.rlaunch.p;
+        q.stats_rec = t.rec;
+        t.rec_units = q.units_per_sample;
+        t.rec_nvalid = q.HB * q.W;
+      } else if (op.plaunch.ok && t.rec && !no_rec) {
         PlaneParams& q = op.plaunch.p;
         q.stats_rec = t.rec;
         t.rec_units = q.units_per_sample;
@@ -671,9 +705,15 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
           if (int e = pack_first_input_enqueue(rc.future, rc.past, u->tens[u->first_in].p16, rc.batch, l0.H, l0.W,
                                                c.past_len, c.future_len, c.in_channels, rc.dup, st))
             return e;
-          PlaneLaunch L = u->first_plane;
-          L.p.out32 = u->tens[op.out].p32;
-          if (int e = plane_enqueue(L, st)) return e;
+          if (u->first_res.ok) {
+            Res32Launch R = u->first_res;
+            R.p.out32 = u->tens[op.out].p32;
+            if (int e = res32_enqueue(R, st)) return e;
+          } else {
+            PlaneLaunch L = u->first_plane;
+            L.p.out32 = u->tens[op.out].p32;
+            if (int e = plane_enqueue(L, st)) return e;
+          }
           if (launches) ++*launches;
           break;
         }
@@ -722,6 +762,17 @@ int run_ops(cm_unet* u, RunCtx& rc, cudaStream_t st, int64_t* launches,
         if (launches) *launches += nl - 1;
       } break;
       case OP_CONV: {
+        if (op.rlaunch.ok) {
+          Res32Launch R = op.rlaunch;
+          if (op.temb_off >= 0) {
+            R.p.temb = rc.temb + op.temb_off;
+            R.p.t_dev = rc.t_dev;
+            R.p.temb_ld = u->temb_ld;
+            R.p.temb_bstride = rc.temb_bstride;
+          }
+          if (int e = res32_enqueue(R, st)) return e;
+          break;
+        }
         if (op.plaunch.ok) {
           PlaneLaunch L = op.plaunch;
           if (op.temb_off >= 0) {

@@ -389,3 +389,39 @@ def test_conv_plane_vs_torch(nat, case, terms):
     e = rel_l2(out32, ref)
     assert e <= (2e-5 if terms == 2 else 1e-3), f"rel-L2 {e:.3e}; " + describe_mismatch(out32, ref)
     assert rel_l2(out16.float(), ref) <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# weights-resident 32 -> 32 conv (conv_res32.cuh): tw taps and hi|lo terms stacked along N = 192, one-tile
+# units, weights loaded once per CTA, drain / store warp pipeline.  impl=3 forces it (error if not covered).
+# ---------------------------------------------------------------------------------------------
+RES32_CASES = [
+    (0, 2, 8, 12, 36, 32, 32, 0, True),     # encoder_blocks.0.conv_2 (identity residual), HB = 3
+    (0, 2, 8, 12, 36, 32, 32, 0, False),    # encoder_blocks.0.conv_1 / UNet.first
+    (0, 2, 8, 12, 36, 32, 32, 96, False),   # decoder_blocks.6.conv_2 + match_input (3 chunks)
+    (0, 3, 8, 12, 36, 32, 32, 64, False),   # decoder_blocks.7.conv_2 + match_input (2 chunks), odd batch
+    (0, 1, 8, 28, 24, 32, 32, 0, True),     # HERMES-CR-120 level 0 (HB = 4)
+    (0, 5, 8, 8, 12, 32, 32, 32, True),     # ETH-UCY level 0 (whole plane per unit) + slab + residual
+    (0, 150, 8, 12, 36, 32, 32, 0, True),   # many units per persistent CTA (both TMEM / transpose buffers reused)
+    (0, 1, 3, 12, 36, 32, 32, 0, False),    # fewer units than SMs, odd depth
+]
+
+
+@pytest.mark.parametrize("case", RES32_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d_r%d" % c)
+def test_conv_res32_vs_torch(nat, case):
+    mode, B, D, H, W, cin, cout, cx, resid = case
+    out32, out16, ref, flag = run_conv(nat, mode, B, D, H, W, cin, cout, cx, 2, resid, impl=3)
+    assert flag == 0, f"device protocol error flag {flag}"
+    e = rel_l2(out32, ref)
+    assert e <= 2e-5, f"rel-L2 {e:.3e}; " + describe_mismatch(out32, ref)
+    assert rel_l2(out16.float(), ref) <= 1e-3
+
+
+def test_conv_res32_matches_plane_kernel_and_is_deterministic(nat):
+    """Same operands through conv_plane_kernel and conv_res32_kernel agree to fp32 summation order; two runs of
+    the resident kernel are bit-identical."""
+    a, _, _, _ = run_conv(nat, 0, 4, 8, 12, 36, 32, 32, 96, 2, True, impl=3)
+    b, _, _, _ = run_conv(nat, 0, 4, 8, 12, 36, 32, 32, 96, 2, True, impl=3)
+    c, _, _, _ = run_conv(nat, 0, 4, 8, 12, 36, 32, 32, 96, 2, True, impl=2)
+    assert torch.equal(a, b)
+    assert rel_l2(a, c) <= 2e-6
