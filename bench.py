@@ -410,6 +410,118 @@ def extras_bench(rank, world, dev):
                      "scaling": "weak", "samples": 64 * world, "chain_ms": ms,
                      "sequences_per_s": 64 * world / (ms * 1e-3), "denoiser_step_ms": ms / T_STEPS,
                      "algorithmic_tflops": fl * 64 * world * T_STEPS / (ms * 1e-3) / 1e12, "finite": ok}
+    if rank == 0:
+        out.update(feed_and_metrics_bench(dev))
+    return out
+
+
+def feed_and_metrics_bench(dev):
+    """The callers either side of the hot path, rank 0 only, each against the HBM roofline
+    (MEASURED_PEAKS.json) with the oracle port of the reference's CPU code timed beside it on a bounded sample:
+      * data feed: one epoch of BATCH_SIZE-64 (past, future) windows gathered on the device from HBM-resident raw
+        sequences (reference: MacropropsDataset + DataLoader + per-step .to(device), utils/dataset.py:22-53, ddpm.py:136-137);
+      * metrics tail: PSNR / MASK_PSNR / RE_DENSITY / TV of generate_metrics' 1280-sample batch
+        (reference: utils/metrics/metricsGenerator.py:120-186,293-339)."""
+    import types
+    import numpy as np
+    from crowdmod_ddpm_4d_b200.utils.dataset_gpu import GpuMacropropsDataset, GpuWindowLoader
+    from crowdmod_ddpm_4d_b200.utils.metrics_gpu import GpuMetricsGenerator, compute_metrics_gpu
+    from oracle import dataset_oracle as dso
+    from oracle import metrics_oracle as mo
+    hbm = peaks()["hbm_gbs"]
+    out = {}
+    # ---- data feed: 64 raw ATC sequences of 200 frames, stride 8 -> 1600 windows = 25 batches of 64
+    w = WORKLOADS["atc"]
+    rng = np.random.default_rng(3)
+    seq = rng.normal(size=(64, 3, w["rows"], w["cols"], 200)).astype(np.float32)
+    cfg = types.SimpleNamespace(DATASET=types.SimpleNamespace(PAST_LEN=w["past"], FUTURE_LEN=w["fut"]),
+                                MACROPROPS=types.SimpleNamespace(EPS=1e-6))
+    ds = GpuMacropropsDataset(seq, cfg, 3, stride=8, device=dev)
+    loader = GpuWindowLoader(ds, 64, shuffle=True, drop_last=True)
+    for _ in loader:      # warm-up epoch
+        pass
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    nb = 0
+    for _ in range(4):
+        for past, fut in loader:
+            nb += 1
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = a.elapsed_time(b) / nb
+    per_batch_bytes = 64 * 3 * w["rows"] * w["cols"] * (w["past"] + w["fut"]) * 4 * 2
+    # kernel alone (CUDA events around back-to-back gathers of one fixed batch)
+    import crowdmod_ddpm_4d_b200._native as nat
+    ids = torch.randperm(len(ds), device=dev)[:64].contiguous()
+    pbuf, fbuf = ds.gather(ids)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(200):
+        nat.check(nat.lib().cm_window_gather(nat.ptr(ds.seq_all), 64, 3, w["rows"], w["cols"], 200, nat.ptr(ds._seq_idx),
+                                             nat.ptr(ds._t0), nat.ptr(ids), 64, w["past"], w["fut"], nat.ptr(pbuf), nat.ptr(fbuf),
+                                             nat.current_stream()))
+    b.record()
+    torch.cuda.synchronize()
+    k_us = a.elapsed_time(b) * 1e3 / 200
+    t1 = time.perf_counter()
+    torch.manual_seed(0)
+    ncpu = 0
+    for past, fut in dso.batches(seq, w["past"], w["fut"], 8, 64, shuffle=True, drop_last=True):
+        past.to(dev, non_blocking=False), fut.to(dev, non_blocking=False)
+        ncpu += 1
+    torch.cuda.synchronize()
+    cpu_s = time.perf_counter() - t1
+    out["data_feed"] = {"workload": "config/ATC.yml windows (past 5 + future 3, stride 8) of 64 HBM-resident raw sequences x 200 "
+                                    "frames, shuffled batches of 64", "batches_per_s": nb / wall, "ms_per_batch_device": dev_ms,
+                        "gather_kernel_us": k_us,
+                        "roofline": {"bound": "hbm", "achieved": per_batch_bytes / (k_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
+                                     "frac": per_batch_bytes / (k_us * 1e-6) / 1e9 / hbm,
+                                     "algorithmic_bytes_per_batch": per_batch_bytes},
+                        "cpu_baseline": {"value": ncpu / cpu_s, "unit": "batches/s", "cores": 1, "kind": "port",
+                                         "sample": f"one epoch ({ncpu} batches): host window slicing + collate + .to(device), "
+                                                   "oracle/ restatement of the reference's single-process loader"}}
+    # ---- metrics tail at n = 1280
+    pred, gt = mo.synthetic_pair(1280, w["rows"], w["cols"], w["fut"], 11)
+    pd_, gd = torch.from_numpy(pred).to(dev), torch.from_numpy(gt).to(dev)
+    params = types.SimpleNamespace(MPROPS_COUNT=3)
+    for _ in range(2):
+        gen = GpuMetricsGenerator(pd_, gd, params)
+        compute_metrics_gpu(cfg, gen, "ALL", 20)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        gen = GpuMetricsGenerator(pd_, gd, params)
+        compute_metrics_gpu(cfg, gen, "ALL", 20)
+    torch.cuda.synchronize()
+    gpu_s = (time.perf_counter() - t0) / 5
+    outbuf = torch.empty(1280, w["fut"], 21, dtype=torch.float64, device=dev)
+    a.record()
+    for _ in range(50):
+        nat.check(nat.lib().cm_metrics_reduce(nat.ptr(pd_), nat.ptr(gd), 1280, 3, w["rows"], w["cols"], w["fut"], nat.ptr(outbuf),
+                                              nat.current_stream()))
+    b.record()
+    torch.cuda.synchronize()
+    k_us = a.elapsed_time(b) * 1e3 / 50
+    mbytes = 2 * pred.size * 4
+    t1 = time.perf_counter()
+    ncpu = 64
+    with np.errstate(all="ignore"):
+        mo.compute_psnr_metric(pred[:ncpu], gt[:ncpu], 4, 1e-6)
+        mo.compute_psnr_metric(pred[:ncpu], gt[:ncpu], 4, 1e-6, masked=True)
+        mo.compute_re_density(pred[:ncpu], gt[:ncpu], 4, 1e-6)
+        mo.compute_tv_metric(pred[:ncpu], gt[:ncpu])
+    cpu_s = (time.perf_counter() - t1) * (1280 / ncpu)
+    out["metrics_tail"] = {"workload": "PSNR + MASK_PSNR + RE_DENSITY + TV of 1280 predicted ATC sequences (generate_metrics batch), "
+                                       "device tensors in, numpy tables out (one D2H read of 1280 x 3 x 21 doubles)",
+                           "samples_per_s": 1280 / gpu_s, "ms_total": gpu_s * 1e3, "reduce_kernel_us": k_us,
+                           "roofline": {"bound": "hbm", "achieved": mbytes / (k_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
+                                        "frac": mbytes / (k_us * 1e-6) / 1e9 / hbm, "algorithmic_bytes": mbytes},
+                           "cpu_baseline": {"value": 1280 / cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
+                                            "sample": f"{ncpu} of 1280 samples through the oracle/ restatement of the reference's "
+                                                      "per-sample numpy loops, extrapolated"}}
     return out
 
 

@@ -18,6 +18,7 @@ Plotting (utils/plot/*) and CPU metrics (utils/metrics/*) are outside the hot pa
 imported from the reference when present on sys.path and skipped (with a log line) otherwise.
 """
 import gc
+import os
 import logging
 import re
 
@@ -414,12 +415,37 @@ class DDPM_model:
                 break
         logging.info("===" * 20)
         logging.info(f'Computing metrics on predicted mprops sequences with {self.arch} model.')
-        try:
-            from utils.metrics.metricsGenerator import MetricsGenerator, compute_metrics
-        except ImportError:
-            logging.info("utils.metrics not importable (reference not on sys.path): metrics skipped")
-            return pred_seq_list, gt_seq_list
-        metricsGenerator = MetricsGenerator(pred_seq_list, gt_seq_list, self.cfg.METRICS, output_dir)
-        compute_metrics(self.cfg, metricsGenerator, metric, chunkRepdPastSeq, match, batches_to_use,
-                        samples_per_batch, self.arch)
+        # reduction metrics (PSNR / MASK_PSNR / RE_DENSITY / TV) on the device in one launch; SSIM, the motion-feature
+        # histograms and the energy metric stay with the reference's CPU class when it is importable
+        from ...utils.metrics_gpu import GpuMetricsGenerator, compute_metrics_gpu
+        title = (f"{self.cfg.DATASET.BATCH_SIZE * chunkRepdPastSeq * batches_to_use} samples in total "
+                 f"(BS:{self.cfg.DATASET.BATCH_SIZE}, Rep:{chunkRepdPastSeq}, TB:{batches_to_use})-({self.arch})")
+        covered = []
+        if metric in ("ALL",) + GpuMetricsGenerator.GPU_METRICS:
+            gpu_gen = GpuMetricsGenerator(pred_seq_list, gt_seq_list, self.cfg.METRICS, output_dir)
+            covered = compute_metrics_gpu(self.cfg, gpu_gen, metric, chunkRepdPastSeq)
+            gpu_files = gpu_gen.save_data_metrics(match, title, samples_per_batch)
+            self.last_metrics = gpu_gen.data_dict
+        rest = metric if metric not in covered else None
+        if metric == "ALL" or rest is not None:
+            try:
+                from utils.metrics.metricsGenerator import MetricsGenerator
+            except ImportError:
+                logging.info("utils.metrics not importable (reference not on sys.path): SSIM / motion-feature / energy "
+                             "metrics skipped")
+                return pred_seq_list, gt_seq_list
+            ref_gen = MetricsGenerator(pred_seq_list, gt_seq_list, self.cfg.METRICS, output_dir)
+            if metric in ('SSIM', 'ALL'):
+                ref_gen.compute_ssim_metric(chunkRepdPastSeq)
+            if metric in ('MF_MSE', 'MF_BHATT', 'ALL'):
+                ref_gen.compute_motion_feature_metrics(metric in ('MF_MSE', 'ALL'), metric in ('MF_BHATT', 'ALL'))
+            if metric in ('ENERGY', 'ALLA'):
+                ref_gen.compute_energy_metric(chunkRepdPastSeq)
+            ref_gen.save_data_metrics(match, title, samples_per_batch)
+            if covered:          # the reference rewrote metrics_files.json with its own files only: merge ours back in
+                import json
+                jp = os.path.join(output_dir, "metrics_files.json")
+                files = json.load(open(jp))
+                files.update({k: v for k, v in gpu_files.items() if k != "title"})
+                json.dump(files, open(jp, "w"), indent=2)
         return pred_seq_list, gt_seq_list

@@ -204,6 +204,30 @@ CM_API int cm_op_conv3d_wgrad(int mode, const void* act16, int B, int D, int H, 
                               const void* extra16, int cin_extra, const void* dout16, int cout,
                               float* dw, float* dwx, int impl, void* stream);
 
+/* ---- callers either side of the hot path -------------------------------------- */
+
+/* Data feed: one batch of (past, future) windows gathered ON the device from HBM-resident raw sequences.
+ * Replaces MacropropsDataset.__getitem__ + DataLoader collate + the per-step host->device copy
+ * (/root/reference/utils/dataset.py:46-53, models/diffusion/ddpm.py:136-137).
+ * seq: fp32 [n_seq][channels][rows][cols][raw_len]; seq_idx / t0: int32 device tables of the dataset's windows
+ * (sequence and first frame, the (seq_idx, t) pairs of dataset.py:33-37); ids: int64 [batch] device, the windows of
+ * this batch (NULL: windows 0..batch-1); past: fp32 [batch][channels][rows][cols][past_len], future: fp32
+ * [batch][channels][rows][cols][future_len].  Bit-exact copy; ONE launch, stream-ordered, no allocation. */
+CM_API int cm_window_gather(const float* seq, int64_t n_seq, int channels, int rows, int cols, int raw_len,
+                     const int32_t* seq_idx, const int32_t* t0, const int64_t* ids, int batch, int past_len,
+                     int future_len, float* past, float* future, void* stream);
+
+/* Metrics tail: per (sample, frame) reductions from which PSNR / MASK_PSNR / RE_DENSITY / TV_OVER_TIME and the
+ * macro-property ranges are closed forms (/root/reference/utils/metrics/metricsGenerator.py:43-92,120-186,293-339).
+ * pred, gt: fp32 [n][channels >= 3][rows][cols][frames] on the device (rho, vx, vy first).
+ * out: fp64 [n][frames][CM_METRICS_PER_FRAME] on the device:
+ *   [0..2]  sum (gt - pred)^2 per property        [3..5]  the same over cells with gt rho > 1e-5   [6] number of such cells
+ *   [7..9]  total variation of pred per property  [10..12] total variation of gt
+ *   [13]    sum of pred rho   [14] sum of gt rho   [15 + 2c], [16 + 2c]  min / max of gt property c */
+#define CM_METRICS_PER_FRAME 21
+CM_API int cm_metrics_reduce(const float* pred, const float* gt, int n, int channels, int rows, int cols, int frames,
+                      double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

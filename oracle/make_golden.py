@@ -149,6 +149,25 @@ def schedule_case(ns):
                       "sqrt_one_minus_alpha_bar")})
 
 
+def metrics_case(ns, name, n, rows, cols, F, seed, chunk, eps):
+    """Reduction metrics of the reference's MetricsGenerator (utils/metrics/metricsGenerator.py:120-186,293-339) on a
+    seeded (pred, gt) pair; the pair itself is regenerated from the seed by oracle.metrics_oracle.synthetic_pair."""
+    from oracle import metrics_oracle as mo
+    pred, gt = mo.synthetic_pair(n, rows, cols, F, seed)
+    params = ns.EasyDict({"MPROPS_COUNT": 3})
+    gen = ns.MetricsGenerator([torch.from_numpy(p) for p in pred], [torch.from_numpy(g) for g in gt], params, None)
+    with np.errstate(all="ignore"):
+        gen.compute_psnr_metric(chunk, eps)
+        gen.compute_psnr_metric(chunk, eps, masked_flag=True)
+        gen.compute_re_density_metric(chunk, eps)
+        gen.compute_tv_metric()
+    keys = ["PSNR", "MAX_PSNR", "PSNR_OVER_TIME", "MAX_PSNR_OVER_TIME", "MASK_PSNR", "MAX_MASK_PSNR",
+            "MASK_PSNR_OVER_TIME", "MAX_MASK_PSNR_OVER_TIME", "RE_DENSITY", "MIN_RE_DENSITY", "TV_OVER_TIME"]
+    save(name, {"n": n, "rows": rows, "cols": cols, "F": F, "seed": seed, "chunk": chunk, "eps": eps,
+                "ranges": [gen.rho_range, gen.vx_range, gen.vy_range]},
+         **{k: gen.data_dict[k] for k in keys})
+
+
 def main():
     """python -m oracle.make_golden [case ...]: regenerate every golden, or only the named ones."""
     ns = ref_shim.load()
@@ -159,6 +178,8 @@ def main():
         # whole chain; reference loop models/diffusion/ddpm.py:206-236)
         if "chain_atc_T1000" in only:
             chain_case(ns, "chain_atc_T1000", ATC, 42, 2, 12, 36, 5, 3, 1000, 0.5, "None", "DDPM")
+        if "metrics_small" in only:
+            metrics_case(ns, "metrics_small", 8, 12, 36, 3, 7, 4, 1e-6)
         return
     schedule_case(ns)
     unet_case(ns, "unet_atc_b2", ATC, 42, 2, 12, 36, 5, 3, [7, 640])
@@ -172,6 +193,7 @@ def main():
     kw = dict(ATC, dropout_rate=0.0)
     train_case(ns, "train_atc_b2", kw, 42, 2, 12, 36, 5, 3, 1000, 0.5)
     chain_case(ns, "chain_atc_T1000", ATC, 42, 2, 12, 36, 5, 3, 1000, 0.5, "None", "DDPM")
+    metrics_case(ns, "metrics_small", 8, 12, 36, 3, 7, 4, 1e-6)
 
 
 if __name__ == "__main__":

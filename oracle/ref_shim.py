@@ -137,6 +137,17 @@ def load():
         ns.DDPM = ns.ddpm.DDPM
         ns.DDPM_model = ns.ddpm.DDPM_model
         ns.EasyDict = sys.modules["easydict"].EasyDict
+        # the callers either side of the path: CPU metrics tail, windowed dataset
+        try:
+            ns.metrics = importlib.import_module("utils.metrics.metricsGenerator")
+            ns.MetricsGenerator = ns.metrics.MetricsGenerator
+        except Exception as e:  # noqa: BLE001 - optional: only the f3 pins need it
+            ns.metrics, ns.MetricsGenerator, ns.metrics_error = None, None, repr(e)
+        try:
+            ns.dataset = importlib.import_module("utils.dataset")
+            ns.MacropropsDataset = ns.dataset.MacropropsDataset
+        except Exception as e:  # noqa: BLE001
+            ns.dataset, ns.MacropropsDataset, ns.dataset_error = None, None, repr(e)
         return ns
     finally:
         sys.path.remove(REF_ROOT)

@@ -68,3 +68,28 @@ def test_schedule_matches_reference_golden():
     # anchors quoted in SURVEY.md §8c
     assert abs(s["beta"][0].item() - 5e-5) < 1e-9 and abs(s["beta"][999].item() - 1e-2) < 1e-8
     assert abs(s["alpha_bar"][999].item() - 6.4618e-3) < 1e-6
+
+
+def test_metrics_oracle_vs_reference_golden():
+    """oracle/metrics_oracle.py against the reference's MetricsGenerator outputs (metricsGenerator.py:120-186,
+    293-339) on the seeded pair, including the empty-mask frame whose masked PSNR is nan in the reference."""
+    import json
+    import os
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_small.npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    pred, gt = mo.synthetic_pair(meta["n"], meta["rows"], meta["cols"], meta["F"], meta["seed"])
+    assert np.allclose(mo.mprops_ranges(gt), meta["ranges"], rtol=0, atol=0)
+    with np.errstate(all="ignore"):
+        a = mo.compute_psnr_metric(pred, gt, meta["chunk"], meta["eps"])
+        b = mo.compute_psnr_metric(pred, gt, meta["chunk"], meta["eps"], masked=True)
+    for k, v in zip(["PSNR", "MAX_PSNR", "PSNR_OVER_TIME", "MAX_PSNR_OVER_TIME"], a):
+        np.testing.assert_allclose(v, g[k], rtol=0, atol=1e-12)
+    for k, v in zip(["MASK_PSNR", "MAX_MASK_PSNR", "MASK_PSNR_OVER_TIME", "MAX_MASK_PSNR_OVER_TIME"], b):
+        assert np.isnan(g[k]).sum() > 0                      # the empty frame
+        np.testing.assert_allclose(v, g[k], rtol=0, atol=1e-12, equal_nan=True)
+    re, mre = mo.compute_re_density(pred, gt, meta["chunk"], meta["eps"])
+    np.testing.assert_array_equal(re, g["RE_DENSITY"])
+    np.testing.assert_array_equal(mre, g["MIN_RE_DENSITY"])
+    np.testing.assert_array_equal(mo.compute_tv_metric(pred, gt), g["TV_OVER_TIME"])

@@ -62,3 +62,54 @@ def test_schedule_and_step_vs_live_reference(ns):
     torch.manual_seed(9)
     z = torch.randn_like(x)
     assert torch.equal(out, do.ddpm_step(s, e, x, 321, z))
+
+
+def test_metrics_oracle_pinned_to_live_reference():
+    """the numpy restatement equals the unmodified MetricsGenerator on a fresh seeded pair."""
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    ns = ref_shim.load()
+    if ns.MetricsGenerator is None:
+        pytest.skip("reference metrics module not importable: " + getattr(ns, "metrics_error", ""))
+    pred, gt = mo.synthetic_pair(6, 8, 12, 3, 99)
+    gen = ns.MetricsGenerator([torch.from_numpy(p) for p in pred], [torch.from_numpy(g) for g in gt],
+                              ns.EasyDict({"MPROPS_COUNT": 3}), None)
+    with np.errstate(all="ignore"):
+        gen.compute_psnr_metric(3, 1e-6)
+        gen.compute_psnr_metric(3, 1e-6, masked_flag=True)
+        gen.compute_re_density_metric(3, 1e-6)
+        gen.compute_tv_metric()
+        a = mo.compute_psnr_metric(pred, gt, 3, 1e-6)
+        b = mo.compute_psnr_metric(pred, gt, 3, 1e-6, masked=True)
+    for k, v in zip(["PSNR", "MAX_PSNR", "PSNR_OVER_TIME", "MAX_PSNR_OVER_TIME"], a):
+        np.testing.assert_allclose(v, gen.data_dict[k], rtol=0, atol=1e-12)
+    for k, v in zip(["MASK_PSNR", "MAX_MASK_PSNR", "MASK_PSNR_OVER_TIME", "MAX_MASK_PSNR_OVER_TIME"], b):
+        np.testing.assert_allclose(v, gen.data_dict[k], rtol=0, atol=1e-12, equal_nan=True)
+    re, mre = mo.compute_re_density(pred, gt, 3, 1e-6)
+    np.testing.assert_array_equal(re, gen.data_dict["RE_DENSITY"])
+    np.testing.assert_array_equal(mre, gen.data_dict["MIN_RE_DENSITY"])
+    np.testing.assert_array_equal(mo.compute_tv_metric(pred, gt), gen.data_dict["TV_OVER_TIME"])
+
+
+def test_dataset_oracle_pinned_to_live_reference():
+    """window index table, windows and DataLoader batch order equal the unmodified
+    MacropropsDataset + torch DataLoader (utils/dataset.py:22-53,169-190), shuffled and not."""
+    import numpy as np
+    from torch.utils.data import DataLoader
+    from oracle import dataset_oracle as dso
+    ns = ref_shim.load()
+    if ns.MacropropsDataset is None:
+        pytest.skip("reference dataset module not importable: " + getattr(ns, "dataset_error", ""))
+    rng = np.random.default_rng(5)
+    seq = rng.normal(size=(3, 3, 4, 5, 23)).astype(np.float32)
+    cfg = ns.EasyDict({"DATASET": {"PAST_LEN": 5, "FUTURE_LEN": 3}})
+    ds = ns.MacropropsDataset(seq, cfg, 3, stride=4)
+    assert [tuple(i) for i in ds.indices] == dso.window_indices(3, 23, 5, 3, 4)
+    for shuffle, drop_last in ((False, False), (True, True), (True, False)):
+        torch.manual_seed(1234)
+        ref_batches = list(DataLoader(ds, batch_size=4, shuffle=shuffle, drop_last=drop_last))
+        torch.manual_seed(1234)
+        ours = list(dso.batches(seq, 5, 3, 4, 4, shuffle=shuffle, drop_last=drop_last))
+        assert len(ours) == len(ref_batches)
+        for (p0, f0), (p1, f1) in zip(ref_batches, ours):
+            assert torch.equal(p0, p1) and torch.equal(f0, f1)
