@@ -37,6 +37,14 @@ class UNetConfig(C.Structure):
     ]
 
 
+class DitConfig(C.Structure):
+    """struct cm_dit_config (include/crowdmod_b200.h)."""
+
+    _fields_ = [(k, C.c_int32) for k in (
+        "in_channels", "out_channels", "rows", "cols", "past_len", "future_len", "t_patch", "patch", "hidden", "depth",
+        "heads", "mlp_hidden", "time_multiple", "table_steps", "t_max_slots")]
+
+
 class ChainArgs(C.Structure):
     """struct cm_chain_args (include/crowdmod_b200.h)."""
 
@@ -117,6 +125,16 @@ SIGNATURES = {
     "cm_op_final_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p]),
+    "cm_dit_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cm_dit_destroy": (C.c_int, [C.c_void_p]),
+    "cm_dit_param_count": (C.c_int, [C.c_void_p]),
+    "cm_dit_param_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "cm_dit_bind_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
+    "cm_dit_pack": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cm_dit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cm_dit_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cm_dit_flops_per_sample": (C.c_double, [C.c_void_p]),
+    "cm_dit_last_launches": (C.c_int64, [C.c_void_p]),
     "cm_window_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cm_metrics_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

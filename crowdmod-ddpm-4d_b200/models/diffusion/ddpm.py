@@ -194,8 +194,15 @@ class DDPM_model:
                         dropout_rate=c.DROPOUT_RATE, time_multiple=c.TIME_EMB_MULT,
                         condition=c.CONDITION)
         if self.arch == "DDPM-DiT":
-            raise NotImplementedError("DDPM-DiT (DiT4D_V4) is outside this round's hot path "
-                                      "(SURVEY.md §8f #2); use arch='DDPM-UNet'")
+            # reference ddpm.py:88-104 (sampling / inference natively; training this backbone raises in forward)
+            from ..backbones.DiT4D_V4 import DiT4D_V4
+            c = self.denoiser_cfg
+            return DiT4D_V4(input_channels=self.mprops_count, output_channels=self.mprops_count,
+                            grid_rows=self.cfg.MACROPROPS.ROWS, grid_cols=self.cfg.MACROPROPS.COLS,
+                            past_len=self.cfg.DATASET.PAST_LEN, future_len=self.cfg.DATASET.FUTURE_LEN,
+                            t_patch_size=c.T_PATCH_SIZE, patch_size=c.PATCH_SIZE, hidden_size=c.HIDDEN_SIZE,
+                            depth=c.DEPTH, num_heads=c.NUM_HEADS, mlp_ratio=c.MLP_RATIO, dropout_rate=c.DROPOUT_RATE,
+                            time_multiple=c.TIME_EMB_MULT, condition=c.CONDITION)
         raise ValueError(f"Unknown Architecture {self.arch}")
 
     # ------------------------------------------------------------------ training

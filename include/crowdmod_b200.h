@@ -204,6 +204,37 @@ CM_API int cm_op_conv3d_wgrad(int mode, const void* act16, int B, int D, int H, 
                               const void* extra16, int cin_extra, const void* dout16, int cout,
                               float* dw, float* dwx, int impl, void* stream);
 
+/* ---- second backbone: DiT4D_V4 ------------------------------------------------------
+ * Replaces /root/reference/models/backbones/DiT4D_V4.py:228-375 (selected by --arch DDPM-DiT at
+ * models/diffusion/ddpm.py:88-104) for inference / sampling: same forward(future, t, past) contract and the same
+ * reverse chain (cm_chain_args) as the UNet plan; parameters are bound by the reference's state_dict names. */
+typedef struct cm_dit_config {
+  int32_t in_channels, out_channels;   /* mprops_count (1..4)                                   */
+  int32_t rows, cols;                  /* MACROPROPS.ROWS / COLS                                */
+  int32_t past_len, future_len;        /* DATASET.PAST_LEN / FUTURE_LEN                         */
+  int32_t t_patch, patch;              /* T_PATCH_SIZE / PATCH_SIZE                             */
+  int32_t hidden, depth, heads;        /* HIDDEN_SIZE / DEPTH / NUM_HEADS                       */
+  int32_t mlp_hidden;                  /* int(HIDDEN_SIZE * MLP_RATIO)                          */
+  int32_t time_multiple;               /* TIME_EMB_MULT                                         */
+  int32_t table_steps;                 /* rows of the sinusoid table (total_time_steps)         */
+  int32_t t_max_slots;                 /* rows of temporal_pos_embed (T_max // t_patch)         */
+} cm_dit_config;
+typedef struct cm_dit cm_dit;
+CM_API int cm_dit_create(const cm_dit_config* cfg, cm_dit** out);                  /* DiT4D_V4.__init__ :229-311 */
+CM_API int cm_dit_destroy(cm_dit* d);
+CM_API int cm_dit_param_count(const cm_dit* d);
+CM_API int cm_dit_param_info(const cm_dit* d, int idx, char* name, int name_cap, int64_t* shape5, int* ndim);
+CM_API int cm_dit_bind_params(cm_dit* d, const void* const* ptrs, int count);      /* state_dict order of param_info */
+CM_API int cm_dit_pack(cm_dit* d, void* stream);                                   /* fp16 hi|lo caches; after load / weight change */
+/* DiT4D_V4.forward(future, t, past) :348-375 (eval): future fp32 [B,C,H,W,F], t int64 [B], past fp32 [B,C,H,W,P], all device */
+CM_API int cm_dit_forward(cm_dit* d, const float* future, const int64_t* t, const float* past, float* eps_out, int batch,
+                   void* stream);
+/* _generate_ddpm / _generate_ddim with this backbone (ddpm.py:206-282): eager launches, the update fused into the
+ * un-patch kernel; use_graph is ignored */
+CM_API int cm_dit_sample(cm_dit* d, const cm_chain_args* args, void* stream);
+CM_API double cm_dit_flops_per_sample(const cm_dit* d);
+CM_API int64_t cm_dit_last_launches(const cm_dit* d);
+
 /* ---- callers either side of the hot path -------------------------------------- */
 
 /* Data feed: one batch of (past, future) windows gathered ON the device from HBM-resident raw sequences.

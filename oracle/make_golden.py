@@ -168,6 +168,32 @@ def metrics_case(ns, name, n, rows, cols, F, seed, chunk, eps):
          **{k: gen.data_dict[k] for k in keys})
 
 
+DIT_ATC = dict(input_channels=3, output_channels=3, grid_rows=12, grid_cols=36, past_len=5, future_len=3, t_patch_size=4,
+               patch_size=4, hidden_size=256, depth=6, num_heads=4, mlp_ratio=4.0, dropout_rate=0.1, time_multiple=4)
+DIT_SMALL = dict(input_channels=3, output_channels=3, grid_rows=8, grid_cols=12, past_len=4, future_len=4, t_patch_size=2,
+                 patch_size=4, hidden_size=128, depth=2, num_heads=4, mlp_ratio=4.0, dropout_rate=0.1, time_multiple=4)
+
+
+def dit_case(ns, name, kw, seed, B, tvals):
+    """DiT4D_V4.forward of the unmodified reference (models/backbones/DiT4D_V4.py:348-375), eval mode, seeded init with
+    the zero-initialised AdaLN / final projections filled by oracle.dit_oracle.randomize_zero_init (same seed)."""
+    from oracle import dit_oracle as dto
+    torch.manual_seed(seed)
+    m = ns.DiT4D_V4(**kw).eval()
+    init_hash = sd_hash(m.state_dict())
+    sd = dto.randomize_zero_init({k: v.detach().clone() for k, v in m.state_dict().items()}, seed)
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(seed + 1)
+    fut = torch.randn(B, kw["input_channels"], kw["grid_rows"], kw["grid_cols"], kw["future_len"], generator=g)
+    from oracle import ddpm_oracle as _dpo
+    past = _dpo.synthetic_macroprops(B, kw["input_channels"], kw["grid_rows"], kw["grid_cols"], kw["past_len"], seed + 2)
+    t = torch.tensor(tvals)
+    with torch.no_grad():
+        eps = m(fut, t, past)
+    save(name, {"kw": kw, "seed": seed, "B": B, "t": tvals, "init_sha256": init_hash, "n_keys": len(sd)},
+         future=fut.numpy(), past=past.numpy(), eps=eps.numpy())
+
+
 def main():
     """python -m oracle.make_golden [case ...]: regenerate every golden, or only the named ones."""
     ns = ref_shim.load()
@@ -180,6 +206,9 @@ def main():
             chain_case(ns, "chain_atc_T1000", ATC, 42, 2, 12, 36, 5, 3, 1000, 0.5, "None", "DDPM")
         if "metrics_small" in only:
             metrics_case(ns, "metrics_small", 8, 12, 36, 3, 7, 4, 1e-6)
+        if "dit" in only:
+            dit_case(ns, "dit_atc_b2", DIT_ATC, 42, 2, [7, 640])
+            dit_case(ns, "dit_small_b3", DIT_SMALL, 11, 3, [0, 999, 31])
         return
     schedule_case(ns)
     unet_case(ns, "unet_atc_b2", ATC, 42, 2, 12, 36, 5, 3, [7, 640])
@@ -194,6 +223,8 @@ def main():
     train_case(ns, "train_atc_b2", kw, 42, 2, 12, 36, 5, 3, 1000, 0.5)
     chain_case(ns, "chain_atc_T1000", ATC, 42, 2, 12, 36, 5, 3, 1000, 0.5, "None", "DDPM")
     metrics_case(ns, "metrics_small", 8, 12, 36, 3, 7, 4, 1e-6)
+    dit_case(ns, "dit_atc_b2", DIT_ATC, 42, 2, [7, 640])
+    dit_case(ns, "dit_small_b3", DIT_SMALL, 11, 3, [0, 999, 31])
 
 
 if __name__ == "__main__":

@@ -137,6 +137,11 @@ def load():
         ns.DDPM = ns.ddpm.DDPM
         ns.DDPM_model = ns.ddpm.DDPM_model
         ns.EasyDict = sys.modules["easydict"].EasyDict
+        try:
+            ns.dit = importlib.import_module("models.backbones.DiT4D_V4")
+            ns.DiT4D_V4 = ns.dit.DiT4D_V4
+        except Exception as e:  # noqa: BLE001 - optional: only the f2 pins need it
+            ns.dit, ns.DiT4D_V4, ns.dit_error = None, None, repr(e)
         # the callers either side of the path: CPU metrics tail, windowed dataset
         try:
             ns.metrics = importlib.import_module("utils.metrics.metricsGenerator")

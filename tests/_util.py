@@ -54,3 +54,17 @@ def chain_noise(meta):
 
 def rel_l2(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def build_dit(meta):
+    """Product DiT4D_V4 initialised under the golden's seed (SHA-256 of the seeded init == the reference's), then the
+    zero-initialised AdaLN / final projections filled exactly as oracle/make_golden.py::dit_case did."""
+    from crowdmod_ddpm_4d_b200.models.backbones.DiT4D_V4 import DiT4D_V4
+    from oracle import dit_oracle as dto
+    torch.manual_seed(meta["seed"])
+    net = DiT4D_V4(**meta["kw"])
+    assert len(net.state_dict()) == meta["n_keys"]
+    assert sd_hash(net.state_dict()) == meta["init_sha256"], "seeded DiT init differs from the reference's"
+    sd = dto.randomize_zero_init({k: v.detach().clone() for k, v in net.state_dict().items()}, meta["seed"])
+    net.load_state_dict(sd)
+    return net, sd

@@ -93,3 +93,21 @@ def test_metrics_oracle_vs_reference_golden():
     np.testing.assert_array_equal(re, g["RE_DENSITY"])
     np.testing.assert_array_equal(mre, g["MIN_RE_DENSITY"])
     np.testing.assert_array_equal(mo.compute_tv_metric(pred, gt), g["TV_OVER_TIME"])
+
+
+@pytest.mark.parametrize("name", ["dit_atc_b2", "dit_small_b3"])
+def test_dit_oracle_and_mirror_module_vs_reference_golden(name):
+    """oracle/dit_oracle.py reproduces the reference DiT4D_V4 forward (DiT4D_V4.py:348-375) and the product's mirror
+    module has the reference's state_dict keys and seeded initialisation bit for bit."""
+    from oracle import dit_oracle as dto
+    from tests._util import build_dit, load_golden
+    meta, a = load_golden(name)
+    net, sd = build_dit(meta)
+    kw = meta["kw"]
+    with torch.no_grad():
+        eps = dto.dit_forward(sd, a["future"], torch.tensor(meta["t"]), a["past"], patch=kw["patch_size"],
+                              t_patch=kw["t_patch_size"], heads=kw["num_heads"], depth=kw["depth"])
+    err = ((eps - a["eps"]).norm() / a["eps"].norm()).item()
+    assert err <= 2e-6, err
+    with pytest.raises(RuntimeError):
+        net(a["future"], torch.tensor(meta["t"]), a["past"])          # CPU tensors: no CPU path
