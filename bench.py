@@ -410,9 +410,79 @@ def extras_bench(rank, world, dev):
                      "scaling": "weak", "samples": 64 * world, "chain_ms": ms,
                      "sequences_per_s": 64 * world / (ms * 1e-3), "denoiser_step_ms": ms / T_STEPS,
                      "algorithmic_tflops": fl * 64 * world * T_STEPS / (ms * 1e-3) / 1e12, "finite": ok}
+    # (4) the second backbone (--arch DDPM-DiT, config/ATC.yml MODEL.DDPM.DIT): 1000-step chain, 64 samples per GPU
+    out["dit_atc"] = dit_bench(rank, world, dev, tsteps, coef)
     if rank == 0:
         out.update(feed_and_metrics_bench(dev))
     return out
+
+
+def dit_bench(rank, world, dev, tsteps, coef):
+    """DiT4D_V4 (reference models/backbones/DiT4D_V4.py, config/ATC.yml: patch 4, t_patch 4, hidden 256, depth 6, 4 heads)
+    through cm_dit_sample: weak scaling, no collective.  The CPU baseline is the oracle port of the same forward."""
+    import torch.distributed as dist
+    from crowdmod_ddpm_4d_b200.models.backbones.DiT4D_V4 import DiT4D_V4
+    w = WORKLOADS["atc"]
+    kw = dict(input_channels=3, output_channels=3, grid_rows=w["rows"], grid_cols=w["cols"], past_len=w["past"],
+              future_len=w["fut"], t_patch_size=4, patch_size=4, hidden_size=256, depth=6, num_heads=4, mlp_ratio=4.0,
+              dropout_rate=0.1, time_multiple=4)
+    torch.manual_seed(42)
+    net = DiT4D_V4(**kw).to(dev).eval()
+    n = 64
+    past = synthetic_macroprops(n, 3, w["rows"], w["cols"], w["past"], 77 + rank, dev)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    shape = (n, 3, w["rows"], w["cols"], w["fut"])
+    x = torch.randn(shape, device=dev, generator=gen)
+    net.sample_chain(past, x, tsteps[:8], coef[:8], mode=0, seed=1, sample_offset=rank * n)      # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x = torch.randn(shape, device=dev, generator=gen)
+    t0 = time.perf_counter()
+    a.record()
+    net.sample_chain(past, x, tsteps, coef, mode=0, seed=3, sample_offset=rank * n)
+    b.record()
+    t_issue = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches, fl = net.native_stats()
+    # one forward alone (device events) for the denoiser-step figure without the host loop
+    t = torch.full((n,), 500, device=dev, dtype=torch.long)
+    with torch.no_grad():
+        net(x, t, past)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(20):
+            net(x, t, past)
+        b.record()
+        torch.cuda.synchronize()
+    fwd_ms = a.elapsed_time(b) / 20
+    res = {"workload": "config/ATC.yml MODEL.DDPM.DIT (DiT4D_V4: patch 4, t_patch 4, hidden 256, depth 6, 4 heads): 1000-step "
+                       "chain, 64 samples per GPU", "scaling": "weak", "samples": n * world, "chain_ms": ms.item(),
+           "sequences_per_s": n * world / (ms.item() * 1e-3), "denoiser_step_ms": ms.item() / T_STEPS,
+           "forward_ms_device": fwd_ms, "host_issue_ms_per_step": t_issue * 1e3 / T_STEPS,
+           "launches_per_step": launches // T_STEPS, "algorithmic_gflop_per_sample_step": fl / 1e9,
+           "algorithmic_tflops": fl * n * world * T_STEPS / (ms.item() * 1e-3) / 1e12, "finite": bool(torch.isfinite(x).all().item())}
+    if rank == 0:
+        from oracle import dit_oracle as dto
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        xc, pc, tc = x[:8].cpu(), past[:8].cpu(), t[:8].cpu()
+        torch.set_num_threads(os.cpu_count())
+        with torch.no_grad():
+            dto.dit_forward(sd, xc, tc, pc, patch=4, t_patch=4, heads=4, depth=6)
+            t1 = time.perf_counter()
+            for _ in range(4):
+                dto.dit_forward(sd, xc, tc, pc, patch=4, t_patch=4, heads=4, depth=6)
+            cpu_step = (time.perf_counter() - t1) / 4
+        res["cpu_baseline"] = {"value": 8 / (cpu_step * T_STEPS), "unit": "sequences/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "4 denoiser evaluations at batch 8 (of 64) on the host cores (oracle/ restatement of "
+                                         "DiT4D_V4.forward), extrapolated to 1000 steps"}
+    del net
+    torch.cuda.empty_cache()
+    return res
 
 
 def feed_and_metrics_bench(dev):

@@ -144,7 +144,7 @@ size_t conv_packed_k(int mode, int cin, int cin_extra) {
 }
 
 int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
-                 const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms) {
+                 const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms, bool allow_splitk) {
   if (int rc = load_driver_syms()) return rc;
   CM_CHECK(mode >= 0 && mode <= 4, "bad conv mode %d", mode);
   CM_CHECK(cin % 32 == 0 && cin_extra % 32 == 0, "channels must be multiples of 32 (cin=%d extra=%d)",
@@ -183,7 +183,7 @@ int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H
     // widest N tile (A and the weights are fetched once per tile) and split K across a cluster.
     const long nkb_all = (long)(k * k * k) * (cin / bk) + cin_extra / bk;
     static const bool no_split = getenv("CM_NO_SPLITK") != nullptr;
-    if (!no_split && p.nphase == 1 && m_tiles * (cout / bn) < 100) {
+    if (!no_split && allow_splitk && p.nphase == 1 && m_tiles * (cout / bn) < 100) {
       long sk = 2 * 148 / (m_tiles * (cout / bn));   // two CTAs per SM (see the stage budget below)
       if (sk > 8) sk = 8;
       while (sk > 1 && nkb_all / sk < 4) --sk;

@@ -486,7 +486,7 @@ struct ConvLaunch {
 // 2 = nearest-x2 + k3 p1 decomposed into 8 phase convs with 2x2x2 combined taps (UpSample),
 // 3 = 1x1x1.  Extra source: 1x1x1 over the OUTPUT grid with cin_extra channels.
 int conv_prepare(ConvLaunch* L, int mode, const __half* act, int B, int D, int H, int W, int cin,
-                 const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms);
+                 const __half* extra, int cin_extra, const __half* wpacked, int cout, int terms, bool allow_splitk = true);
 int conv_enqueue(const ConvLaunch& L, cudaStream_t st);
 size_t conv_packed_k(int mode, int cin, int cin_extra);   // K elements of the packed weight rows
 

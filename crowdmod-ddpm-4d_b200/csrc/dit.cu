@@ -8,6 +8,7 @@
 // bandwidth kernels between them: LayerNorm + AdaLN modulate -> fp16 operand, gated residual add, exact GELU, the
 // temporal cross-attention (future slots query the T_p <= 8 slots of their spatial patch), patch gather / scatter, and
 // the DDPM / DDIM update fused into the un-patch kernel.  Sampling (eval) only: training this backbone still raises.
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -219,10 +220,12 @@ struct UnpatchParams {
   float* x;
   const float* coef;     // device [nsteps][8]
   int step;
+  const int* step_dev;   // device step index (graph replay): overrides `step` when set
   int mode;
   const float* noise;
   unsigned long long seed;
   long long sample_offset;
+  const unsigned long long* chain_dev;   // device {seed, sample_offset}: overrides the two fields above when set
   float* history;
 };
 // un-patch + slice to the future frames (DiT4D_V4.py:80-102) + DDPM.step / DDIM update / Sparsity guidance / Philox
@@ -246,18 +249,21 @@ __global__ void dit_unpatch_step_kernel(UnpatchParams p) {
     if (p.eps_out)
       for (int c = 0; c < p.C; ++c) p.eps_out[e0 + c * plane] = eps[c];
     if (!p.x) continue;
-    const float* cf = p.coef + (size_t)p.step * 8;
+    const int step = p.step_dev ? *p.step_dev : p.step;
+    const unsigned long long seed = p.chain_dev ? p.chain_dev[0] : p.seed;
+    const long long soff = p.chain_dev ? static_cast<long long>(p.chain_dev[1]) : p.sample_offset;
+    const float* cf = p.coef + (size_t)step * 8;
     const size_t nelem = (size_t)p.B * p.C * plane;
     float z[4] = {0.f, 0.f, 0.f, 0.f};
     const float zc = (p.mode == 0) ? cf[2] : cf[4];
     if (zc != 0.f) {
       if (p.noise) {
-        for (int c = 0; c < p.C; ++c) z[c] = p.noise[(size_t)p.step * nelem + e0 + c * plane];
+        for (int c = 0; c < p.C; ++c) z[c] = p.noise[(size_t)step * nelem + e0 + c * plane];
       } else {
-        const unsigned long long gp = ((unsigned long long)(p.sample_offset + b)) * (unsigned long long)plane +
+        const unsigned long long gp = ((unsigned long long)(soff + b)) * (unsigned long long)plane +
                                       ((size_t)y * p.W + xw) * p.F + f;
-        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)p.step, 0u),
-                                        make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)step, 0u),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
         const float2 n0 = box_muller(rnd.x, rnd.y), n1 = box_muller(rnd.z, rnd.w);
         z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
       }
@@ -277,7 +283,7 @@ __global__ void dit_unpatch_step_kernel(UnpatchParams p) {
         xn -= cf[5] * sg;
       }
       p.x[e] = xn;
-      if (p.history) p.history[(size_t)(p.step + 1) * nelem + e] = xn;
+      if (p.history) p.history[(size_t)(step + 1) * nelem + e] = xn;
     }
   }
 }
@@ -286,6 +292,19 @@ __global__ void dit_fill_t_kernel(long long* t, int B, int value) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) t[i] = value;
 }
+__global__ void dit_fill_t_range_kernel(long long* t, int n, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = first + i;
+}
+// sampling steps are batch-uniform: the step's (shift, scale, gate) vectors of every block are ONE row of the table
+// precomputed per weight load (the analogue of the UNet plan's time-embedding table); copied to mods row 0
+__global__ void dit_select_mods_kernel(float* __restrict__ mods, const float* __restrict__ table, const int* __restrict__ tsteps,
+                                       const int* __restrict__ step_dev, int J) {
+  const float* row = table + (size_t)tsteps[*step_dev] * J;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J / 4; i += gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(mods)[i] = reinterpret_cast<const float4*>(row)[i];
+}
+__global__ void dit_advance_kernel(int* step_dev) { ++*step_dev; }
 
 int grid_for(size_t work_items, int block = 256) {
   size_t b = (work_items + block - 1) / block;
@@ -335,6 +354,14 @@ struct cm_dit {
   float *h32 = nullptr, *h2_32 = nullptr, *c32 = nullptr, *mods = nullptr, *x32 = nullptr, *qkv32 = nullptr, *tmp32 = nullptr,
         *mlp32 = nullptr, *out32 = nullptr, *chain_x = nullptr, *chain_past = nullptr, *d_coef = nullptr;
   int coef_cap = 0;
+  float* mods_table = nullptr;         // [table_steps][Jtot]: AdaLN vectors of every timestep (sampling, batch-uniform t)
+  bool table_ready = false;
+  int* d_step = nullptr;
+  int* d_tsteps = nullptr;
+  unsigned long long* d_chain = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  cm_chain_args graph_key{};
+  int64_t graph_launches_per_step = 0;
   int64_t last_launches = 0;
   double flops_per_sample = 0.0;
 
@@ -508,17 +535,22 @@ int pack_all(cm_dit* u, cudaStream_t st) {
   }
   if (int e = pack_linear(u, u->final_lin, st)) return e;
   u->packed = true;
+  u->table_ready = false;
   return 0;
 }
 
 int reserve(cm_dit* u, int batch) {
   if (batch <= u->reserved_batch) return 0;
+  if (u->graph_exec) {
+    cudaGraphExecDestroy(u->graph_exec);
+    u->graph_exec = nullptr;
+  }
   if (u->arena) CM_CUDA(cudaFree(u->arena));
   u->arena = nullptr;
   u->prepared_batch = 0;
   const cm_dit_config& c = u->cfg;
   const size_t R = (size_t)batch * u->tokens, Rq = (size_t)batch * u->nq * u->Ns;
-  const size_t Bp = (size_t)(batch + 127) / 128 * 128;      // the time-path GEMMs read whole 128-row tiles (TMA zero-fills)
+  const size_t Bp = (size_t)(batch + 127) / 128 * 128;      // the time-path buffers hold whole 128-row tiles (>= one table chunk)
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   const size_t o_t = take(Bp * 8), o_e16 = take(Bp * u->D * 2), o_h16 = take(Bp * u->E * 2);
@@ -556,9 +588,13 @@ int reserve(cm_dit* u, int batch) {
   return 0;
 }
 
+#define DIT_LAUNCH_CHECK() CM_CUDA(cudaGetLastError())
+
 // GEMM out32[rows][cout] = act16[rows][cin] . W^T + bias  (conv_umma 1x1x1 mode; rows = nb * d * h * w)
 int prep_gemm(cm_dit* u, DitLinear& l, const __half* act, int nb, int d, int h, int w, float* out32) {
-  if (int rc = conv_prepare(&l.launch, 3, act, nb, d, h, w, l.cin, nullptr, 0, u->wpack + l.pack_off, l.cout, 2)) return rc;
+  // K <= 1024 here: narrower N tiles fill the SMs without the cluster split-K reduction (CM_DIT_SPLITK=1 to compare)
+  static const bool splitk = getenv("CM_DIT_SPLITK") != nullptr;
+  if (int rc = conv_prepare(&l.launch, 3, act, nb, d, h, w, l.cin, nullptr, 0, u->wpack + l.pack_off, l.cout, 2, splitk)) return rc;
   l.launch.p.bias = l.b >= 0 ? u->params[l.b].ptr : l.b_dev;
   l.launch.p.out32 = out32;
   l.launch.p.out16 = nullptr;
@@ -582,31 +618,46 @@ int prepare(cm_dit* u, int batch) {
     if (int e = prep_gemm(u, b.fc2, u->g16, batch, 1, Tp, Ns, u->tmp32)) return e;
   }
   if (int e = prep_gemm(u, u->final_lin, u->xm16, batch, 1, Tp, Ns, u->out32)) return e;
+  if (u->graph_exec) {            // the captured step bakes the launches of the previous batch
+    cudaGraphExecDestroy(u->graph_exec);
+    u->graph_exec = nullptr;
+  }
   u->prepared_batch = batch;
   return 0;
 }
 
-#define DIT_LAUNCH_CHECK() CM_CUDA(cudaGetLastError())
-
-// one denoiser evaluation: t_dev / future / past -> out32 (FinalLayer output), then un-patch (+ optional update)
-int run_forward(cm_dit* u, int B, const float* future, const float* past, UnpatchParams up, cudaStream_t st, int64_t* launches) {
+// diffusion-time conditioning of `rows` timesteps (t_dev): c = SiLU(time_proj(time_blocks(t))), then every block's AdaLN
+// vectors from SiLU(c) in ONE GEMM (DiT4D_V4.py:363, :134-137, :222): 8 launches.  The four GEMM launches must have been
+// prepared for `rows` rows with their outputs where the caller wants them.
+int run_conditioning(cm_dit* u, int rows, DitLinear& t1, DitLinear& t2, DitLinear& tproj, DitLinear& adaln, cudaStream_t st) {
   const cm_dit_config& c = u->cfg;
-  const int D = u->D, E = u->E, Tp = u->Tp, Ns = u->Ns, R = B * u->tokens, Rq = B * u->nq * Ns;
+  const int D = u->D, E = u->E;
+  dit_gather_emb_kernel<<<rows, 128, 0, st>>>(u->params[u->p_table].ptr, u->t_dev, D, c.table_steps, u->e16);
+  DIT_LAUNCH_CHECK();
+  if (int e = conv_enqueue(t1.launch, st)) return e;
+  dit_act16_kernel<<<grid_for((size_t)rows * E / 4), 256, 0, st>>>(u->h32, u->h16, (size_t)rows * E / 4, 1);
+  DIT_LAUNCH_CHECK();
+  if (int e = conv_enqueue(t2.launch, st)) return e;
+  dit_act16_kernel<<<grid_for((size_t)rows * E / 4), 256, 0, st>>>(u->h2_32, u->h16, (size_t)rows * E / 4, 0);
+  DIT_LAUNCH_CHECK();
+  if (int e = conv_enqueue(tproj.launch, st)) return e;
+  dit_act16_kernel<<<grid_for((size_t)rows * D / 4), 256, 0, st>>>(u->c32, u->e16, (size_t)rows * D / 4, 2);
+  DIT_LAUNCH_CHECK();
+  return conv_enqueue(adaln.launch, st);
+}
+
+// one denoiser evaluation: (t_dev |mods row 0) / future / past -> out32 (FinalLayer output), then un-patch (+ optional
+// update).  ld_mods = Jtot: per-sample AdaLN vectors computed here from t_dev; ld_mods = 0: mods row 0 already holds the
+// step's vectors for the whole batch (sampling: batch-uniform timestep, table row selected by the caller).
+int run_forward(cm_dit* u, int B, const float* future, const float* past, UnpatchParams up, int ld_mods, cudaStream_t st,
+                int64_t* launches) {
+  const cm_dit_config& c = u->cfg;
+  const int D = u->D, Tp = u->Tp, Ns = u->Ns, R = B * u->tokens, Rq = B * u->nq * Ns;
   int64_t n = 0;
-  // ---- diffusion-time conditioning: c = SiLU(time_proj(time_blocks(t))); AdaLN input SiLU(c) (DiT4D_V4.py:363, :134-137)
-  dit_gather_emb_kernel<<<B, 128, 0, st>>>(u->params[u->p_table].ptr, u->t_dev, D, c.table_steps, u->e16);
-  DIT_LAUNCH_CHECK();
-  if (int e = conv_enqueue(u->t1.launch, st)) return e;
-  dit_act16_kernel<<<grid_for((size_t)B * E / 4), 256, 0, st>>>(u->h32, u->h16, (size_t)B * E / 4, 1);
-  DIT_LAUNCH_CHECK();
-  if (int e = conv_enqueue(u->t2.launch, st)) return e;
-  dit_act16_kernel<<<grid_for((size_t)B * E / 4), 256, 0, st>>>(u->h2_32, u->h16, (size_t)B * E / 4, 0);
-  DIT_LAUNCH_CHECK();
-  if (int e = conv_enqueue(u->tproj.launch, st)) return e;
-  dit_act16_kernel<<<grid_for((size_t)B * D / 4), 256, 0, st>>>(u->c32, u->e16, (size_t)B * D / 4, 2);
-  DIT_LAUNCH_CHECK();
-  if (int e = conv_enqueue(u->adaln.launch, st)) return e;      // mods [B][Jtot]: every block's 9 (and the final 2) vectors
-  n += 8;
+  if (ld_mods != 0) {
+    if (int e = run_conditioning(u, B, u->t1, u->t2, u->tproj, u->adaln, st)) return e;
+    n += 8;
+  }
   // ---- patchify + positional embeddings
   PatchGeom g{B, c.in_channels, c.rows, c.cols, c.past_len, c.future_len, c.patch, c.t_patch, u->hp, u->wp, Tp, u->Kpad};
   dit_patchify_kernel<<<grid_for((size_t)R * u->Kpad), 256, 0, st>>>(future, past, g, u->a16);
@@ -621,16 +672,16 @@ int run_forward(cm_dit* u, int B, const float* future, const float* past, Unpatc
     cm_dit::Block& b = u->blocks[i];
     const int mo = i * 9 * D;     // chunk(9): shift1, scale1, gate1, shift2, scale2, gate2, shift3, scale3, gate3
     // 1. spatial self-attention (every temporal slot is its own sequence of Ns tokens)
-    dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, u->Jtot, mo, mo + D, u->tokens, R, D, u->xm16);
+    dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, ld_mods, mo, mo + D, u->tokens, R, D, u->xm16);
     DIT_LAUNCH_CHECK();
     if (int e = conv_enqueue(b.s_in.launch, st)) return e;
     if (int e = attn_core_enqueue(u->qkv32, u->ctx16, B * Tp, Ns, D, c.heads, st, 1)) return e;
     if (int e = conv_enqueue(b.s_out.launch, st)) return e;
-    dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, u->Jtot, mo + 2 * D, R, u->tokens, u->tokens,
+    dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 2 * D, R, u->tokens, u->tokens,
                                                                      0, D);
     DIT_LAUNCH_CHECK();
     // 2. temporal cross-attention (future slots of every spatial patch query all of its slots)
-    dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, u->Jtot, mo + 3 * D, mo + 4 * D, u->tokens, R, D, u->xm16);
+    dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, ld_mods, mo + 3 * D, mo + 4 * D, u->tokens, R, D, u->xm16);
     DIT_LAUNCH_CHECK();
     if (int e = conv_enqueue(b.t_in.launch, st)) return e;
     {
@@ -639,24 +690,24 @@ int run_forward(cm_dit* u, int B, const float* future, const float* past, Unpatc
       DIT_LAUNCH_CHECK();
     }
     if (int e = conv_enqueue(b.t_out.launch, st)) return e;
-    dit_gate_add_kernel<<<grid_for((size_t)Rq * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, u->Jtot, mo + 5 * D, Rq, u->nq * Ns,
+    dit_gate_add_kernel<<<grid_for((size_t)Rq * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 5 * D, Rq, u->nq * Ns,
                                                                       u->tokens, u->qs * Ns, D);
     DIT_LAUNCH_CHECK();
     // 3. MLP
-    dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, u->Jtot, mo + 6 * D, mo + 7 * D, u->tokens, R, D, u->xm16);
+    dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, ld_mods, mo + 6 * D, mo + 7 * D, u->tokens, R, D, u->xm16);
     DIT_LAUNCH_CHECK();
     if (int e = conv_enqueue(b.fc1.launch, st)) return e;
     dit_act16_kernel<<<grid_for((size_t)R * u->Dm / 4), 256, 0, st>>>(u->mlp32, u->g16, (size_t)R * u->Dm / 4, 3);
     DIT_LAUNCH_CHECK();
     if (int e = conv_enqueue(b.fc2.launch, st)) return e;
-    dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, u->Jtot, mo + 8 * D, R, u->tokens, u->tokens,
+    dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 8 * D, R, u->tokens, u->tokens,
                                                                      0, D);
     DIT_LAUNCH_CHECK();
     n += 15;
   }
   // ---- final layer (chunk(2): shift, scale) + un-patch (+ reverse-step update)
   const int mo = c.depth * 9 * D;
-  dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, u->Jtot, mo, mo + D, u->tokens, R, D, u->xm16);
+  dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, ld_mods, mo, mo + D, u->tokens, R, D, u->xm16);
   DIT_LAUNCH_CHECK();
   if (int e = conv_enqueue(u->final_lin.launch, st)) return e;
   up.out = u->out32;
@@ -667,6 +718,28 @@ int run_forward(cm_dit* u, int B, const float* future, const float* past, Unpatc
   DIT_LAUNCH_CHECK();
   n += 3;
   if (launches) *launches += n;
+  return 0;
+}
+
+// AdaLN vectors of EVERY timestep, once per weight load: the conditioning path in chunks of 128 timesteps with the last
+// GEMM writing straight into the table.  Needs the arena of a batch >= 128 rows for the time-path buffers (they are
+// sized for max(batch, 128) rows).
+int build_mods_table(cm_dit* u, cudaStream_t st) {
+  if (u->table_ready) return 0;
+  const cm_dit_config& c = u->cfg;
+  if (!u->mods_table) CM_CUDA(cudaMalloc(&u->mods_table, (size_t)c.table_steps * u->Jtot * sizeof(float)));
+  for (int t0 = 0; t0 < c.table_steps; t0 += 128) {
+    const int rows = c.table_steps - t0 < 128 ? c.table_steps - t0 : 128;
+    DitLinear t1 = u->t1, t2 = u->t2, tp = u->tproj, ad = u->adaln;
+    if (int e = prep_gemm(u, t1, u->e16, rows, 1, 1, 1, u->h32)) return e;
+    if (int e = prep_gemm(u, t2, u->h16, rows, 1, 1, 1, u->h2_32)) return e;
+    if (int e = prep_gemm(u, tp, u->h16, rows, 1, 1, 1, u->c32)) return e;
+    if (int e = prep_gemm(u, ad, u->e16, rows, 1, 1, 1, u->mods_table + (size_t)t0 * u->Jtot)) return e;
+    dit_fill_t_range_kernel<<<1, 128, 0, st>>>(u->t_dev, rows, t0);
+    DIT_LAUNCH_CHECK();
+    if (int e = run_conditioning(u, rows, t1, t2, tp, ad, st)) return e;
+  }
+  u->table_ready = true;
   return 0;
 }
 
@@ -702,6 +775,11 @@ int cm_dit_destroy(cm_dit* u) {
   if (u->adaln_bbuf) cudaFree(u->adaln_bbuf);
   if (u->patch_wbuf) cudaFree(u->patch_wbuf);
   if (u->d_coef) cudaFree(u->d_coef);
+  if (u->d_tsteps) cudaFree(u->d_tsteps);
+  if (u->d_step) cudaFree(u->d_step);
+  if (u->d_chain) cudaFree(u->d_chain);
+  if (u->mods_table) cudaFree(u->mods_table);
+  if (u->graph_exec) cudaGraphExecDestroy(u->graph_exec);
   delete u;
   return 0;
 }
@@ -748,7 +826,7 @@ int cm_dit_forward(cm_dit* u, const float* future, const int64_t* t, const float
   UnpatchParams up{};
   up.eps_out = eps_out;
   u->last_launches = 0;
-  return run_forward(u, batch, future, past, up, st, &u->last_launches);
+  return run_forward(u, batch, future, past, up, u->Jtot, st, &u->last_launches);
 }
 
 int cm_dit_sample(cm_dit* u, const cm_chain_args* a, void* stream) {
@@ -757,31 +835,87 @@ int cm_dit_sample(cm_dit* u, const cm_chain_args* a, void* stream) {
   CM_CHECK(a->mode == 0 || a->mode == 1, "mode must be 0 (DDPM) or 1 (DDIM)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = ensure_ready(u, a->n, st)) return e;
+  if (int e = build_mods_table(u, st)) return e;
   const cm_dit_config& c = u->cfg;
+  for (int i = 0; i < a->nsteps; ++i)
+    CM_CHECK(a->tsteps[i] >= 0 && a->tsteps[i] < c.table_steps, "timestep %d outside the table", a->tsteps[i]);
   if (a->nsteps > u->coef_cap) {
     if (u->d_coef) CM_CUDA(cudaFree(u->d_coef));
+    if (u->d_tsteps) CM_CUDA(cudaFree(u->d_tsteps));
     CM_CUDA(cudaMalloc(&u->d_coef, (size_t)a->nsteps * 8 * sizeof(float)));
+    CM_CUDA(cudaMalloc(&u->d_tsteps, (size_t)a->nsteps * sizeof(int)));
     u->coef_cap = a->nsteps;
+    if (u->graph_exec) {
+      cudaGraphExecDestroy(u->graph_exec);
+      u->graph_exec = nullptr;
+    }
   }
+  if (!u->d_step) CM_CUDA(cudaMalloc(&u->d_step, sizeof(int)));
+  if (!u->d_chain) CM_CUDA(cudaMalloc(&u->d_chain, 2 * sizeof(unsigned long long)));
+  // step index, timesteps, coefficients, Philox seed / shard offset, x and past all travel through buffers the handle
+  // owns: one captured step serves every chain of this (n, mode, noise, history)
+  const unsigned long long chain_host[2] = {a->seed, static_cast<unsigned long long>(a->sample_offset)};
   CM_CUDA(cudaMemcpyAsync(u->d_coef, a->coef, (size_t)a->nsteps * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CM_CUDA(cudaMemcpyAsync(u->d_tsteps, a->tsteps, (size_t)a->nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+  CM_CUDA(cudaMemcpyAsync(u->d_chain, chain_host, sizeof(chain_host), cudaMemcpyHostToDevice, st));
+  CM_CUDA(cudaMemsetAsync(u->d_step, 0, sizeof(int), st));
   const size_t xel = (size_t)a->n * c.out_channels * c.rows * c.cols * c.future_len;
+  const size_t pel = (size_t)a->n * c.in_channels * c.rows * c.cols * c.past_len;
   CM_CUDA(cudaMemcpyAsync(u->chain_x, a->x, xel * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  u->last_launches = 0;
-  for (int i = 0; i < a->nsteps; ++i) {
-    dit_fill_t_kernel<<<(a->n + 127) / 128, 128, 0, st>>>(u->t_dev, a->n, a->tsteps[i]);
+  CM_CUDA(cudaMemcpyAsync(u->chain_past, a->past, pel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  UnpatchParams up{};
+  up.x = u->chain_x;
+  up.coef = u->d_coef;
+  up.step_dev = u->d_step;
+  up.mode = a->mode;
+  up.noise = a->noise;
+  up.chain_dev = u->d_chain;
+  up.history = a->history;
+  auto one_step = [&](cudaStream_t s2, int64_t* launches) -> int {
+    dit_select_mods_kernel<<<8, 256, 0, s2>>>(u->mods, u->mods_table, u->d_tsteps, u->d_step, u->Jtot);
     CM_CUDA(cudaGetLastError());
-    UnpatchParams up{};
-    up.x = u->chain_x;
-    up.coef = u->d_coef;
-    up.step = i;
-    up.mode = a->mode;
-    up.noise = a->noise;
-    up.seed = a->seed;
-    up.sample_offset = a->sample_offset;
-    up.history = a->history;
     // the denoiser reads the CURRENT x (the chain's staging copy) as its `future` input
-    if (int e = run_forward(u, a->n, u->chain_x, a->past, up, st, &u->last_launches)) return e;
-    ++u->last_launches;
+    if (int e = run_forward(u, a->n, u->chain_x, u->chain_past, up, 0, s2, launches)) return e;
+    dit_advance_kernel<<<1, 1, 0, s2>>>(u->d_step);
+    CM_CUDA(cudaGetLastError());
+    if (launches) *launches += 2;
+    return 0;
+  };
+  u->last_launches = 0;
+  if (!a->use_graph) {
+    for (int i = 0; i < a->nsteps; ++i)
+      if (int e = one_step(st, &u->last_launches)) return e;
+  } else {
+    const cm_chain_args& k = u->graph_key;
+    const bool reuse = u->graph_exec && k.n == a->n && k.mode == a->mode && k.noise == a->noise && k.history == a->history;
+    if (!reuse) {
+      if (u->graph_exec) {
+        cudaGraphExecDestroy(u->graph_exec);
+        u->graph_exec = nullptr;
+      }
+      cudaStream_t cs;
+      CM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t g = nullptr;
+      int64_t per_step = 0;
+      cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      int e = 0;
+      if (ce == cudaSuccess) {
+        e = one_step(cs, &per_step);
+        ce = cudaStreamEndCapture(cs, &g);
+      }
+      cudaStreamDestroy(cs);
+      if (e || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        if (e) return e;
+        CM_CUDA(ce);
+      }
+      CM_CUDA(cudaGraphInstantiate(&u->graph_exec, g, 0));
+      cudaGraphDestroy(g);
+      u->graph_key = *a;
+      u->graph_launches_per_step = per_step;
+    }
+    for (int i = 0; i < a->nsteps; ++i) CM_CUDA(cudaGraphLaunch(u->graph_exec, st));
+    u->last_launches = u->graph_launches_per_step * a->nsteps;
   }
   CM_CUDA(cudaMemcpyAsync(a->x, u->chain_x, xel * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

@@ -270,7 +270,7 @@ class DiT4D_V4(nn.Module):
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         a.sample_offset = int(sample_offset)
         a.history = history.data_ptr() if history is not None else None
-        a.use_graph = 0
+        a.use_graph = 0 if use_graph in (False, 0, "eager") else 1     # one captured step, replayed nsteps times
         n.check(n.lib().cm_dit_sample(plan.handle, C.byref(a), n.current_stream()))
         return x
 

@@ -229,8 +229,9 @@ CM_API int cm_dit_pack(cm_dit* d, void* stream);                                
 /* DiT4D_V4.forward(future, t, past) :348-375 (eval): future fp32 [B,C,H,W,F], t int64 [B], past fp32 [B,C,H,W,P], all device */
 CM_API int cm_dit_forward(cm_dit* d, const float* future, const int64_t* t, const float* past, float* eps_out, int batch,
                    void* stream);
-/* _generate_ddpm / _generate_ddim with this backbone (ddpm.py:206-282): eager launches, the update fused into the
- * un-patch kernel; use_graph is ignored */
+/* _generate_ddpm / _generate_ddim with this backbone (ddpm.py:206-282): the update is fused into the un-patch kernel;
+ * the AdaLN vectors of all timesteps come from a table built once per weight load; use_graph = 0 eager launches,
+ * != 0 one captured step replayed nsteps times (seed / offset / x / past go through buffers the handle owns) */
 CM_API int cm_dit_sample(cm_dit* d, const cm_chain_args* args, void* stream);
 CM_API double cm_dit_flops_per_sample(const cm_dit* d);
 CM_API int64_t cm_dit_last_launches(const cm_dit* d);

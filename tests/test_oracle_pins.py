@@ -113,3 +113,39 @@ def test_dataset_oracle_pinned_to_live_reference():
         assert len(ours) == len(ref_batches)
         for (p0, f0), (p1, f1) in zip(ref_batches, ours):
             assert torch.equal(p0, p1) and torch.equal(f0, f1)
+
+
+@pytest.mark.parametrize("kw,geom", [
+    (dict(input_channels=3, output_channels=3, grid_rows=12, grid_cols=36, past_len=5, future_len=3, t_patch_size=4,
+          patch_size=4, hidden_size=256, depth=6, num_heads=4, mlp_ratio=4.0, dropout_rate=0.1, time_multiple=4), 2),
+    (dict(input_channels=3, output_channels=3, grid_rows=8, grid_cols=12, past_len=5, future_len=3, t_patch_size=2,
+          patch_size=2, hidden_size=128, depth=2, num_heads=4, mlp_ratio=4.0, dropout_rate=0.1, time_multiple=4), 3),
+])
+def test_dit_oracle_and_mirror_pinned_to_live_reference(kw, geom):
+    """oracle/dit_oracle.py == the unmodified DiT4D_V4.forward (eval), and the product's mirror
+    module reproduces the reference's state_dict (keys, shapes, seeded values) bit for bit."""
+    from oracle import dit_oracle as dto
+    from crowdmod_ddpm_4d_b200.models.backbones.DiT4D_V4 import DiT4D_V4
+    ns = ref_shim.load()
+    if ns.DiT4D_V4 is None:
+        pytest.skip("reference DiT4D_V4 not importable: " + getattr(ns, "dit_error", ""))
+    torch.manual_seed(5)
+    ref = ns.DiT4D_V4(**kw).eval()
+    torch.manual_seed(5)
+    mine = DiT4D_V4(**kw)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs) == list(ms)
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    sd = dto.randomize_zero_init({k: v.detach().clone() for k, v in rs.items()}, 1)
+    ref.load_state_dict(sd)
+    B = geom
+    g = torch.Generator().manual_seed(0)
+    fut = torch.randn(B, 3, kw["grid_rows"], kw["grid_cols"], kw["future_len"], generator=g)
+    past = torch.randn(B, 3, kw["grid_rows"], kw["grid_cols"], kw["past_len"], generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    with torch.no_grad():
+        want = ref(fut, t, past)
+        got = dto.dit_forward(sd, fut, t, past, patch=kw["patch_size"], t_patch=kw["t_patch_size"], heads=kw["num_heads"],
+                              depth=kw["depth"])
+    assert ((want - got).norm() / want.norm()).item() <= 2e-6
