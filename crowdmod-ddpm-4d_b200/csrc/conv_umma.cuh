@@ -56,6 +56,12 @@ struct ConvParams {
   int out_ld;
   int out16_ld, out16_lo;   // fp16 copy: row stride in elements (0 -> out_ld); out16_lo > 0: also write the lo half
                             // fp16(v - hi) out16_lo elements further (hi|lo pair operand of the training forward)
+  // optional epilogue extras of the non-split path (the DiT plan, dit.cu): v = act(acc + bias); v *= gate[sample][n];
+  // v += resid; rows of sample b land at output row b*rmap_out + rmap_off + (m - b*pps) (resid is read there too)
+  int act;               // 0 none, 1 exact GELU
+  const float* gate;     // fp32 [samples][gate_ld] or nullptr
+  int gate_ld;
+  int rmap_out, rmap_off;   // rmap_out > 0: remap output rows (samples of pps GEMM rows -> samples of rmap_out rows)
   int scatter;           // 1: rows are low-res pixels, written to (2z+pz, 2p+pp, 2q+pq)
   // split-K (M-starved deep-K layers): gridDim.z = ksplit CTAs of one thread-block cluster share
   // an output tile, each accumulating kb_per_split k-blocks; the partial tiles are reduced in a
@@ -265,10 +271,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         r -= sz * P.oh * P.ow;
         sp = r / P.ow;
         sq = r - sp * P.ow;
+      } else if (P.rmap_out > 0) {
+        orow = static_cast<size_t>(b) * P.rmap_out + P.rmap_off + (m - b * P.pps);
       } else {
         orow = static_cast<size_t>(m);
       }
     }
+    const float* gate_row = (P.gate && valid) ? P.gate + static_cast<size_t>(b) * P.gate_ld + n_tile * BN : nullptr;
     const float* temb_row = nullptr;     // per-sample rows (training): added per element
     if (P.temb && !temb_uniform)
       temb_row = P.temb + static_cast<size_t>(b) * P.temb_bstride + n_tile * BN;
@@ -342,6 +351,17 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         for (int i = 0; i < 16; i += 4) {
           const float4 t4 = *reinterpret_cast<const float4*>(temb_row + c * 16 + i);
           v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
+        }
+      }
+      if (P.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+      }
+      if (gate_row) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gate_row + c * 16 + i);
+          v[i] *= g4.x; v[i + 1] *= g4.y; v[i + 2] *= g4.z; v[i + 3] *= g4.w;
         }
       }
       if (rp) {

@@ -354,6 +354,7 @@ struct cm_dit {
   float *h32 = nullptr, *h2_32 = nullptr, *c32 = nullptr, *mods = nullptr, *x32 = nullptr, *qkv32 = nullptr, *tmp32 = nullptr,
         *mlp32 = nullptr, *out32 = nullptr, *chain_x = nullptr, *chain_past = nullptr, *d_coef = nullptr;
   int coef_cap = 0;
+  bool fused = true;                   // epilogue fusions on (CM_DIT_NOFUSE=1 keeps the separate bandwidth kernels)
   float* mods_table = nullptr;         // [table_steps][Jtot]: AdaLN vectors of every timestep (sampling, batch-uniform t)
   bool table_ready = false;
   int* d_step = nullptr;
@@ -593,7 +594,7 @@ int reserve(cm_dit* u, int batch) {
 // GEMM out32[rows][cout] = act16[rows][cin] . W^T + bias  (conv_umma 1x1x1 mode; rows = nb * d * h * w)
 int prep_gemm(cm_dit* u, DitLinear& l, const __half* act, int nb, int d, int h, int w, float* out32) {
   // K <= 1024 here: narrower N tiles fill the SMs without the cluster split-K reduction (CM_DIT_SPLITK=1 to compare)
-  static const bool splitk = getenv("CM_DIT_SPLITK") != nullptr;
+  static const bool splitk = getenv("CM_DIT_SPLITK") != nullptr && !u->fused;   // the epilogue fusions live in the non-split path
   if (int rc = conv_prepare(&l.launch, 3, act, nb, d, h, w, l.cin, nullptr, 0, u->wpack + l.pack_off, l.cout, 2, splitk)) return rc;
   l.launch.p.bias = l.b >= 0 ? u->params[l.b].ptr : l.b_dev;
   l.launch.p.out32 = out32;
@@ -616,6 +617,20 @@ int prepare(cm_dit* u, int batch) {
     if (int e = prep_gemm(u, b.t_out, u->ctx16, batch, 1, u->nq, Ns, u->tmp32)) return e;
     if (int e = prep_gemm(u, b.fc1, u->xm16, batch, 1, Tp, Ns, u->mlp32)) return e;
     if (int e = prep_gemm(u, b.fc2, u->g16, batch, 1, Tp, Ns, u->tmp32)) return e;
+    if (u->fused) {
+      // epilogue fusions (ConvParams::act / gate / rmap): GELU + fp16 operand out of fc1; the three gated residuals
+      // x += gate * (GEMM + bias) written in place into the token stream (the temporal one into the future slots)
+      b.fc1.launch.p.act = 1;
+      b.fc1.launch.p.out32 = nullptr;
+      b.fc1.launch.p.out16 = u->g16;
+      for (DitLinear* l : {&b.s_out, &b.t_out, &b.fc2}) {
+        l->launch.p.resid = u->x32;
+        l->launch.p.out32 = u->x32;
+        l->launch.p.gate = u->mods;           // + the block's gate offset, set per launch in run_forward
+      }
+      b.t_out.launch.p.rmap_out = u->tokens;
+      b.t_out.launch.p.rmap_off = u->qs * Ns;
+    }
   }
   if (int e = prep_gemm(u, u->final_lin, u->xm16, batch, 1, Tp, Ns, u->out32)) return e;
   if (u->graph_exec) {            // the captured step bakes the launches of the previous batch
@@ -676,10 +691,17 @@ int run_forward(cm_dit* u, int B, const float* future, const float* past, Unpatc
     DIT_LAUNCH_CHECK();
     if (int e = conv_enqueue(b.s_in.launch, st)) return e;
     if (int e = attn_core_enqueue(u->qkv32, u->ctx16, B * Tp, Ns, D, c.heads, st, 1)) return e;
-    if (int e = conv_enqueue(b.s_out.launch, st)) return e;
-    dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 2 * D, R, u->tokens, u->tokens,
-                                                                     0, D);
-    DIT_LAUNCH_CHECK();
+    if (u->fused) {
+      ConvLaunch L = b.s_out.launch;
+      L.p.gate = u->mods + mo + 2 * D;
+      L.p.gate_ld = ld_mods;
+      if (int e = conv_enqueue(L, st)) return e;
+    } else {
+      if (int e = conv_enqueue(b.s_out.launch, st)) return e;
+      dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 2 * D, R, u->tokens,
+                                                                       u->tokens, 0, D);
+      DIT_LAUNCH_CHECK();
+    }
     // 2. temporal cross-attention (future slots of every spatial patch query all of its slots)
     dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, ld_mods, mo + 3 * D, mo + 4 * D, u->tokens, R, D, u->xm16);
     DIT_LAUNCH_CHECK();
@@ -689,21 +711,36 @@ int run_forward(cm_dit* u, int B, const float* future, const float* past, Unpatc
       dit_tattn_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(u->qkv32, u->ctx16, B, Tp, Ns, D, c.heads, u->qs);
       DIT_LAUNCH_CHECK();
     }
-    if (int e = conv_enqueue(b.t_out.launch, st)) return e;
-    dit_gate_add_kernel<<<grid_for((size_t)Rq * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 5 * D, Rq, u->nq * Ns,
-                                                                      u->tokens, u->qs * Ns, D);
-    DIT_LAUNCH_CHECK();
+    if (u->fused) {
+      ConvLaunch L = b.t_out.launch;
+      L.p.gate = u->mods + mo + 5 * D;
+      L.p.gate_ld = ld_mods;
+      if (int e = conv_enqueue(L, st)) return e;
+    } else {
+      if (int e = conv_enqueue(b.t_out.launch, st)) return e;
+      dit_gate_add_kernel<<<grid_for((size_t)Rq * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 5 * D, Rq, u->nq * Ns,
+                                                                        u->tokens, u->qs * Ns, D);
+      DIT_LAUNCH_CHECK();
+    }
     // 3. MLP
     dit_ln_mod_kernel<<<ln_blocks, 256, 0, st>>>(u->x32, u->mods, ld_mods, mo + 6 * D, mo + 7 * D, u->tokens, R, D, u->xm16);
     DIT_LAUNCH_CHECK();
     if (int e = conv_enqueue(b.fc1.launch, st)) return e;
-    dit_act16_kernel<<<grid_for((size_t)R * u->Dm / 4), 256, 0, st>>>(u->mlp32, u->g16, (size_t)R * u->Dm / 4, 3);
-    DIT_LAUNCH_CHECK();
-    if (int e = conv_enqueue(b.fc2.launch, st)) return e;
-    dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 8 * D, R, u->tokens, u->tokens,
-                                                                     0, D);
-    DIT_LAUNCH_CHECK();
-    n += 15;
+    if (u->fused) {
+      ConvLaunch L = b.fc2.launch;
+      L.p.gate = u->mods + mo + 8 * D;
+      L.p.gate_ld = ld_mods;
+      if (int e = conv_enqueue(L, st)) return e;
+      n += 11;
+    } else {
+      dit_act16_kernel<<<grid_for((size_t)R * u->Dm / 4), 256, 0, st>>>(u->mlp32, u->g16, (size_t)R * u->Dm / 4, 3);
+      DIT_LAUNCH_CHECK();
+      if (int e = conv_enqueue(b.fc2.launch, st)) return e;
+      dit_gate_add_kernel<<<grid_for((size_t)R * D / 4), 256, 0, st>>>(u->x32, u->tmp32, u->mods, ld_mods, mo + 8 * D, R, u->tokens,
+                                                                       u->tokens, 0, D);
+      DIT_LAUNCH_CHECK();
+      n += 15;
+    }
   }
   // ---- final layer (chunk(2): shift, scale) + un-patch (+ reverse-step update)
   const int mo = c.depth * 9 * D;
@@ -759,6 +796,7 @@ int cm_dit_create(const cm_dit_config* cfg, cm_dit** out) {
   CM_CHECK(cfg && out, "null argument");
   cm_dit* u = new cm_dit();
   u->cfg = *cfg;
+  u->fused = getenv("CM_DIT_NOFUSE") == nullptr;
   if (int e = build(u)) {
     delete u;
     return e;
