@@ -155,3 +155,46 @@ def test_checkpoint_layout(tmp_path):
     m2 = DDPM_model(cfg, "DDPM-UNet", 3)
     m2.denoiser.load_state_dict(ck["model"])
     assert all(torch.equal(a, b) for a, b in zip(m.denoiser.state_dict().values(), m2.denoiser.state_dict().values()))
+
+
+def test_feed_and_metrics_modules_have_no_cpu_path():
+    """The callers either side of the path refuse CPU tensors instead of falling back."""
+    import types
+    import numpy as np
+    import pytest
+    import torch
+    from crowdmod_ddpm_4d_b200 import _native
+    from crowdmod_ddpm_4d_b200.utils.dataset_gpu import GpuMacropropsDataset
+    from crowdmod_ddpm_4d_b200.utils.metrics_gpu import GpuMetricsGenerator
+    cfg = types.SimpleNamespace(DATASET=types.SimpleNamespace(PAST_LEN=5, FUTURE_LEN=3))
+    seq = np.zeros((2, 3, 4, 4, 12), dtype=np.float32)
+    with pytest.raises(_native.NativeError):
+        GpuMacropropsDataset(seq, cfg, 3, stride=2, device="cpu")
+    with pytest.raises(ValueError):
+        GpuMacropropsDataset(seq[0], cfg, 3, stride=2, device="cpu")
+    x = torch.zeros(2, 3, 4, 4, 3)
+    with pytest.raises(_native.NativeError):
+        GpuMetricsGenerator(x, x, types.SimpleNamespace(MPROPS_COUNT=3))
+    with pytest.raises(ValueError):
+        GpuMetricsGenerator(x, x[:1], types.SimpleNamespace(MPROPS_COUNT=3))
+    # headers / file naming follow the reference's MetricsGenerator (metricsGenerator.py:13-35)
+    assert GpuMetricsGenerator.HEADERS["RE_DENSITY"] == "re_f6,re_f7,re_f8"
+    assert GpuMetricsGenerator.HEADERS["PSNR"] == "rho,vx,vy"
+
+
+def test_dit_plan_entry_points_work_without_gpu():
+    """cm_dit_create validates the reference's constructor constraints (DiT4D_V4.py:26-31, :252-254) and lists the
+    99 state_dict entries of the ATC configuration."""
+    import ctypes
+    import crowdmod_ddpm_4d_b200._native as n
+    cfg = n.DitConfig(in_channels=3, out_channels=3, rows=12, cols=36, past_len=5, future_len=3, t_patch=4, patch=4,
+                      hidden=256, depth=6, heads=4, mlp_hidden=1024, time_multiple=4, table_steps=1000, t_max_slots=8)
+    h = ctypes.c_void_p()
+    n.check(n.lib().cm_dit_create(ctypes.byref(cfg), ctypes.byref(h)))
+    assert n.lib().cm_dit_param_count(h) == 99
+    assert abs(n.lib().cm_dit_flops_per_sample(h) / 1e9 - 0.667) < 0.01
+    n.check(n.lib().cm_dit_destroy(h))
+    bad = n.DitConfig(in_channels=3, out_channels=3, rows=12, cols=36, past_len=5, future_len=3, t_patch=3, patch=4,
+                      hidden=256, depth=6, heads=4, mlp_hidden=1024, time_multiple=4, table_steps=1000, t_max_slots=8)
+    assert n.lib().cm_dit_create(ctypes.byref(bad), ctypes.byref(h)) != 0
+    assert b"divisible by t_patch" in n.lib().cm_last_error()
