@@ -240,6 +240,31 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, ui
       : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// TS form: the A operand (128 rows x 16 fp16 = 8 packed 32-bit columns per k16 step) is read from tensor memory, where
+// tcgen05.cp (or tcgen05.st) put it; B stays a shared-memory descriptor.  Measured (tools/utccp_microbench.cu): an SS-mode
+// MMA whose A tile differs from its predecessor's pays ~131 cycles for the A fetch whatever N is.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 256 bits (one k16 slice of a K-major fp16 tile, same descriptor as the MMA's
+// A operand) into lanes 0..127 x 8 columns at taddr.  Asynchronous; ordered with later tcgen05.mma of the same thread.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint32_t desc_lo, uint32_t desc_hi) {
+  asm volatile(
+      "{\n\t.reg .b64 ds;\n\t"
+      "mov.b64 ds, {%1, %2};\n\t"
+      "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n\t}\n"
+      :
+      : "r"(taddr), "r"(desc_lo), "r"(desc_hi)
+      : "memory");
+}
 __host__ __device__ constexpr uint32_t kmajor_desc_hi(int row_bytes) {
   return static_cast<uint32_t>(((8 * row_bytes) >> 4) & 0x3FFF) | (1u << 14) |
          (static_cast<uint32_t>(row_bytes == 128 ? 2 : 4) << 29);

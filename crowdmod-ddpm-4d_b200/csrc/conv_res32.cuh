@@ -29,7 +29,7 @@
 
 namespace cm {
 
-constexpr int R32_THREADS = 640;       // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 drain, warps12-19 store
+constexpr int R32_THREADS = 640;       // warp0 TMA, warp1 MMA (one thread), warp2 TMEM alloc, warp3 idle, warps4-11 drain, warps12-19 store
 constexpr int R32_DRAIN_W0 = 4;        // first drain warp (warp % 4 = TMEM lane quarter)
 constexpr int R32_STORE_W0 = 12;       // first store warp
 constexpr int R32_MAX_STAGES = 8;
@@ -174,47 +174,92 @@ __global__ void __launch_bounds__(R32_THREADS, 1) conv_res32_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // Variants measured on B200 and rejected: a second issuing warp alternating units (same
-    // launch time; it needs per-issuer rings to stay free of mbarrier phase aliasing, and two-slot rings are
-    // slower), a scout warp publishing the barrier phases through shared memory (35.3 us against 31.3).
-    bool alive = mbar_wait(wbar, 0, P.err_flag, 505);
-    const uint32_t w_lo0 = kmajor_desc_lo(smem_u32(wsm));
-    const uint32_t wx_lo0 = kmajor_desc_lo(smem_u32(wxsm));
-    const uint32_t th_step = (static_cast<uint32_t>(P.Wp) * 64) >> 4;   // one grid row of the halo box
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int u = blockIdx.x; u < P.n_units && alive; u += gridDim.x, ++it) {
-      const int buf = it & 1;
-      if (it >= 2 && !mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1, P.err_flag, 504)) break;
-      tc_fence_after();
-      PL_TRACE(1, 3);
-      const uint32_t d_base = tmem_base + buf * R32_NST;
-      for (int ks = 0; ks < nks; ++ks) {
-        if (!mbar_wait(&full_bar[s], ph, P.err_flag, 502)) { alive = false; break; }
-        PL_TRACE(1, 4);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(ring + s * P.stage_bytes));
-          if (ks < 3) {
+    // ===================== MMA issuer (one thread) =====================
+    // tcgen05.mma issue is effectively synchronous (the issuing thread is held while the tensor pipe works off its one
+    // queued MMA), so every instruction the issuer executes between two MMAs of different stages is tensor-pipe idle
+    // time: the per-stage wait / commit / descriptor code of the first version cost ~330 cycles per stage, 3 600 cycles
+    // per unit against 1 728 of MMA work (tools/plane_trace.py).  This version keeps the issuer's instruction stream
+    // minimal: ONE thread (no elect / warp-sync per stage), the four barriers a unit depends on (accumulator buffer free,
+    // the three td planes loaded) polled TOGETHER up front with independent try_waits (64 cycles for three against 158 for
+    // one bounded wait loop, tools/umma_microbench.cu), then the 18 MMAs of the unit straight-line with compile-time
+    // weight offsets, the per-stage commits (slot release) in between.  Variants measured and rejected: a second issuing
+    // warp alternating units (32.3 us against 35.2 with the old loop: each issuer owns one accumulator buffer, so the two
+    // alternate instead of overlapping), a scout warp publishing barrier phases through shared memory (35.3 us).
+    if (lane == 0) {
+      bool alive = mbar_wait(wbar, 0, P.err_flag, 505);
+      const uint32_t w_lo0 = kmajor_desc_lo(smem_u32(wsm));
+      const uint32_t wx_lo0 = kmajor_desc_lo(smem_u32(wxsm));
+      const uint32_t ring_lo = kmajor_desc_lo(smem_u32(ring));
+      const uint32_t stage16 = static_cast<uint32_t>(P.stage_bytes) >> 4;
+      const uint32_t th_step = (static_cast<uint32_t>(P.Wp) * 64) >> 4;   // one grid row of the halo box
+      const uint32_t full0 = smem_u32(full_bar);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < P.n_units && alive; u += gridDim.x, ++it) {
+        const int buf = it & 1;
+        // slots / parities of the unit's three main stages
+        int sl[3];
+        uint32_t pr[3];
 #pragma unroll
-            for (int th = 0; th < 3; ++th) {
-              const uint32_t b_lo = w_lo0 + (((ks * 3 + th) * R32_WBLK) >> 4);
-              const uint32_t a_lo = a_lo0 + th * th_step;
-              umma_f16_lohi(d_base, a_lo, b_lo, DESC_HI, IDESC, (ks == 0 && th == 0) ? 0u : 1u);
-              umma_f16_lohi(d_base, a_lo + 2, b_lo + 2, DESC_HI, IDESC, 1u);
-            }
-          } else {
-            const uint32_t b_lo = wx_lo0 + (((ks - 3) * R32_WX) >> 4);
-            umma_f16_lohi(d_base + 2 * C, a_lo0, b_lo, DESC_HI, IDESC_X, 1u);
-            umma_f16_lohi(d_base + 2 * C, a_lo0 + 2, b_lo + 2, DESC_HI, IDESC_X, 1u);
-          }
-          umma_commit(&empty_bar[s]);
-          if (ks == nks - 1) umma_commit(&tmem_full[buf]);     // accumulator of this unit complete
+        for (int k = 0; k < 3; ++k) {
+          sl[k] = s;
+          pr[k] = ph;
+          if (++s == S) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
+        {
+          // fast path: all four phases already complete (the producer runs a ring ahead, the drain warps a unit ahead)
+          const uint32_t te = it >= 2 ? smem_u32(&tmem_empty[buf]) : full0 + sl[0] * 8;
+          const uint32_t tp = it >= 2 ? static_cast<uint32_t>(((it >> 1) - 1) & 1) : pr[0];
+          uint32_t ok;
+          asm volatile(
+              "{\n\t.reg .pred P0, P1, P2, P3;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 P0, [%1], %5;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 P1, [%2], %6;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 P2, [%3], %7;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 P3, [%4], %8;\n\t"
+              "and.pred P0, P0, P1;\n\tand.pred P2, P2, P3;\n\tand.pred P0, P0, P2;\n\t"
+              "selp.u32 %0, 1, 0, P0;\n\t}\n"
+              : "=r"(ok)
+              : "r"(te), "r"(full0 + sl[0] * 8), "r"(full0 + sl[1] * 8), "r"(full0 + sl[2] * 8), "r"(tp), "r"(pr[0]),
+                "r"(pr[1]), "r"(pr[2])
+              : "memory");
+          if (!ok) {
+            if (it >= 2 && !mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1, P.err_flag, 504)) break;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              if (alive && !mbar_wait(&full_bar[sl[k]], pr[k], P.err_flag, 502)) alive = false;
+            if (!alive) break;
+          }
+        }
+        tc_fence_after();
+        PL_TRACE(1, 4);
+        const uint32_t d_base = tmem_base + buf * R32_NST;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+          const uint32_t a_lo0 = ring_lo + sl[ks] * stage16;
+#pragma unroll
+          for (int th = 0; th < 3; ++th) {
+            const uint32_t b_lo = w_lo0 + (((ks * 3 + th) * R32_WBLK) >> 4);
+            const uint32_t a_lo = a_lo0 + th * th_step;
+            umma_f16_lohi(d_base, a_lo, b_lo, DESC_HI, IDESC, (ks == 0 && th == 0) ? 0u : 1u);
+            umma_f16_lohi(d_base, a_lo + 2, b_lo + 2, DESC_HI, IDESC, 1u);
+          }
+          umma_commit(&empty_bar[sl[ks]]);
+        }
+        // fused 1x1x1 chunks: one stage each, centre-tap columns
+        for (int x = 0; x < P.nx; ++x) {
+          if (!mbar_wait(&full_bar[s], ph, P.err_flag, 502)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t a_lo0 = ring_lo + s * stage16;
+          const uint32_t b_lo = wx_lo0 + ((x * R32_WX) >> 4);
+          umma_f16_lohi(d_base + 2 * C, a_lo0, b_lo, DESC_HI, IDESC_X, 1u);
+          umma_f16_lohi(d_base + 2 * C, a_lo0 + 2, b_lo + 2, DESC_HI, IDESC_X, 1u);
+          umma_commit(&empty_bar[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        if (!alive) break;
+        umma_commit(&tmem_full[buf]);                          // accumulator of this unit complete
         PL_TRACE(1, 6);
-        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= R32_DRAIN_W0 && warp < R32_STORE_W0) {

@@ -110,6 +110,69 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int G, int NM, Res* ou
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// pace of 64 back-to-back MMAs whose operands are (re)used in different patterns: vary = 0 same A and B every time,
+// 1 a different A tile per MMA (B fixed), 2 a different B tile per MMA (A fixed), 3 both different.  Distinct tiles are
+// 4 KB (A) / N*ROWB bytes (B) apart inside a 96 KB window, so nothing can be served from an operand cache.
+template <int N, int ROWB>
+__global__ void __launch_bounds__(128, 1) bench_fresh(int vary, Res* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t IDESC = make_idesc_f16(128, N);
+  constexpr uint32_t DESC_HI = kmajor_desc_hi(ROWB);
+  const uint32_t a0 = kmajor_desc_lo(smem_u32(smem));
+  const uint32_t b0 = kmajor_desc_lo(smem_u32(smem) + 96 * 1024);
+  constexpr uint32_t A_STEP = (128 * ROWB) >> 4, B_STEP = (N * ROWB) >> 4;     // one whole tile further
+  constexpr int NA = 96 * 1024 / (128 * ROWB), NB = 96 * 1024 / (N * ROWB);
+  if (warp == 1 && lane == 0) {
+    long long t0 = clk();
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      const uint32_t a = a0 + ((vary & 1) ? (i % NA) * A_STEP : 0) + 2 * (i & 1);
+      const uint32_t b = b0 + ((vary & 2) ? (i % NB) * B_STEP : 0) + 2 * (i & 1);
+      umma_f16_lohi(tmem_base, a, b, DESC_HI, IDESC, 1u);
+    }
+    umma_commit(&bar);
+    long long t1 = clk();
+    mbar_wait(&bar, 0, nullptr, 0);
+    long long t2 = clk();
+    out->t[0] = t1 - t0;
+    out->t[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int N, int ROWB>
+void run_fresh(const char* name, Res* d) {
+  cudaFuncSetAttribute(bench_fresh<N, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static const char* what[4] = {"same A, same B", "fresh A, same B", "same A, fresh B", "fresh A, fresh B"};
+  for (int vary = 0; vary < 4; ++vary) {
+    Res h{};
+    cudaMemset(d, 0, sizeof(Res));
+    bench_fresh<N, ROWB><<<1, 128, 200 * 1024>>>(vary, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s fresh %d: %s\n", name, vary, cudaGetErrorString(e)); exit(1); }
+    cudaMemcpy(&h, d, sizeof(Res), cudaMemcpyDeviceToHost);
+    printf("%s %-18s: 64 MMAs issue %lld, complete %lld (%.1f / MMA)\n", name, what[vary], h.t[0], h.t[1], (h.t[1] - 752) / 63.0);
+  }
+}
+
 // cost of single instructions, averaged over 64 repetitions (lane 0 of warp 1)
 __global__ void __launch_bounds__(128, 1) instr_costs(Res* out) {
   __shared__ uint64_t bars[4];
@@ -144,6 +207,31 @@ __global__ void __launch_bounds__(128, 1) instr_costs(Res* out) {
     // commit issue cost alone (arrivals pile up on bars[2] with a huge expected count: never waited on)
     for (int i = 0; i < 32; ++i) umma_commit(&bars[2]);
     long long t6 = clk();
+    // mbarrier.test_wait (non-blocking) on a completed phase, and three independent try_waits issued back to back
+    long long t7 = clk();
+    uint32_t acc = 0;
+    for (int i = 0; i < 64; ++i) {
+      uint32_t ok;
+      asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+                   : "=r"(ok) : "r"(smem_u32(&bars[0])), "r"(0u) : "memory");
+      if (!ok) break;
+      acc += ok;
+    }
+    long long t8 = clk();
+    for (int i = 0; i < 64; ++i) {
+      uint32_t ok;
+      asm volatile("{\n\t.reg .pred P, Q, R;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %4;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 Q, [%2], %4;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 R, [%3], %4;\n\t"
+                   "and.pred P, P, Q;\n\tand.pred P, P, R;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+                   : "=r"(ok) : "r"(smem_u32(&bars[0])), "r"(smem_u32(&bars[0])), "r"(smem_u32(&bars[0])), "r"(0u) : "memory");
+      if (!ok) break;
+      acc += ok;
+    }
+    long long t9 = clk();
+    out->t[7] = (t8 - t7) / 64 + (acc == 12345);
+    out->t[8] = (t9 - t8) / 64;
     out->t[0] = (t1 - t0) / 64;
     out->t[1] = (t2 - t1) / 64;
     out->t[2] = (t3 - t2) / 64;
@@ -220,9 +308,13 @@ int main() {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("instr_costs: %s\n", cudaGetErrorString(e)); return 1; }
     cudaMemcpy(&h, d, sizeof(Res), cudaMemcpyDeviceToHost);
-    printf("try_wait(completed) %lld cyc | fence::after %lld | fence::before %lld | commit+wait round trip %lld | empty loop(64) %lld | commit issue %lld | elect+syncwarp %lld\n",
-           h.t[0], h.t[1], h.t[2], h.t[3], h.t[4], h.t[5], h.t[6]);
+    printf("try_wait(completed) %lld cyc | fence::after %lld | fence::before %lld | commit+wait round trip %lld | empty loop(64) %lld | commit issue %lld | elect+syncwarp %lld | test_wait(completed) %lld | 3 try_waits back to back %lld\n",
+           h.t[0], h.t[1], h.t[2], h.t[3], h.t[4], h.t[5], h.t[6], h.t[7], h.t[8]);
   }
+  run_fresh<192, 64>("N=192 SW64 ", d);
+  run_fresh<96, 64>("N=96  SW64 ", d);
+  run_fresh<192, 128>("N=192 SW128", d);
+  run_fresh<256, 128>("N=256 SW128", d);
   run_offsets<192, 64>("N=192 SW64 ", d);
   run_offsets<96, 64>("N=96  SW64 ", d);
   run_offsets<192, 128>("N=192 SW128", d);
