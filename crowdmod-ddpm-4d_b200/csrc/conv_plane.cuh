@@ -236,6 +236,9 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // (a one-thread issuer with the stage's 12 MMA groups unrolled, as in conv_res32_kernel, was measured here: the
+    // 96 -> 32 layer 79.7 -> 75.8 us, but the level-1 instantiations (N = 192 MMAs, BN = 64) 49.1 -> 55.1 / 28.7 -> 31.8 us
+    // and the 1 280-sample chain 81.2 -> 76.4 seq/s: not kept)
     constexpr uint32_t DESC_HI = kmajor_desc_hi(ROWB);
     constexpr uint32_t TILE_LO = (128 * ROWB) >> 4;          // descriptor step between M tiles
     int s = 0;
