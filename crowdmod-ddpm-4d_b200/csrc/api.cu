@@ -310,6 +310,12 @@ int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int head
                            static_cast<cudaStream_t>(stream));
 }
 
+int cm_op_attn_core_backward(const float* qkv, const float* dctx, float* dqkv, int B, int S, int C, int heads,
+                             void* stream) {
+  if (int e = backward_init()) return e;
+  return attn_core_backward_enqueue(qkv, dctx, dqkv, B, S, C, heads, static_cast<cudaStream_t>(stream));
+}
+
 int cm_op_attn_block(const float* x, const float* gamma, const float* beta, const float* w_in, const float* b_in,
                      const float* w_out, const float* b_out, float* out32, void* out16, int B, int S, int C,
                      int heads, float eps, void* stream) {

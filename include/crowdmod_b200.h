@@ -176,6 +176,11 @@ CM_API int cm_op_gn_silu(const float* src0, int c0, const float* src1, int c1, c
                   const float* beta, int B, int pixels, float eps, int silu, void* out_norm16,
                   void* out_raw16, void* stream);
 CM_API int cm_op_attn_core(const float* qkv, void* ctx16, int B, int S, int C, int heads, void* stream);
+/* backward of the attention core (autograd of softmax(Q K^T / sqrt(dh)) V inside nn.MultiheadAttention, reference
+ * models/backbones/layers.py:5-18 under loss.backward(), ddpm.py:143): qkv fp32 [B][S][3C] (the in_proj output the
+ * training forward saved), dctx fp32 [B][S][C] = gradient of the core's output, dqkv fp32 [B][S][3C] out. */
+CM_API int cm_op_attn_core_backward(const float* qkv, const float* dctx, float* dqkv, int B, int S, int C, int heads,
+                             void* stream);
 /* whole AttentionBlock of the sampling path (reference models/backbones/layers.py:5-18: GroupNorm(8) ->
  * nn.MultiheadAttention(C, heads) self-attention -> + x) as ONE launch.  x, out32: fp32 [B][S][C] tokens
  * (channels-last); w_in [3C][C] / b_in [3C] = mhsa.in_proj_weight / in_proj_bias, w_out [C][C] / b_out [C] =

@@ -182,6 +182,36 @@ def test_attn_core(nat, B, S, C_):
     assert rel_l2(ctx.float(), ref) <= 7e-4
 
 
+@pytest.mark.parametrize("B,S,C_", [(3, 54, 128), (2, 108, 256), (2, 84, 128), (2, 1, 128), (1, 7, 64), (2, 27, 32), (1, 128, 128),
+                                    (2, 33, 256)])
+def test_attn_core_backward_vs_torch_autograd(nat, B, S, C_):
+    """Register-tiled shared-memory GEMM backward of softmax(Q K^T / sqrt(dh)) V (fp32 throughout) against autograd in
+    float64: ragged S (not a multiple of 4, S = 1), dh = 8 ... 64, the largest tile (S = 128) and the ATC_medium shape."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    heads = 4
+    dh = C_ // heads
+    qkv = torch.randn(B, S, 3 * C_, device="cuda", generator=g)
+    dctx = torch.randn(B, S, C_, device="cuda", generator=g)
+    dqkv = torch.full((B, S, 3 * C_), float("nan"), device="cuda")
+    nat.check(nat.lib().cm_op_attn_core_backward(nat.ptr(qkv), nat.ptr(dctx), nat.ptr(dqkv), B, S, C_, heads,
+                                                 nat.current_stream()))
+    torch.cuda.synchronize()
+    x = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(B, S, heads, dh).transpose(1, 2) for t in x.split(C_, dim=2)]
+    p = torch.softmax((q @ k.transpose(-1, -2)) / dh ** 0.5, dim=-1)
+    ctx = (p @ v).transpose(1, 2).reshape(B, S, C_)
+    ctx.backward(dctx.double())
+    assert torch.isfinite(dqkv).all()
+    for name, sl in (("dQ", slice(0, C_)), ("dK", slice(C_, 2 * C_)), ("dV", slice(2 * C_, 3 * C_))):
+        e = rel_l2(dqkv[..., sl].double(), x.grad[..., sl])
+        assert e <= 2e-6, f"{name} rel-L2 {e:.3e}"
+    again = torch.empty_like(dqkv)
+    nat.check(nat.lib().cm_op_attn_core_backward(nat.ptr(qkv), nat.ptr(dctx), nat.ptr(again), B, S, C_, heads,
+                                                 nat.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(dqkv, again), "attention backward is not deterministic"
+
+
 @pytest.mark.parametrize("B,S", [(2, 54), (3, 84), (1, 12), (2, 1), (2, 16), (1, 100), (2, 128)])
 def test_attn_block_fused(nat, B, S):
     """Fused AttentionBlock (layers.py:5-18) vs torch GroupNorm + nn.MultiheadAttention in fp32."""
