@@ -269,6 +269,8 @@ class UNet(nn.Module):
         B = future.shape[0]
         eps = torch.empty((B, self.output_channels, rows, cols, future_len), device=future.device,
                           dtype=torch.float32)
+        if B == 0:                       # the reference's torch ops accept an empty batch and return an empty tensor
+            return eps
         n.check(n.lib().cm_unet_forward(plan.handle, n.ptr(future), n.ptr(t), n.ptr(past), n.ptr(eps),
                                         B, n.current_stream()))
         return eps
@@ -283,6 +285,8 @@ class UNet(nn.Module):
         noise: optional CUDA tensor [nsteps, *x.shape] of injected z; None -> Philox(seed).
         """
         self._require_cuda(past, x, noise, history)
+        if x.shape[0] == 0:              # empty sample batch: nothing to denoise (the reference loop is a no-op on it)
+            return x
         n = _native()
         rows, cols, past_len, future_len = self._geometry(x, past)
         plan = self._plan(rows, cols, past_len, future_len)

@@ -56,6 +56,25 @@ def test_unet_forward_vs_oracle_fresh_inputs_b5():
         assert rel_l2(eps[b].cpu(), ref[b]) <= 2 * EPS_TOL
 
 
+def test_empty_and_single_sample_batches():
+    """Edge cases of the drop-in surface: an empty batch returns an empty tensor (as the reference's torch ops do) from the
+    forward and from the fused chain; a single sample equals the same sample inside a batch of 3 bit for bit."""
+    meta, a = load_golden("unet_atc_b2")
+    net = build_unet(meta).cuda().eval()
+    fut, past, t = a["future"].cuda(), a["past"].cuda(), a["t"].cuda()
+    with torch.no_grad():
+        e0 = net(fut[:0], t[:0], past[:0])
+        assert e0.shape == (0,) + tuple(fut.shape[1:]) and e0.dtype == torch.float32
+        from crowdmod_ddpm_4d_b200.models.diffusion.ddpm import DDPM, ddpm_coefficients
+        ts, coef = ddpm_coefficients(DDPM(timesteps=4, scale=0.5))
+        x0 = fut[:0].clone().contiguous()
+        assert net.sample_chain(past[:0].contiguous(), x0, ts, coef, mode=0, seed=1).shape[0] == 0
+        one = net(fut[:1], t[:1], past[:1])
+        three = net(fut[:1].repeat(3, 1, 1, 1, 1), t[:1].repeat(3), past[:1].repeat(3, 1, 1, 1, 1))
+    assert torch.equal(one[0], three[0]) and torch.equal(one[0], three[2])
+    assert rel_l2(one.cpu(), a["eps"][:1]) <= EPS_TOL
+
+
 def test_unet_forward_vs_oracle_at_baseline_batch_64():
     """eps against the CPU oracle at the BASELINE batch (config/ATC.yml, B = 64): full SM fill, every persistent
     CTA walks several units, ragged last wave -- the regime bench.py times.  Gate per sample as well."""
