@@ -1466,15 +1466,21 @@ template <int MT, int NTW, int KT, int ALD>
 __device__ __forceinline__ void ab_gemm(const __half* __restrict__ A, int m_base, const __half* __restrict__ Whi,
                                         const __half* __restrict__ Wlo, const int (&nb)[NTW], int kcol0,
                                         float (&acc)[MT][NTW][4], int g, int t) {
+  // The k index inside a 16-wide block is permuted identically for A and B (fragment slots (2t, 2t+1) and (2t+8, 2t+9) of
+  // thread t take the four CONSECUTIVE physical k's 4t .. 4t+3): the product is a sum over all 16 k's either way, and every
+  // fragment pair becomes one 8-byte load instead of two 4-byte ones (the kernel's top stalls were lg_throttle and
+  // long_scoreboard on these weight loads, profiles/r1_attn_block_ncu_full_raw.csv).
   uint32_t bh[2][NTW][2], bl[2][NTW][2];
   auto load_b = [&](int kt, int buf) {
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt) {
-      const size_t o = (size_t)(nb[nt] + g) * AB_C + kcol0 + kt * 16 + 2 * t;
-      bh[buf][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(Whi + o));
-      bh[buf][nt][1] = __ldg(reinterpret_cast<const uint32_t*>(Whi + o + 8));
-      bl[buf][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(Wlo + o));
-      bl[buf][nt][1] = __ldg(reinterpret_cast<const uint32_t*>(Wlo + o + 8));
+      const size_t o = (size_t)(nb[nt] + g) * AB_C + kcol0 + kt * 16 + 4 * t;
+      const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(Whi + o));
+      const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(Wlo + o));
+      bh[buf][nt][0] = h2.x;
+      bh[buf][nt][1] = h2.y;
+      bl[buf][nt][0] = l2.x;
+      bl[buf][nt][1] = l2.y;
     }
   };
   load_b(0, 0);
@@ -1484,12 +1490,14 @@ __device__ __forceinline__ void ab_gemm(const __half* __restrict__ A, int m_base
     if (kt + 1 < KT) load_b(kt + 1, buf ^ 1);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const __half* ar = A + (size_t)(m_base + mt * 16 + g) * ALD + kt * 16 + 2 * t;
+      const __half* ar = A + (size_t)(m_base + mt * 16 + g) * ALD + kt * 16 + 4 * t;
+      const uint2 a_lo = *reinterpret_cast<const uint2*>(ar);             // row g:     physical k 4t .. 4t+3
+      const uint2 a_hi = *reinterpret_cast<const uint2*>(ar + 8 * ALD);   // row g + 8
       uint32_t a[4];
-      a[0] = *reinterpret_cast<const uint32_t*>(ar);
-      a[1] = *reinterpret_cast<const uint32_t*>(ar + 8 * ALD);
-      a[2] = *reinterpret_cast<const uint32_t*>(ar + 8);
-      a[3] = *reinterpret_cast<const uint32_t*>(ar + 8 * ALD + 8);
+      a[0] = a_lo.x;
+      a[1] = a_hi.x;
+      a[2] = a_lo.y;
+      a[3] = a_hi.y;
 #pragma unroll
       for (int nt = 0; nt < NTW; ++nt) {
         mma_16816(acc[mt][nt], a, bl[buf][nt][0], bl[buf][nt][1]);
