@@ -9,6 +9,7 @@
 
 #include "../../include/crowdmod_b200.h"
 #include "backward.cuh"
+#include "wgrad_plane.cuh"
 #include "conv_plane.cuh"
 #include "conv_res32.cuh"
 #include "conv_umma.cuh"
@@ -461,6 +462,54 @@ int cm_op_conv3d_wgrad(int mode, const void* act16, int B, int D, int H, int W, 
         cudaEventDestroy(b);
         cudaMemsetAsync(G, 0, gel * sizeof(float), st);
         rc = wgrad_enqueue(L, st);
+      }
+    }
+  } else if (impl == 2) {
+    // plane / halo scheme (wgrad_plane.cuh): one launch per 32-channel chunk of the main source; the fused 1x1x1 source
+    // goes through wgrad_umma_kernel in 1x1x1 mode into its rows of G
+    CM_CHECK(mode == 0, "plane wgrad covers k3 s1 p1 convs (mode 0), got mode %d", mode);
+    WgradPlaneLaunch PL[8];
+    const int nc = cin / 32;
+    CM_CHECK(nc >= 1 && nc <= 8, "plane wgrad: cin %d not covered", cin);
+    for (int c = 0; c < nc && !rc; ++c) {
+      rc = wgrad_plane_prepare(&PL[c], static_cast<const __half*>(act16), B, D, H, W, cin, 0, c * 32,
+                               static_cast<const __half*>(dout16), 0, cout, G);
+      if (!rc && !PL[c].ok) {
+        cm::set_error("plane wgrad does not cover this shape");
+        rc = 1;
+      }
+    }
+    WgradLaunch XL;
+    if (!rc && cin_extra)
+      rc = wgrad_prepare(&XL, 3, static_cast<const __half*>(extra16), B, D, H, W, cin_extra, nullptr, 0,
+                         static_cast<const __half*>(dout16), cout, G + (size_t)27 * cin * cout);
+    auto run = [&]() {
+      int e = 0;
+      for (int c = 0; c < nc && !e; ++c) e = wgrad_plane_enqueue(PL[c], st);
+      if (!e && cin_extra) e = wgrad_enqueue(XL, st);
+      return e;
+    };
+    if (!rc) rc = run();
+    if (!rc) {
+      if (const char* e = getenv("CM_DBG_REPS")) {
+        const int reps = atoi(e);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaStreamSynchronize(st);
+        cudaEventRecord(a, st);
+        for (int i = 0; i < reps && !rc; ++i) rc = run();
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "CM_DBG wgrad plane B=%d D=%d H=%d W=%d cin=%d+%d cout=%d HB=%d units=%d stages=%d grid=%d: %.2f us per conv (%.1f TF/s)\n",
+                B, D, H, W, cin, cin_extra, cout, PL[0].p.HB, PL[0].p.n_units, PL[0].p.stages, PL[0].grid.x, ms * 1e3f / reps,
+                2.0 * B * D * H * W * cout * (27.0 * cin + cin_extra) / (ms * 1e-3 / reps) * 1e-12);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        cudaMemsetAsync(G, 0, gel * sizeof(float), st);
+        rc = run();
       }
     }
   } else {

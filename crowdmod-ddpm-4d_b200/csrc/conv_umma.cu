@@ -4,6 +4,7 @@
 #include "wgrad_umma.cuh"
 #include "conv_plane.cuh"
 #include "conv_res32.cuh"
+#include "wgrad_plane.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -587,6 +588,7 @@ int wgrad_init() {
   static bool done = false;
   if (done) return 0;
   if (int rc = load_driver_syms()) return rc;
+  if (int rc = wgrad_plane_init()) return rc;
   if (int rc = wg_attr_t<32, 32, 32>()) return rc;
   if (int rc = wg_attr_t<32, 64, 64>()) return rc;
   if (int rc = wg_attr_t<32, 64, 128>()) return rc;
@@ -696,6 +698,79 @@ int wgrad_prepare(WgradLaunch* L, int mode, const __half* act, int B, int D, int
   L->smem = (size_t)stages * stage_bytes + 1024 + 256;
   L->grid = dim3(m_tiles, p.n_tiles * splits, p.nphase);
   L->flops = 2.0 * p.M * cout * (double)p.krows * p.nphase;
+  return 0;
+}
+
+// ================================ weight gradient, plane / halo scheme (wgrad_plane.cuh) ================================
+namespace {
+int make_plane_box_map(CUtensorMap* map, const __half* base, int B, int D, int H, int W, int C, int ld, int box_w, int box_h) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2,
+                           (cuuint64_t)D * H * W * ld * 2};
+  cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad plane box) failed: %d (B=%d D=%d H=%d W=%d C=%d ld=%d box %dx%d)",
+           (int)r, B, D, H, W, C, ld, box_w, box_h);
+  return 0;
+}
+}  // namespace
+
+int wgrad_plane_prepare(WgradPlaneLaunch* L, const __half* act, int B, int D, int H, int W, int cin, int act_ld, int c0,
+                        const __half* dout, int dout_ld, int cout, float* G) {
+  if (int rc = load_driver_syms()) return rc;
+  memset(L, 0, sizeof(*L));
+  L->ok = false;
+  if (getenv("CM_NO_WGRAD_PLANE") != nullptr) return 0;
+  if (cout != 32 || cin % 32 != 0 || c0 % 32 != 0 || c0 + 32 > cin) return 0;
+  const int Wp = W + 2;
+  const int HB = (Wp % 2 == 0) ? 6 : 14;                     // (HB + 2) * Wp must be a multiple of 16 (pixels per MMA)
+  if (Wp > 256 || HB + 3 > 256 || ((HB + 2) * Wp) % 16 != 0) return 0;
+  if (act_ld <= 0) act_ld = cin;
+  if (dout_ld <= 0) dout_ld = cout;
+  WgradPlaneParams& p = L->p;
+  p.H = H; p.W = W; p.D = D; p.Wp = Wp; p.HB = HB;
+  p.hblocks = (H + HB - 1) / HB;
+  p.units_per_sample = D * p.hblocks;
+  p.n_units = B * p.units_per_sample;
+  p.c0 = c0;
+  p.ksteps = (HB + 2) * Wp / 16;
+  p.a_box_bytes = (HB + 3) * Wp * 64;
+  p.a_slot_bytes = (p.a_box_bytes + 1023) & ~1023;
+  p.g_box_bytes = HB * Wp * 64;
+  p.g_data_off = (2 * Wp * 64 + 1023) & ~1023;               // zero guard rows in front of the box (>= two grid rows)
+  p.g_slot_bytes = (p.g_data_off + p.g_box_bytes + 2 * Wp * 64 + 1023) & ~1023;
+  p.stage_bytes = 3 * p.a_slot_bytes + p.g_slot_bytes;
+  int stages = (int)((227L * 1024 - 1024 - 256) / p.stage_bytes);
+  if (stages > WP_MAX_STAGES) stages = WP_MAX_STAGES;
+  if (stages < 2) return 0;
+  p.stages = stages;
+  p.cin = cin;
+  p.G = G;
+  p.err_flag = device_error_flag();
+  if (int rc = make_plane_box_map(&p.amap, act, B, D, H, W, cin, act_ld, Wp, HB + 3)) return rc;
+  if (int rc = make_plane_box_map(&p.gmap, dout, B, D, H, W, cout, dout_ld, Wp, HB)) return rc;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+  L->grid = dim3(p.n_units < n_sm ? p.n_units : n_sm, 1, 1);
+  L->smem = (size_t)stages * p.stage_bytes + 1024 + 256;
+  L->ok = true;
+  return 0;
+}
+
+int wgrad_plane_enqueue(const WgradPlaneLaunch& L, cudaStream_t st) {
+  wgrad_plane_kernel<32><<<L.grid, WP_THREADS, L.smem, st>>>(L.p);
+  CM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int wgrad_plane_init() {
+  static bool done = false;
+  if (done) return 0;
+  CM_CUDA(cudaFuncSetAttribute(wgrad_plane_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  done = true;
   return 0;
 }
 

@@ -18,6 +18,7 @@
 #include "backward.cuh"
 #include "conv_plane.cuh"
 #include "conv_res32.cuh"
+#include "wgrad_plane.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 #include "pack.cuh"
@@ -75,6 +76,11 @@ struct Op {
   ConvLaunch dlaunch, dxlaunch;
   PlaneLaunch dplaunch;     // dgrad of a k3 s1 conv is a k3 s1 conv: plane-tile kernel when it fits
   WgradLaunch wlaunch;
+  // full-resolution convs with 32 output channels: plane / halo weight gradient (wgrad_plane.cuh), one launch per
+  // 32-channel chunk of the main source, the fused 1x1x1 source through wgrad_umma_kernel in 1x1x1 mode (n_wpl = 0: off)
+  WgradPlaneLaunch wpl[4];
+  int n_wpl = 0;
+  WgradLaunch wxlaunch;
 };
 
 struct Level {
@@ -1067,6 +1073,24 @@ int prepare_train(cm_unet* u, int batch) {
                                op.cin_extra, u->g16[op.out], op.cout, u->G + op.g_off, dup * op.cout,
                                u->live_dup * op.cin, u->live_dup * op.cin_extra))
       return rc;
+    op.n_wpl = 0;
+    if (op.mode == 0 && op.cout == 32 && op.cin % 32 == 0 && op.cin / 32 <= 4) {
+      const int nc = op.cin / 32;
+      bool ok = true;
+      for (int c = 0; c < nc && ok; ++c) {
+        if (int rc = wgrad_plane_prepare(&op.wpl[c], u->tens[op.in].p16, batch, li.D, li.H, li.W, op.cin, u->live_dup * op.cin,
+                                         c * 32, u->g16[op.out], dup * op.cout, op.cout, u->G + op.g_off))
+          return rc;
+        ok = op.wpl[c].ok;
+      }
+      if (ok && op.cin_extra) {
+        if (int rc = wgrad_prepare(&op.wxlaunch, 3, extra, batch, li.D, li.H, li.W, op.cin_extra, nullptr, 0, u->g16[op.out],
+                                   op.cout, u->G + op.g_off + (size_t)27 * op.cin * op.cout, dup * op.cout,
+                                   u->live_dup * op.cin_extra, 0))
+          return rc;
+      }
+      if (ok) op.n_wpl = nc;
+    }
   }
   u->train_prepared = batch;
   return 0;
@@ -1217,7 +1241,15 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
           ++nl;
         }
         mark("dgrad " + op.tag);
-        if (int e = wgrad_enqueue(op.wlaunch, st)) return e;
+        if (op.n_wpl > 0) {
+          for (int c = 0; c < op.n_wpl; ++c)
+            if (int e = wgrad_plane_enqueue(op.wpl[c], st)) return e;
+          if (op.cin_extra)
+            if (int e = wgrad_enqueue(op.wxlaunch, st)) return e;
+          nl += op.n_wpl - 1 + (op.cin_extra ? 1 : 0);
+        } else if (int e = wgrad_enqueue(op.wlaunch, st)) {
+          return e;
+        }
         mark("wgrad " + op.tag);
         // packed-K scratch -> nn.Conv3d weight layout: all convs in one launch after the op loop
         for (long long v : {(long long)op.mode, (long long)op.g_off, (long long)u->grad_off[op.w],

@@ -390,6 +390,37 @@ def test_conv_wgrad_vs_torch_autograd(nat, case, impl):
         assert rel_l2(dwx, rwx) <= 3e-5
 
 
+# plane / halo weight gradient (wgrad_plane.cuh): one haloed box per td plane + one dOut box per unit serve all 27 taps
+# (th = row-offset views, tw = the M dimension's chunks one row apart), nine accumulators resident in TMEM.  impl=2 forces it.
+WGRAD_PLANE_CASES = [
+    (0, 2, 8, 12, 36, 32, 32, 0),      # encoder_blocks.0.conv_1 / conv_2 (ATC): ragged last row block (12 = 8 + 4)
+    (0, 1, 8, 28, 24, 32, 32, 0),      # HERMES-CR-120 level 0: 4 row blocks, last one half empty
+    (0, 3, 8, 8, 12, 32, 32, 0),       # ETH-UCY level 0: whole planes
+    (0, 2, 8, 12, 36, 96, 32, 0),      # decoder_blocks.6.conv_1: three 32-channel chunks
+    (0, 2, 8, 12, 36, 32, 32, 96),     # decoder_blocks.6.conv_2 + match_input rows (1x1x1 source through wgrad_umma)
+    (0, 40, 8, 12, 36, 64, 32, 0),     # more units than SMs: several units accumulate in one CTA's TMEM
+    (0, 1, 2, 5, 9, 32, 32, 0),        # odd width (W + 2 = 11): 16-row blocks, H < HB
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_PLANE_CASES, ids=lambda c: "m%d_B%d_%dx%dx%d_ci%d_co%d_x%d" % c)
+def test_conv_wgrad_plane_vs_torch_autograd(nat, case):
+    mode, B, D, H, W, cin, cout, cx = case
+    act, w, extra, wx, dout = _bwd_inputs(*case)
+    dw = torch.full_like(w, float("nan"))
+    dwx = torch.full_like(wx, float("nan")) if cx else None
+    nat.check(nat.lib().cm_op_conv3d_wgrad(mode, nat.ptr(act), B, D, H, W, cin, nat.ptr(extra), cx,
+                                           nat.ptr(dout), cout, nat.ptr(dw), nat.ptr(dwx), 2,
+                                           nat.current_stream()))
+    torch.cuda.synchronize()
+    assert nat.lib().cm_device_error() == 0
+    _, rw, rwx = torch_conv_grads(mode, act, extra, w, wx, dout)
+    e = rel_l2(dw, rw)
+    assert e <= 3e-5, f"plane wgrad rel-L2 {e:.3e}; " + describe_mismatch(dw.reshape(cout, -1), rw.reshape(cout, -1))
+    if cx:
+        assert rel_l2(dwx, rwx) <= 3e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # plane-tile conv (conv_plane.cuh): W-shifted descriptor views of one haloed TMA box, stacked hi|lo
 # MMA, persistent CTAs with double-buffered TMEM.  impl=2 forces it (error if not covered).

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # ncu launch list (durations) of one training step (forward + native backward), HERMES-CR-120 shape, batch 64
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 830 -c 460 --csv --log-file gpurun_out/launches_train.csv python tools/bwd_trace.py > gpurun_out/ncu_ll_train.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 640 -c 330 --csv --log-file gpurun_out/launches_train.csv python tools/bwd_trace.py > gpurun_out/ncu_ll_train.log 2>&1
 echo "exit $?"
 python - <<'PY'
 import csv, collections
