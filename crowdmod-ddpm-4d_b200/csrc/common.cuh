@@ -295,6 +295,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// four consecutive fp32 adds into global memory as ONE reduction (REDG.E.ADD.F32x4, sm_90+; p 16-byte aligned): a quarter of
+// the L2 atomic operations of four scalar atomicAdd() calls
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // same, without the wait: issue several loads, then tmem_ld_wait() once
 __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float (&v)[16]) {
   asm volatile(

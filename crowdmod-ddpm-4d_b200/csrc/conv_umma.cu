@@ -750,6 +750,7 @@ int wgrad_plane_prepare(WgradPlaneLaunch* L, const __half* act, int B, int D, in
   p.cin = cin;
   p.G = G;
   p.err_flag = device_error_flag();
+  if (const char* e = getenv("CM_WGP_DBG")) p.dbg = atoi(e);
   if (int rc = make_plane_box_map(&p.amap, act, B, D, H, W, cin, act_ld, Wp, HB + 3)) return rc;
   if (int rc = make_plane_box_map(&p.gmap, dout, B, D, H, W, cout, dout_ld, Wp, HB)) return rc;
   int n_sm = 148;

@@ -45,6 +45,7 @@ struct WgradPlaneParams {
   int g_slot_bytes;      // guard + box + guard
   int cin;               // channels of the whole main source: G row = tap * cin + c0 + ci
   float* G;              // [27 * cin (+ extra rows)][32] fp32, zeroed by the caller
+  int dbg;               // bring-up knobs (CM_WGP_DBG): 1 no TMA loads, 4 no MMA
   int* err_flag;
 };
 
@@ -103,11 +104,15 @@ __global__ void __launch_bounds__(WP_THREADS, 1) wgrad_plane_kernel(const __grid
         const int d = v / P.hblocks;
         const int h0 = (v - d * P.hblocks) * P.HB;
         uint8_t* sa = smem + s * P.stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx);
+        if (P.dbg & 1) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_expect_tx(&full_bar[s], tx);
 #pragma unroll
-        for (int td = 0; td < 3; ++td)
-          tma_load_tile_5d(&P.amap, &full_bar[s], sa + td * P.a_slot_bytes, P.c0, -1, h0 - 1, d + td - 1, n);
-        tma_load_tile_5d(&P.gmap, &full_bar[s], sa + 3 * P.a_slot_bytes + P.g_data_off, 0, 0, h0, d, n);
+          for (int td = 0; td < 3; ++td)
+            tma_load_tile_5d(&P.amap, &full_bar[s], sa + td * P.a_slot_bytes, P.c0, -1, h0 - 1, d + td - 1, n);
+          tma_load_tile_5d(&P.gmap, &full_bar[s], sa + 3 * P.a_slot_bytes + P.g_data_off, 0, 0, h0, d, n);
+        }
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1) wgrad_plane_kernel(const __grid
         // N chunks (th = 2, 1, 0) one grid row apart, starting two grid rows above the dOut box
         const uint32_t g_lo0 = mnmajor_desc_lo(base + 3 * P.a_slot_bytes + P.g_data_off - 2 * P.Wp * 64, P.Wp * 64);
 #pragma unroll
-        for (int td = 0; td < 3; ++td) {
+        for (int td = 0; td < 3 && !(P.dbg & 4); ++td) {
           // M chunks (tw = 0..3) one box row (64 B) apart
           const uint32_t a_lo = mnmajor_desc_lo(base + td * P.a_slot_bytes, 64);
           const uint32_t d_tmem = tmem_base + td * 96;
@@ -150,8 +155,12 @@ __global__ void __launch_bounds__(WP_THREADS, 1) wgrad_plane_kernel(const __grid
     if (mbar_wait(tmem_full, 0, P.err_flag, 213)) {
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(tw * 32) << 16);
+      // every CTA adds into the same 27 x 32 rows: start at a different (td, th) block per CTA so that the CTAs finishing
+      // together spread over nine times as many L2 lines, one 128-byte row per thread as eight 16-byte reductions
+      const int a0 = static_cast<int>(blockIdx.x % 9u);
 #pragma unroll 1
-      for (int a = 0; a < 9; ++a) {                          // (td, N chunk j): th = 2 - j
+      for (int aa = 0; aa < 9; ++aa) {                       // (td, N chunk j): th = 2 - j
+        const int a = aa + a0 < 9 ? aa + a0 : aa + a0 - 9;
         const int td = a / 3, th = 2 - (a - td * 3);
         float v0[16], v1[16];
         tmem_ld16_async(t_lane + a * 32, v0);
@@ -160,9 +169,9 @@ __global__ void __launch_bounds__(WP_THREADS, 1) wgrad_plane_kernel(const __grid
         if (tw < 3) {
           float* gp = P.G + (static_cast<size_t>((td * 3 + th) * 3 + tw) * P.cin + P.c0 + lane) * 32;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(gp + i, v0[i]);
+          for (int i = 0; i < 16; i += 4) red_add_v4(gp + i, v0[i], v0[i + 1], v0[i + 2], v0[i + 3]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(gp + 16 + i, v1[i]);
+          for (int i = 0; i < 16; i += 4) red_add_v4(gp + 16 + i, v1[i], v1[i + 1], v1[i + 2], v1[i + 3]);
         }
       }
     }

@@ -208,7 +208,7 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams P) {
       tmem_ld16(t_lane + c * 16, v);
       if (!valid) continue;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) atomicAdd(gp + c * 16 + i, v[i]);
+      for (int i = 0; i < 16; i += 4) red_add_v4(gp + c * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
   }
   tc_fence_before();
