@@ -206,7 +206,11 @@ int rowsum_enqueue(const float* in, float* out, int B, int C, int ld, int accumu
 // G -> nn.Conv3d weight-gradient layout
 // =============================================================================================
 __device__ __forceinline__ void unpack_wgrad_body(int fwd_mode, const float* __restrict__ G, float* __restrict__ dw,
-                                                  float* __restrict__ dwx, int cout, int cin, int cinx, int perm) {
+                                                  float* __restrict__ dwx, int cout, int cin_arg, int cinx, int perm) {
+  // cin_arg = cin | (cin_g << 16): cin_g = channels per tap of G when it is wider than the weight (the first conv's packed
+  // 32-channel operand), 0 = the same
+  const int cin = cin_arg & 0xffff;
+  const int cin_g = (cin_arg >> 16) ? (cin_arg >> 16) : cin;
   const int taps = (fwd_mode == 3) ? 1 : 27;
   const size_t n_main = (size_t)cout * cin * taps;
   const size_t total = n_main + (size_t)cout * cinx;
@@ -230,7 +234,7 @@ __device__ __forceinline__ void unpack_wgrad_body(int fwd_mode, const float* __r
       if (perm) { td = st % 3; tw = (st / 3) % 3; th = st / 9; }
       else { tw = st % 3; th = (st / 3) % 3; td = st / 9; }
       if (fwd_mode != 2) {
-        v = G[((size_t)((td * 3 + th) * 3 + tw) * cin + ci) * cout + co];
+        v = G[((size_t)((td * 3 + th) * 3 + tw) * cin_g + ci) * cout + co];
       } else {
         // fold the 8 phases x 8 taps: original tap k of one dim lives in (p, a) pairs
         //   k=0: (0,0),(1,0)   k=1: (0,1),(1,0)   k=2: (0,1),(1,1)

@@ -112,6 +112,9 @@ struct cm_unet {
   size_t first_wpack_off = 0;
   PlaneLaunch first_plane;
   Res32Launch first_res;
+  WgradPlaneLaunch first_wpl;          // first conv's weight gradient through the plane / halo kernel (base_channels == 32)
+  size_t first_g_off = 0;              // its packed-K scratch (27 taps x 32 packed channels x 32) and channel-sum slot
+  int first_colsum_off = 0;
   // device state
   __half* wpack = nullptr;
   size_t wpack_elems = 0;
@@ -384,6 +387,10 @@ int build_plan(cm_unet* u) {
   first.out = u->add_tensor(0, base);
   u->tens[first.out].need32 = true;
   u->ops.push_back(first);
+  u->first_g_off = u->g_elems;
+  u->g_elems += (size_t)27 * 32 * base;
+  u->first_colsum_off = u->colsum_per_sample;
+  u->colsum_per_sample += base;
 
   int cur = first.out;
   std::vector<int> skips{cur};
@@ -883,7 +890,7 @@ int reserve_train(cm_unet* u, int batch) {
   std::vector<size_t> o32(u->tens.size()), o16(u->tens.size(), (size_t)-1);
   std::vector<char> is_conv_out(u->tens.size(), 0);
   for (const Op& op : u->ops)
-    if (op.type == OP_CONV) is_conv_out[op.out] = 1;
+    if (op.type == OP_CONV || op.type == OP_FIRST) is_conv_out[op.out] = 1;
   for (size_t i = 0; i < u->tens.size(); ++i) {
     const Tens& t = u->tens[i];
     const size_t n = (size_t)batch * u->levels[t.level].pps() * t.C;
@@ -1092,6 +1099,16 @@ int prepare_train(cm_unet* u, int batch) {
       if (ok) op.n_wpl = nc;
     }
   }
+  // first conv: its operand is the packed fp16 input [pixels][32 (x live_dup)] of the forward (channels >= in_channels are
+  // zero), so its weight gradient is one plane launch over the hi halves like any other 32 -> 32 layer
+  u->first_wpl.ok = false;
+  if (u->first_plane.ok && u->cfg.base_channels == 32 && getenv("CM_FIRST_WGRAD_SIMT") == nullptr) {
+    const Level& l0 = u->levels[0];
+    const int out = u->ops[0].out;
+    if (int rc = wgrad_plane_prepare(&u->first_wpl, u->tens[u->first_in].p16, batch, l0.D, l0.H, l0.W, 32, u->live_dup * 32, 0,
+                                     u->g16[out], u->dgrad_dup * 32, 32, u->G + u->first_g_off))
+      return rc;
+  }
   u->train_prepared = batch;
   return 0;
 }
@@ -1271,10 +1288,26 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
       } break;
       case OP_FIRST: {
         CM_CHECK(written[op.out], "backward: gradient of the first conv output missing");
-        if (int e = first_conv_wgrad_enqueue(u->live_future, u->live_past, u->g32[op.out], gp(u->p_first_w),
-                                             gp(u->p_first_b), B, l0.H, l0.W, c.past_len, c.future_len,
-                                             c.in_channels, c.base_channels, st))
+        if (u->first_wpl.ok) {
+          float* cs = u->colsum + (size_t)B * u->first_colsum_off;
+          if (int e = cast_colsum_enqueue(u->g32[op.out], u->g16[op.out], u->dgrad_dup, nullptr, 0, cs, c.base_channels, B,
+                                          l0.pps(), c.base_channels, st))
+            return e;
+          rs_tab.push_back((long long)(cs - reinterpret_cast<const float*>(u->tarena)));
+          rs_tab.push_back((long long)c.base_channels);
+          rs_tab.push_back((long long)c.base_channels);
+          rs_tab.push_back((long long)u->grad_off[u->p_first_b]);
+          if (int e = wgrad_plane_enqueue(u->first_wpl, st)) return e;
+          // G rows are (tap, 32 packed channels): cin of G in the upper half of the cin entry
+          for (long long v : {0LL, (long long)u->first_g_off, (long long)u->grad_off[u->p_first_w], -1LL,
+                              (long long)c.base_channels, (long long)c.in_channels | (32LL << 16), 0LL, 1LL})
+            up_tab.push_back(v);
+          ++nl;
+        } else if (int e = first_conv_wgrad_enqueue(u->live_future, u->live_past, u->g32[op.out], gp(u->p_first_w),
+                                                    gp(u->p_first_b), B, l0.H, l0.W, c.past_len, c.future_len,
+                                                    c.in_channels, c.base_channels, st)) {
           return e;
+        }
         ++nl;
         mark("first_wgrad " + op.tag);
       } break;
