@@ -206,14 +206,17 @@ int rowsum_enqueue(const float* in, float* out, int B, int C, int ld, int accumu
 // G -> nn.Conv3d weight-gradient layout
 // =============================================================================================
 __device__ __forceinline__ void unpack_wgrad_body(int fwd_mode, const float* __restrict__ G, float* __restrict__ dw,
-                                                  float* __restrict__ dwx, int cout, int cin_arg, int cinx, int perm) {
+                                                  float* __restrict__ dwx, int cout_arg, int cin_arg, int cinx, int perm) {
+  // cout_arg = cout | (cout_g << 16) likewise: columns per row of G (the final conv's d_eps packed into 32 columns)
+  const int cout_w = cout_arg & 0xffff;
+  const int cout = (cout_arg >> 16) ? (cout_arg >> 16) : cout_w;
   // cin_arg = cin | (cin_g << 16): cin_g = channels per tap of G when it is wider than the weight (the first conv's packed
   // 32-channel operand), 0 = the same
   const int cin = cin_arg & 0xffff;
   const int cin_g = (cin_arg >> 16) ? (cin_arg >> 16) : cin;
   const int taps = (fwd_mode == 3) ? 1 : 27;
-  const size_t n_main = (size_t)cout * cin * taps;
-  const size_t total = n_main + (size_t)cout * cinx;
+  const size_t n_main = (size_t)cout_w * cin * taps;
+  const size_t total = n_main + (size_t)cout_w * cinx;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     if (idx >= n_main) {
@@ -871,9 +874,59 @@ final_conv_wgrad_kernel(const float* __restrict__ deps, const float* __restrict_
   }
 }
 
+// d_eps * scale -> columns 0 .. cout-1 of the fp16 dOut operand [B][L][H][W][32] of the plane weight-gradient kernel (future
+// frames only; everything else in the buffer stays zero) and the bias gradient (block sums, one atomic per CTA and channel)
+__global__ void __launch_bounds__(256)
+pack_final_dout_kernel(const float* __restrict__ deps, const float* __restrict__ scale_dev, __half* __restrict__ out,
+                       float* __restrict__ db, int B, int H, int W, int L, int P, int cout) {
+  __shared__ float red[8][4];
+  const float scale = scale_dev ? scale_dev[0] : 1.f;
+  const int F = L - P;
+  const size_t total = (size_t)B * F * H * W;
+  const size_t plane = (size_t)H * W * F;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wc = (int)(i % W);
+    size_t r = i / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int f = (int)(r % F);
+    const int b = (int)(r / F);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = 0; co < cout; ++co) {
+      v[co] = deps[((size_t)b * cout + co) * plane + ((size_t)h * W + wc) * F + f] * scale;
+      s[co] += v[co];
+    }
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h0);
+    u.y = *reinterpret_cast<const uint32_t*>(&h1);
+    const size_t pix = (((size_t)b * L + P + f) * H + h) * W + wc;
+    *reinterpret_cast<uint2*>(out + pix * 32) = u;
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[co] += __shfl_xor_sync(0xffffffffu, s[co], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int co = 0; co < 4; ++co) red[warp][co] = s[co];
+  }
+  __syncthreads();
+  if (threadIdx.x < cout) {
+    float a = 0.f;
+    for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+    atomicAdd(db + threadIdx.x, a);
+  }
+}
+
+// dout16 != nullptr: the weight gradient is left to the caller's plane launch over dout16 (filled here, with the bias
+// gradient); nullptr: the SIMT weight-gradient kernel
 int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act, int act_ld, int act_lo,
                                 const float* w, float* dact, float* dw, float* db, int B, int H, int W,
-                                int L, int P, int cin, int cout, cudaStream_t st) {
+                                int L, int P, int cin, int cout, __half* dout16, cudaStream_t st) {
   const int ald = act_ld > 0 ? act_ld : cin;
   CM_CHECK(cout >= 1 && cout <= 4, "final conv supports 1..4 output channels (got %d)", cout);
   CM_CHECK(cin % 32 == 0 && 27 * cin <= 2048, "final conv backward: cin must be a multiple of 32, <= 64");
@@ -886,7 +939,10 @@ int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const
 #define CM_FB(CO)                                                                                   \
   case CO:                                                                                          \
     final_conv_dact_kernel<CO><<<blocks, 256, smem, st>>>(deps, scale_dev, w, dact, B, H, W, L, P, cin); \
-    final_conv_wgrad_kernel<CO><<<wblocks, 256, 0, st>>>(deps, scale_dev, act, ald, act_lo, dw, db, B, H, W, L, P, cin, ppc); \
+    if (dout16)                                                                                     \
+      pack_final_dout_kernel<<<592, 256, 0, st>>>(deps, scale_dev, dout16, db, B, H, W, L, P, cout); \
+    else                                                                                            \
+      final_conv_wgrad_kernel<CO><<<wblocks, 256, 0, st>>>(deps, scale_dev, act, ald, act_lo, dw, db, B, H, W, L, P, cin, ppc); \
     break;
   switch (cout) { CM_FB(1) CM_FB(2) CM_FB(3) CM_FB(4) }
 #undef CM_FB

@@ -86,7 +86,7 @@ int attn_core_backward_enqueue(const float* qkv, const float* dctx, float* dqkv,
 // act: fp16 [B][L][H][W][act_ld] (act_ld 0 -> cin); act_lo > 0: hi|lo pair rows, the lo half is added
 int final_conv_backward_enqueue(const float* deps, const float* scale_dev, const __half* act, int act_ld, int act_lo,
                                 const float* w, float* dact, float* dw, float* db, int B, int H, int W,
-                                int L, int P, int cin, int cout, cudaStream_t st);
+                                int L, int P, int cin, int cout, __half* dout16, cudaStream_t st);
 // ---- first conv weight / bias gradient (unet.py:32; inputs need no gradient) ----
 // dout fp32 [B][L][H][W][cout]; dw [cout][cin][27], db [cout] accumulated with atomics.
 int first_conv_wgrad_enqueue(const float* x, const float* past, const float* dout, float* dw, float* db,

@@ -115,6 +115,9 @@ struct cm_unet {
   WgradPlaneLaunch first_wpl;          // first conv's weight gradient through the plane / halo kernel (base_channels == 32)
   size_t first_g_off = 0;              // its packed-K scratch (27 taps x 32 packed channels x 32) and channel-sum slot
   int first_colsum_off = 0;
+  WgradPlaneLaunch final_wpl;          // final conv's weight gradient the same way: d_eps packed into 32 fp16 columns
+  size_t final_g_off = 0;
+  __half* final_d16 = nullptr;         // [B * L * H * W][32]: columns >= out_channels and past frames stay zero
   // device state
   __half* wpack = nullptr;
   size_t wpack_elems = 0;
@@ -441,6 +444,8 @@ int build_plan(cm_unet* u) {
   fin.in = afin;
   fin.cin = in_ch;
   u->ops.push_back(fin);
+  u->final_g_off = u->g_elems;
+  u->g_elems += (size_t)27 * 32 * 32;
 
   // algorithmic FLOPs per sample of the reference graph (dense formulation: 27-tap upsample
   // convs, separate 1x1 match_input, attention), SURVEY.md §8(d)
@@ -910,6 +915,7 @@ int reserve_train(cm_unet* u, int batch) {
   size_t o_t[8];
   for (int k = 0; k < 8; ++k) o_t[k] = take((size_t)batch * E * 4);
   const size_t o_scale = take(16);
+  const size_t o_fd16 = take((size_t)batch * u->levels[0].pps() * 32 * 2);
   CM_CUDA(cudaMalloc(&u->tarena, off));
   CM_CUDA(cudaMemset(u->tarena, 0, off));
   u->tarena_bytes = off;
@@ -932,6 +938,7 @@ int reserve_train(cm_unet* u, int batch) {
   float** tp[8] = {&u->tsave_h1, &u->tsave_h2, &u->ts1, &u->ts2, &u->tds2, &u->tdh2, &u->tds1, &u->tdh1};
   for (int k = 0; k < 8; ++k) *tp[k] = reinterpret_cast<float*>(u->tarena + o_t[k]);
   u->loss_scale = reinterpret_cast<float*>(u->tarena + o_scale);
+  u->final_d16 = reinterpret_cast<__half*>(u->tarena + o_fd16);
   u->train_reserved = batch;
   return 0;
 }
@@ -1109,6 +1116,14 @@ int prepare_train(cm_unet* u, int batch) {
                                      u->g16[out], u->dgrad_dup * 32, 32, u->G + u->first_g_off))
       return rc;
   }
+  u->final_wpl.ok = false;
+  if (u->ops.back().type == OP_FINAL && u->ops.back().cin == 32 && getenv("CM_FINAL_WGRAD_SIMT") == nullptr) {
+    const Level& l0 = u->levels[0];
+    const Op& fo = u->ops.back();
+    if (int rc = wgrad_plane_prepare(&u->final_wpl, u->tens[fo.in].p16, batch, l0.D, l0.H, l0.W, 32, u->live_dup * 32, 0,
+                                     u->final_d16, 32, 32, u->G + u->final_g_off))
+      return rc;
+  }
   u->train_prepared = batch;
   return 0;
 }
@@ -1169,8 +1184,16 @@ int run_backward(cm_unet* u, const float* d_eps, float* grads, cudaStream_t st, 
         if (int e = final_conv_backward_enqueue(d_eps, u->loss_scale, u->tens[op.in].p16, u->live_dup * op.cin,
                                                 u->live_dup == 2 ? op.cin : 0, u->params[u->p_final_w].ptr, u->g32[op.in], gp(u->p_final_w),
                                                 gp(u->p_final_b), B, l0.H, l0.W, l0.D, c.past_len, op.cin,
-                                                c.out_channels, st))
+                                                c.out_channels, u->final_wpl.ok ? u->final_d16 : nullptr, st))
           return e;
+        if (u->final_wpl.ok) {
+          if (int e = wgrad_plane_enqueue(u->final_wpl, st)) return e;
+          // G is (tap, 32 channels) x 32 packed columns: G's cout in the upper half of the cout entry
+          for (long long v : {0LL, (long long)u->final_g_off, (long long)u->grad_off[u->p_final_w], -1LL,
+                              (long long)c.out_channels | (32LL << 16), (long long)op.cin, 0LL, 1LL})
+            up_tab.push_back(v);
+          ++nl;
+        }
         written[op.in] = 1;
         nl += 2;
         mark("final_bwd " + op.tag);
