@@ -57,6 +57,7 @@ struct PlaneParams {
   int dbg;               // bring-up knobs (CM_PLANE_DBG): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
   const float* bias;
   const float* bias2;
+  int lo_from, lo_from_x;   // as ConvParams: k16 slices of lo-half channels skip the lo weight term
   const float* temb;
   const int* t_dev;
   int temb_ld, temb_bstride;
@@ -245,8 +246,11 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
     uint32_t ph = 0;
     int it = 0;
     bool alive = true;
+    const int lo_from = P.lo_from > 0 ? P.lo_from : 0x40000000;
+    const int lo_from_x = P.lo_from_x > 0 ? P.lo_from_x : 0x40000000;
     for (int u = blockIdx.x; u < P.n_units && alive; u += gridDim.x, ++it) {
       const int buf = it & 1;
+      int cc = 0;
       // wait until the epilogue has drained this accumulator buffer (first two units: free)
       if (it >= 2 && !mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1, P.err_flag, 404)) break;
       tc_fence_after();
@@ -256,6 +260,8 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
         if (!mbar_wait(&full_bar[s], ph, P.err_flag, 402)) { alive = false; break; }
         PL_TRACE(1, 4);
         tc_fence_after();
+        const int rel = ks < nks_main ? cc * BK - lo_from : (ks - nks_main) * BK - lo_from_x;
+        if (++cc == ncm) cc = 0;
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t a_lo0 = kmajor_desc_lo(a_addr);
@@ -270,6 +276,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
                 for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
                   for (int t = 0; t < TERMS; ++t) {
+                    if (t == 1 && rel + k * 16 >= 0) continue;          // lo activation half x lo weight term: skipped
                     const uint32_t b_lo = b_lo0 + ((t * b_term + th * 3 * B_TAP) >> 4) + 2 * k;
                     uint32_t a_lo = a_lo0 + th * th_step + 2 * k;
                     uint32_t d = d_base;
@@ -288,6 +295,7 @@ conv_plane_kernel(const __grid_constant__ PlaneParams P) {
               for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
                 for (int t = 0; t < TERMS; ++t) {
+                  if (t == 1 && rel + k * 16 >= 0) continue;
                   const uint32_t b_lo = b_lo0 + ((t * b_term + B_TAP) >> 4) + 2 * k;
                   uint32_t a_lo = a_lo0 + 2 * k;
                   uint32_t d = d_base + BN;

@@ -42,6 +42,8 @@ struct ConvParams {
   int cin_main, cin_extra;
   int kphase;            // packed-K elements per phase
   int terms;             // 1 = fp16 weights, 2 = hi+lo split weights
+  int lo_from, lo_from_x;   // > 0: channels >= lo_from of the main (lo_from_x: the 1x1x1) source are the lo halves of hi|lo
+                            // operand pairs (training): their k16 slices skip the lo weight term (a_lo * w_lo ~ 2^-22)
   int cout;
   int stages;
   const float* bias;
@@ -87,6 +89,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
   // the narrow layers; the epilogue adds the two halves.
   constexpr int NST = BN * TERMS;
   constexpr uint32_t IDESC = make_idesc_f16(CONV_BM, NST);
+  constexpr uint32_t IDESC_HI = make_idesc_f16(CONV_BM, BN);   // hi weight term only (the first BN rows of the B tile)
   constexpr uint32_t TMEM_COLS = NST < 32 ? 32 : NST;
 
   extern __shared__ uint8_t smem_raw[];
@@ -206,6 +209,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
     // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====
     {
       constexpr uint32_t DESC_HI = kmajor_desc_hi(ROWB);
+      const int lo_from = P.lo_from > 0 ? P.lo_from : 0x40000000;
+      const int lo_from_x = P.lo_from_x > 0 ? P.lo_from_x : 0x40000000;
       const uint32_t lo0 = kmajor_desc_lo(smem_u32(smem));
       const uint32_t lo_stage = static_cast<uint32_t>(stage_bytes) >> 4;
       int s = 0;
@@ -217,16 +222,20 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         tc_fence_after();
         acc = 0;
       }
+      int cc = (kb_lo > 0 && kb_lo < nkb_main) ? kb_lo % ncm : 0;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         if (!mbar_wait(&full_bar[s], ph, P.err_flag, 102)) { alive = false; break; }
         tc_fence_after();
+        // first channel of this k-block relative to where the lo halves of the operand pairs start
+        const int rel = kb < nkb_main ? cc * BK - lo_from : (kb - nkb_main) * BK - lo_from_x;
         if (elect_one()) {
           if (tr && kb < 120) P.trace[8 + kb * 4 + 2] = gtime_ns();
           const uint32_t a_lo = lo0 + s * lo_stage;
           if (!(P.dbg & 4)) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              umma_f16_lohi(tmem_base, a_lo + 2 * k, a_lo + (A_BYTES >> 4) + 2 * k, DESC_HI, IDESC, acc);
+              const uint32_t idesc = (TERMS == 2 && acc && rel + k * 16 >= 0) ? IDESC_HI : IDESC;
+              umma_f16_lohi(tmem_base, a_lo + 2 * k, a_lo + (A_BYTES >> 4) + 2 * k, DESC_HI, idesc, acc);
               acc = 1;
             }
           }
@@ -234,6 +243,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
           else umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs retire
           if (tr && kb < 120) P.trace[8 + kb * 4 + 3] = gtime_ns();
         }
+        if (++cc == ncm) cc = 0;
         if (++s == S) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(tmem_full);       // accumulator of this phase complete

@@ -546,6 +546,12 @@ int reserve(cm_unet* u, int batch) {
   return 0;
 }
 
+// hi|lo operand pairs against hi+lo weight terms: the lo x lo product (2^-22 of the result) is skipped unless CM_KEEP_LOLO is set
+static bool keep_lolo() {
+  static const bool k = getenv("CM_KEEP_LOLO") != nullptr;
+  return k;
+}
+
 // conv launches depend on the live batch (grid, tensor-map extents): (re)built per call batch
 // dup = 1: single fp16 activation operands (sampling / eval); dup = 2: hi|lo pair rows (training forward)
 int prepare_convs(cm_unet* u, int batch, int dup) {
@@ -561,6 +567,7 @@ int prepare_convs(cm_unet* u, int batch, int dup) {
                                  (u->fullres_terms > 0 && dup == 1) ? u->fullres_terms : u->cfg.weight_terms))
         return rc;
       if (u->first_plane.ok) {
+        u->first_plane.p.lo_from = (dup == 2 && !keep_lolo()) ? 32 : 0;
         u->first_plane.p.bias = u->params[u->p_first_b].ptr;
         u->first_plane.p.out32 = nullptr;   // set per run (tensor of the OP_FIRST op)
       }
@@ -600,6 +607,9 @@ int prepare_convs(cm_unet* u, int batch, int dup) {
     if (int rc = conv_prepare(&op.launch, op.mode, tin.p16, batch, li.D, li.H, li.W, op.cin * dup, extra,
                               op.cin_extra * dup, wp, op.cout, terms))
       return rc;
+    const bool skip_lolo = dup == 2 && !keep_lolo();
+    op.launch.p.lo_from = skip_lolo ? op.cin : 0;
+    op.launch.p.lo_from_x = skip_lolo ? op.cin_extra : 0;
     op.plaunch.ok = false;
     static const bool no_plane = getenv("CM_NO_PLANE") != nullptr;
     if (op.mode == 0 && !no_plane) {
@@ -608,6 +618,8 @@ int prepare_convs(cm_unet* u, int batch, int dup) {
         return rc;
       if (op.plaunch.ok) {
         PlaneParams& q = op.plaunch.p;
+        q.lo_from = skip_lolo ? op.cin : 0;
+        q.lo_from_x = skip_lolo ? op.cin_extra : 0;
         q.bias = op.bias >= 0 ? u->params[op.bias].ptr : nullptr;
         q.bias2 = op.bias2 >= 0 ? u->params[op.bias2].ptr : nullptr;
         q.resid = op.resid >= 0 ? u->tens[op.resid].p32 : nullptr;
@@ -1068,18 +1080,23 @@ int prepare_train(cm_unet* u, int batch) {
                               dup * op.cout, nullptr, 0, u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
       return rc;
     op.dlaunch.p.out32 = u->g32[op.in];
+    op.dlaunch.p.lo_from = (dup == 2 && !keep_lolo()) ? op.cout : 0;
     op.dplaunch.ok = false;
     if (op.mode == 0 && getenv("CM_NO_PLANE") == nullptr) {
       if (int rc = plane_prepare(&op.dplaunch, u->g16[op.out], batch, lo.D, lo.H, lo.W, dup * op.cout, nullptr, 0,
                                  u->dpack + op.dpack_off, op.cin, u->cfg.weight_terms))
         return rc;
-      if (op.dplaunch.ok) op.dplaunch.p.out32 = u->g32[op.in];
+      if (op.dplaunch.ok) {
+        op.dplaunch.p.out32 = u->g32[op.in];
+        op.dplaunch.p.lo_from = (dup == 2 && !keep_lolo()) ? op.cout : 0;
+      }
     }
     if (op.cin_extra) {
       if (int rc = conv_prepare(&op.dxlaunch, 3, u->g16[op.out], batch, lo.D, lo.H, lo.W, dup * op.cout, nullptr, 0,
                                 u->dpack + op.dxpack_off, op.cin_extra, u->cfg.weight_terms))
         return rc;
       op.dxlaunch.p.out32 = u->g32[op.extra];
+      op.dxlaunch.p.lo_from = (dup == 2 && !keep_lolo()) ? op.cout : 0;
     }
     const __half* extra = op.extra >= 0 ? u->tens[op.extra].p16 : nullptr;
     // activations / the 1x1 source: the hi halves of the forward's (hi|lo pair) rows
