@@ -404,7 +404,16 @@ int plane_prepare(PlaneLaunch* L, const __half* act, int B, int D, int H, int W,
     const long waves = (units + n_sm - 1) / n_sm;
     const double eff = (double)R * HB * W / (ntiles * 128.0);
     if (eff < 0.6) return;                               // mostly padding: leave it to conv_umma
-    const double score = eff * ((double)units / (waves * n_sm));
+    // useful rows per modelled CTA time: a unit costs its MMAs (~55 cycles each, tw taps stacked along N) plus a fixed
+    // ~2 600 cycles and ~310 cycles per pipeline stage whatever it computes (knock-out skeleton runs, DESIGN.md 3.1.5 and
+    // tools/dgrad_knock.py: 2.3 us per unit on the HERMES grid) -- fewer, fatter units win when the rows-per-tile efficiency
+    // is close.  unit_cost = 0 (CM_PLANE_OLD_SCORE) is the round-1 score eff x fill.
+    static const bool old_score = getenv("CM_PLANE_OLD_SCORE") != nullptr;
+    const double bk_model = R == 1 ? 32.0 : (double)bk;   // th3 stages (single-plane units) use BK = 32
+    const double mma_tile = 55.0 * (9.0 * (cin / 16) + (cin_extra / 16)) * terms;
+    const double stages = (R == 1 ? 3.0 : 9.0) * (cin / bk_model) + cin_extra / bk_model;
+    const double unit_cost = old_score ? 0.0 : 2600.0 + 310.0 * stages;
+    const double score = eff * ((double)units / (waves * n_sm)) * (ntiles * mma_tile) / (ntiles * mma_tile + unit_cost);
     if (score > best * 1.0001 || (score > best * 0.9999 && R * HB > bestR * bestHB)) {
       best = score;
       bestR = R;
