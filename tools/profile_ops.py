@@ -1,5 +1,5 @@
 """Per-op device times of one denoiser step (CUDA events around every launch) at the bench batch.
-usage: python tools/profile_ops.py [batch] [out.json]"""
+usage: [WORKLOAD=atc|atc_medium|ethucy|hermes] python tools/profile_ops.py [batch] [out.json]"""
 import ctypes as C
 import json
 import os
@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import ATC, ROWS, COLS, PAST, FUT, synthetic_macroprops  # noqa: E402
+from bench import WORKLOADS, synthetic_macroprops  # noqa: E402
 from crowdmod_ddpm_4d_b200 import _native as nat  # noqa: E402
 from crowdmod_ddpm_4d_b200.models.backbones.unet import UNet  # noqa: E402
 
@@ -18,6 +18,8 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     out = sys.argv[2] if len(sys.argv) > 2 else None
     reps = int(os.environ.get("REPS", "5"))
+    wl = WORKLOADS[os.environ.get("WORKLOAD", "atc")]
+    ATC, ROWS, COLS, PAST, FUT = wl["unet"], wl["rows"], wl["cols"], wl["past"], wl["fut"]
     dev = torch.device("cuda", 0)
     torch.manual_seed(42)
     net = UNet(**ATC).to(dev).eval()
