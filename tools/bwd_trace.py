@@ -14,8 +14,12 @@ n, R, Cc = 64, 28, 24
 past = synthetic_macroprops(n, 3, R, Cc, 5, 1, dev); fut = synthetic_macroprops(n, 3, R, Cc, 3, 2, dev)
 t = torch.randint(0, 1000, (n,), device=dev)
 for i in range(3):
-    if i == 2: print("=== measured pass", file=sys.stderr, flush=True)
+    if i == 2:
+        print("=== measured pass", file=sys.stderr, flush=True)
+        if os.environ.get("PROFILE_API"):      # ncu --profile-from-start off: the third step only (forward + backward)
+            torch.cuda.synchronize(); torch.cuda.profiler.start()
     loss = F.mse_loss(net(fut, t, past), torch.randn_like(fut))
     net.zero_grad(set_to_none=True)
     loss.backward()
 torch.cuda.synchronize()
+if os.environ.get("PROFILE_API"): torch.cuda.profiler.stop()
