@@ -295,6 +295,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 256-bit global stores (STG.E.256, sm_100+; p 32-byte aligned): a row-per-thread epilogue moves a full 32-byte sector per
+// instruction instead of half of one
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* u) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+
 // four consecutive fp32 adds into global memory as ONE reduction (REDG.E.ADD.F32x4, sm_90+; p 16-byte aligned): a quarter of
 // the L2 atomic operations of four scalar atomicAdd() calls
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {

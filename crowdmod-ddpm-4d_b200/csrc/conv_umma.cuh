@@ -381,40 +381,26 @@ conv_umma_kernel(const __grid_constant__ ConvParams P) {
         }
       }
       const int n = n_tile * BN + c * 16;
+      // row-per-thread stores: 32 bytes (one sector) per instruction (256-bit stores; every row start and n are multiples
+      // of 16 elements, so fp32 chunks are 64-byte and fp16 chunks 32-byte aligned)
       if (P.out32) {
         float* op = P.out32 + orow * P.out_ld + n;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        st_global_v8(op, v);
+        st_global_v8(op + 8, v + 8);
       }
       if (P.out16) {
         __half* op = P.out16 + orow * (P.out16_ld > 0 ? P.out16_ld : P.out_ld) + n;
+        uint32_t uh[8], ul[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 8) {
-          __half2 h0 = __floats2half2_rn(v[i], v[i + 1]);
-          __half2 h1 = __floats2half2_rn(v[i + 2], v[i + 3]);
-          __half2 h2 = __floats2half2_rn(v[i + 4], v[i + 5]);
-          __half2 h3 = __floats2half2_rn(v[i + 6], v[i + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(op + i) = u;
-          if (P.out16_lo > 0) {
-            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2),
-                         f3 = __half22float2(h3);
-            __half2 l0 = __floats2half2_rn(v[i] - f0.x, v[i + 1] - f0.y);
-            __half2 l1 = __floats2half2_rn(v[i + 2] - f1.x, v[i + 3] - f1.y);
-            __half2 l2 = __floats2half2_rn(v[i + 4] - f2.x, v[i + 5] - f2.y);
-            __half2 l3 = __floats2half2_rn(v[i + 6] - f3.x, v[i + 7] - f3.y);
-            u.x = *reinterpret_cast<uint32_t*>(&l0);
-            u.y = *reinterpret_cast<uint32_t*>(&l1);
-            u.z = *reinterpret_cast<uint32_t*>(&l2);
-            u.w = *reinterpret_cast<uint32_t*>(&l3);
-            *reinterpret_cast<uint4*>(op + P.out16_lo + i) = u;
-          }
+        for (int i = 0; i < 8; ++i) {
+          const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+          uh[i] = *reinterpret_cast<const uint32_t*>(&h);
+          const float2 f = __half22float2(h);
+          const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+          ul[i] = *reinterpret_cast<const uint32_t*>(&l);
         }
+        st_global_v8(op, uh);
+        if (P.out16_lo > 0) st_global_v8(op + P.out16_lo, ul);
       }
     }
     if (pi + 1 < ppc) {          // hand the accumulator back to the MMA warp for the next phase
