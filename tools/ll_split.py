@@ -1,3 +1,6 @@
+"""Per-kernel totals of one training step's ncu launch list, split into forward and backward at the first backward-only kernel.
+usage: PROFILE_API=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file L.csv \
+           python tools/bwd_trace.py; python tools/ll_split.py L.csv"""
 import csv, collections, sys
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>10 and r[0].isdigit()]
 # split forward / backward at the first backward-only kernel
